@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py — BEV frames/s of the batch_multi_bev_gen hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (C-ABI, libbevgen_cuda.so)
+  python bench.py --impl reference ...                     the reference algorithm on the host cores (CPU oracle port)
+
+A "step" = one pass of the hot path (getOrderedCloud + markGroundPoints + single & multi BEV,
+BatchMultiBevGen.cpp:735-747, no file encoders) over one batch of synthetic HDL_64E keyframes (BASELINE configs[1]).
+  value : frames/s with the batch already resident in HBM (bevgen_process_device), CUDA events on the compute stream
+  e2e   : frames/s through bevgen_process_host with pinned HOST buffers, H2D and D2H inside the timed region
+  roofline : dominant kernel, algorithmic bytes per launch / its mean launch duration (CUDA events in the library)
+  cpu_baseline : the oracle on the box's host cores, bounded sample, rank 0 / N=1 only
+Multi-GPU: frames shard by index, one process per GPU, no data-path collective ("weak" scaling: F frames per rank);
+torch.distributed is only used for the barrier and the max-over-ranks of the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from _load_pkg import load_pkg, load_synth, load_oracle  # noqa: E402
+
+FIELDS = ("x", "y", "z", "intensity", "row", "col", "label")
+METRIC = "BEV frames/sec (HDL-64E)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sensor", default="HDL_64E")
+    ap.add_argument("--frames", type=int, default=1024, help="frames resident per GPU per step (device path)")
+    ap.add_argument("--e2e-frames", type=int, default=256, help="frames per step of the host-buffer (e2e) path")
+    ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic frames generated, then tiled")
+    ap.add_argument("--wave", type=int, default=int(os.environ.get("BEVGEN_WAVE", "296")), help="frames per launch wave")
+    ap.add_argument("--ref-frames", type=int, default=0, help="reference arm: frames per step (0 = 4 per host thread)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def tile_batch(distinct, F):
+    """Tile the distinct frames to F frames (concatenated SoA + offsets)."""
+    offs_d = distinct["offsets"]
+    D = len(offs_d) - 1
+    order = [i % D for i in range(F)]
+    lens = np.array([offs_d[i + 1] - offs_d[i] for i in order], np.int64)
+    offs = np.zeros(F + 1, np.int64); offs[1:] = np.cumsum(lens)
+    out = {}
+    for k in FIELDS:
+        out[k] = np.concatenate([distinct[k][offs_d[i]:offs_d[i + 1]] for i in order])
+    out["offsets"] = offs
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev, self.rows, self.stop_ev = dev, [], threading.Event()
+
+    def run(self):
+        while not self.stop_ev.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            self.stop_ev.wait(0.2)
+
+    def summary(self):
+        self.stop_ev.set(); self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][2]) if self.rows[0][2].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def algorithmic_bytes(sensor_S, n_in_total, F):
+    # n_in*22 [x,y,z,intensity f32 + row,col u16 + label i16] + S*2 [labels] + 50176 [single] + 1204224 [multi]
+    return n_in_total * 22 + F * (sensor_S * 2 + 50176 + 1204224)
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference algorithm (CPU oracle port — the reference itself needs PCL/OpenCV/VTK and cannot
+    be built here) on all host threads, bounded sample of the same workload.  Rank 0 only."""
+    if rank != 0:
+        return
+    O, synth = load_oracle(), load_synth()
+    cores = os.cpu_count() or 1
+    F = args.ref_frames or 4 * cores
+    distinct = synth.make_batch(args.sensor, min(args.distinct, F))
+    batch = tile_batch(distinct, F)
+    sp = O.sensor(args.sensor)
+    call = lambda: O.frames(sp, batch["offsets"], *[batch[k] for k in FIELDS], n_threads=cores)
+    for _ in range(min(args.warmup, 1)):
+        call()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        call()
+    dt = time.perf_counter() - t0
+    v = F * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s synthetic keyframes, hot loop BatchMultiBevGen.cpp:735-747 without file encoders" % args.sensor,
+                       "frames_per_step": F, "sensor": args.sensor},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": "%d frames/step x %d steps, %d threads (one frame per thread at a time)" % (F, args.steps, cores)},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    pkg, synth = load_pkg(), load_synth()
+    F, Fe = args.frames, args.e2e_frames
+    distinct = synth.make_batch(args.sensor, args.distinct, first=1000 * rank)   # each rank its own shard of keyframes
+    g = pkg.BevGen(args.sensor, device=local, max_frames_per_batch=args.wave)
+    S = g.S
+
+    # ---- device-resident batch (value) ------------------------------------------------------------------------
+    batch = tile_batch(distinct, F)
+    n_total = int(batch["offsets"][-1])
+    din = {k: torch.from_numpy(batch[k]).to(dev) for k in FIELDS}
+    dout = dict(label=torch.empty((F, S), dtype=torch.int16, device=dev), owner=torch.empty((F, S), dtype=torch.int32, device=dev),
+                single=torch.empty((F, 224 * 224), dtype=torch.uint8, device=dev),
+                multi=torch.empty((F, 24 * 224 * 224), dtype=torch.uint8, device=dev))
+    pin, pout = {k: v.data_ptr() for k, v in din.items()}, {k: v.data_ptr() for k, v in dout.items()}
+    in_bytes = sum(v.numel() * v.element_size() for v in din.values())
+    stream = torch.cuda.ExternalStream(g.compute_stream(), device=dev)
+    step = lambda: g.process_device(F, batch["offsets"], pin, pout)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, on_stream):
+        """EXACTLY `steps` calls bracketed by barrier + synchronize; CUDA events on the launching stream; max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(on_stream)
+        for _ in range(steps):
+            fn()
+        e1.record(on_stream)
+        g.sync(); torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([ms, wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    g.sync()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = g.kernel_launches()
+    ms, wall_ms = timed(step, args.steps, stream)
+    launches = g.kernel_launches() - l0
+    clocks = sampler.summary()
+    value = world * F * args.steps / (ms * 1e-3)
+
+    # ---- per-stage CUDA-event timing of the same step (roofline of the dominant kernel) --------------------------
+    g.set_profiling(True)
+    for _ in range(args.steps):
+        step()
+    g.sync()
+    st = g.stage_ms()
+    g.set_profiling(False)
+    kern = {k: v for k, v in st.items() if v[1] > 0 and k != "clear"}
+    dom = max(kern, key=lambda k: kern[k][0])
+    dom_ms_per_launch = kern[dom][0] / kern[dom][1]
+    frames_per_launch = F * args.steps / kern[dom][1]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    alg = algorithmic_bytes(S, n_total, F) / F * frames_per_launch
+    achieved = alg / (dom_ms_per_launch * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_frame": alg / frames_per_launch,
+                "frames_per_launch": frames_per_launch, "ms_per_launch": dom_ms_per_launch,
+                "whole_path_GBps": algorithmic_bytes(S, n_total, F) * args.steps / (ms * 1e-3) / 1e9,
+                "stage_ms_per_step": {k: v[0] / args.steps for k, v in st.items() if v[1] > 0}}
+
+    # ---- e2e: host buffers through bevgen_process_host, pinned, H2D + D2H inside the timed region ------------------
+    del din, dout
+    torch.cuda.empty_cache()
+    hb = tile_batch(distinct, Fe)
+    hin = {}
+    for k in FIELDS:
+        a = pkg.pinned_empty(hb[k].shape, hb[k].dtype); a[...] = hb[k]; hin[k] = a
+    hin["offsets"] = hb["offsets"]
+    hout = g.alloc_outputs(Fe, pinned=True)
+    h2d = int(sum(hin[k].nbytes for k in FIELDS)) + hb["offsets"].nbytes
+    d2h = int(sum(v.nbytes for v in hout.values()))
+    estep = lambda: g.process_host(hin, hout)
+    for _ in range(2):
+        estep()
+    # process_host returns only when the outputs are in host memory, so the wall clock brackets the device work;
+    # events on torch's current stream would not see the library's three streams.
+    _, e_wall = timed(estep, args.steps, torch.cuda.current_stream())
+    e2e_v = world * Fe * args.steps / (e_wall * 1e-3)
+
+    # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        O = load_oracle()
+        cores = os.cpu_count() or 1
+        sp = O.sensor(args.sensor)
+        nfr = min(4 * cores, 1024)
+        cb = tile_batch(distinct, nfr)
+        t0 = time.perf_counter()
+        O.frames(sp, cb["offsets"], *[cb[k] for k in FIELDS], n_threads=cores)
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        one = tile_batch(distinct, min(16, args.distinct))
+        O.frames(sp, one["offsets"], *[one[k] for k in FIELDS], n_threads=1)
+        dt1 = time.perf_counter() - t1
+        cpu = {"value": nfr / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "%d frames once on %d threads (%.1f s); single-thread: %.1f frames/s over %d frames" %
+                         (nfr, cores, dt, (len(one["offsets"]) - 1) / dt1, len(one["offsets"]) - 1),
+               "single_thread_frames_per_s": (len(one["offsets"]) - 1) / dt1}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic (%d distinct seeded %s frames per rank, tiled to %d)" % (args.distinct, args.sensor, F),
+                "config": {"workload": "BASELINE configs[1]: %s synthetic keyframes (~%dk pts/frame), hot loop BatchMultiBevGen.cpp:735-747"
+                                       % (args.sensor, round(n_total / F / 1000)),
+                           "sensor": args.sensor, "frames_per_step_per_gpu": F, "frames_per_wave": args.wave,
+                           "l2_policy": "inputs larger than L2 (%.2f GB of points per step)" % (in_bytes / 1e9),
+                           "parallelism": "frames sharded by index, %d process(es), no collective" % world},
+                "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "frames_per_step_per_gpu": Fe, "ms_per_step": e_wall / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_ms_per_step": wall_ms / args.steps}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,143 @@
+/*
+ * bevgen.h — C-ABI of libbevgen_cuda.so: the B200 (sm_100a) implementation of the batch_multi_bev_gen hot path.
+ *
+ * The reference (soytony/Point-Cloud-Preprocessing-Tools @ d94040e) has no library / plugin / FFI interface for
+ * this path: it sits behind a CLI (BatchMultiBevGen.cpp:664-771) and a directory contract.  This header is the
+ * boundary a host program (our C++ `batch_multi_bev_gen` CLI, or the reference's own main() — see INTEGRATION.md)
+ * binds instead of calling the reference's free functions.  Each entry point names the reference code it replaces.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative code and leaves a message
+ * retrievable through bevgen_last_error() (thread-local).  One context per device; a context is used from one
+ * host thread at a time; contexts are independent (thread-per-GPU sharding, no collective).  There is NO CPU
+ * fallback: if no CUDA device / sm_100 kernel image is usable, bevgen_create() fails.
+ *
+ * Frames are passed as concatenated SoA arrays ("points") plus offsets[F+1]: frame f owns [offsets[f], offsets[f+1]).
+ * Field meaning = pcl::PointXYZIRCT (BatchMultiBevGen.h:43-66); `t` never goes to the GPU.
+ */
+#ifndef BEVGEN_H_
+#define BEVGEN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BEVGEN_API __attribute__((visibility("default")))
+#else
+#define BEVGEN_API
+#endif
+
+#define BEVGEN_GRID_SIZE 224        /* MAX_RANGE*2/interval, BatchMultiBevGen.cpp:266-267,336-337 */
+#define BEVGEN_MAX_RANGE 112
+#define BEVGEN_NUM_LAYERS 24        /* BatchMultiBevGen.cpp:268 */
+#define BEVGEN_SECTOR_ROWS 75       /* BatchMultiBevGen.cpp:25 */
+#define BEVGEN_SECTOR_COLS 50       /* BatchMultiBevGen.cpp:26 */
+#define BEVGEN_MANIP_GRID 201       /* CloudManip.cpp:81-82 with interval 1.0f */
+
+typedef struct bevgen_ctx bevgen_ctx;
+
+/* SensorParams (include/Utility.h:30-36) + the literals of the BEV stage + optional rigid transform. */
+typedef struct bevgen_params {
+  int32_t n_scan, horizon_scan, ground_upper_scan; /* src/Utility.cpp:92-124 */
+  float height_res;
+  int32_t grid_size;      /* must be 224 */
+  int32_t max_range;      /* must be 112 */
+  int32_t n_layers;       /* must be 24  */
+  float lidar_to_ground;  /* must be 2.0f, BatchMultiBevGen.cpp:269 */
+  float rt[12];           /* row-major 3x4 [R|t]; applied to every point before ordering when has_transform != 0   */
+  int32_t has_transform;  /* (pcl::transformPointCloud semantics, CloudManip.cpp:119-128); 0 = identity, skipped    */
+} bevgen_params;
+
+/* Concatenated SoA input (host or device pointers, depending on the call). */
+typedef struct bevgen_points {
+  const float *x, *y, *z, *intensity;
+  const uint16_t *row, *col;
+  const int16_t *label;
+} bevgen_points;
+
+/* Per-frame outputs, frame-major. S = n_scan*horizon_scan.
+ *   label      [F][S]           labels of the ordered cloud after markGroundPoints (0 = ground or empty slot)
+ *   owner      [F][S]           1 + index (within the frame) of the input point that occupies the slot, 0 = empty;
+ *                               with the original records this is the ordered cloud savePCDFileBinary writes (:756)
+ *   single_bev [F][224][224]    computeAndSaveSingleBev matrix (:340-356)
+ *   multi_bev  [F][24][224][224] computeAndSaveMultiBev layers = the .bin payload (:271-292, :307-314)          */
+typedef struct bevgen_outputs {
+  int16_t *label;
+  uint32_t *owner;
+  uint8_t *single_bev;
+  uint8_t *multi_bev;
+} bevgen_outputs;
+
+/* parseSensorType + getSensorParams (src/Utility.cpp:72-124): substring match "HDL_32E" / "HDL_64E" / "OS1_64";
+ * fills the BEV literals and an identity transform.  Returns the SensorType enum value (0,1,2) or -1 if unknown
+ * (the reference prints "Unknown sensor type" and runs on uninitialised params; here it is an error). */
+BEVGEN_API int bevgen_sensor_params(const char *sensor_type, bevgen_params *out);
+
+/* Replaces the per-process globals of BatchMultiBevGen.cpp:29-37.  max_points_per_frame bounds n_in of one frame,
+ * max_frames_per_batch sizes the device scratch (frames processed per launch wave). */
+BEVGEN_API int bevgen_create(bevgen_ctx **ctx, int device, const bevgen_params *params, int max_points_per_frame,
+                  int max_frames_per_batch);
+BEVGEN_API void bevgen_destroy(bevgen_ctx *ctx);
+BEVGEN_API const char *bevgen_last_error(void);
+
+/* Pinned host memory for staging (cudaHostAlloc); process_host/submit run fully async only on such buffers. */
+BEVGEN_API void *bevgen_host_alloc(size_t bytes);
+BEVGEN_API void bevgen_host_free(void *p);
+
+/* The serial hot loop body BatchMultiBevGen.cpp:735-747 (getOrderedCloud + markGroundPoints + both BEVs, without
+ * the file encoders) for n_frames frames.
+ *   _host:   `in` / `out` are HOST buffers; H2D on a copy stream, kernels on the compute stream and D2H on a third
+ *            stream are pipelined over chunks of max_frames_per_batch frames; returns when `out` is complete.
+ *   _device: `in` / `out` are DEVICE buffers on the context's device (offsets stays a host array); work is
+ *            enqueued on the context's compute stream; call bevgen_sync() before reading `out`.            */
+BEVGEN_API int bevgen_process_host(bevgen_ctx *ctx, int n_frames, const int64_t *offsets, const bevgen_points *in,
+                        const bevgen_outputs *out);
+BEVGEN_API int bevgen_process_device(bevgen_ctx *ctx, int n_frames, const int64_t *offsets, const bevgen_points *in,
+                          const bevgen_outputs *out);
+BEVGEN_API int bevgen_sync(bevgen_ctx *ctx);
+
+/* Asynchronous single-frame form used by pipelined callers (one frame of the loop at :727-757):
+ * submit copies the frame into the context's pinned ring and enqueues H2D + kernels + D2H; collect blocks on that
+ * frame's event and copies the results out.  At most `max_frames_per_batch` frames may be in flight.     */
+BEVGEN_API int bevgen_submit(bevgen_ctx *ctx, int frame_id, int n_in, const float *x, const float *y, const float *z,
+                  const float *intensity, const uint16_t *row, const uint16_t *col, const int16_t *label);
+BEVGEN_API int bevgen_collect(bevgen_ctx *ctx, int frame_id, int16_t *label_out, uint32_t *owner_out, uint8_t *single_bev,
+                   uint8_t *multi_bev);
+
+/* selectMajorFrames (BatchMultiBevGen.cpp:502-566).  xyz = K*3 host floats (Pose6f x,y,z, :441-444).
+ * major_idx (host, capacity K) receives the M major-frame indices; *n_major = M.  overlap_nn (host, K, may be
+ * NULL): -1 major, -2 early-skipped (:528), else index into the major list of the overlapping major (:553). */
+BEVGEN_API int bevgen_select_major(bevgen_ctx *ctx, int K, const float *xyz, int32_t *major_idx, int32_t *n_major,
+                        int32_t *overlap_nn);
+/* getKeyFrameLabel (BatchMultiBevGen.cpp:575-636) for keyframe rows [row_begin,row_end) — the per-GPU row split.
+ * labels_out (host, may be NULL): dense (row_end-row_begin)*M floats.  nn_idx / nn_w (host, may be NULL): the two
+ * non-zeros of each row, [rows][2]; one-hot rows have nn_idx[1] = -1, nn_w = {1,0}. */
+BEVGEN_API int bevgen_labels(bevgen_ctx *ctx, int K, const float *xyz, int M, const int32_t *major_idx, int row_begin,
+                  int row_end, float *labels_out, int32_t *nn_idx, float *nn_w);
+
+/* cloud_manip (CloudManip.cpp:111-141): rigid transform of n host points (rt as in bevgen_params) and the two
+ * 201x201 float max-height grids of saveAsMat (:79-95) for the input and the transformed cloud.
+ * Any output pointer may be NULL.  Works on any context (sensor params are not used). */
+BEVGEN_API int bevgen_cloud_manip(bevgen_ctx *ctx, int64_t n, const float *rt, const float *x, const float *y, const float *z,
+                       float *tx, float *ty, float *tz, float *bev_in, float *bev_out);
+
+/* ---- introspection for bench / tests (no reference counterpart) ---------------------------------------------- */
+#define BEVGEN_N_STAGES 8
+/* Stage order: 0 clear, 1 order_claim, 2 order_fill, 3 ground_mark, 4 sector_mean, 5 finalize_bin_scatter,
+ * 6..7 reserved.  When profiling is enabled, process_device brackets every stage with CUDA events on the compute
+ * stream; stage_ms returns the accumulated milliseconds and launch counts since the last reset. */
+BEVGEN_API int bevgen_set_profiling(bevgen_ctx *ctx, int enabled);
+BEVGEN_API int bevgen_stage_ms(bevgen_ctx *ctx, float *ms /*[BEVGEN_N_STAGES]*/, int64_t *launches /*[BEVGEN_N_STAGES]*/);
+BEVGEN_API int64_t bevgen_kernel_launches(bevgen_ctx *ctx); /* total kernels launched by this context so far */
+BEVGEN_API void *bevgen_compute_stream(bevgen_ctx *ctx);    /* cudaStream_t of the compute stream */
+BEVGEN_API const char *bevgen_stage_name(int stage);
+/* Device port of glibc's float atan2f used by the ground criterion, exposed for bit-exactness tests. */
+BEVGEN_API int bevgen_debug_atan2f(bevgen_ctx *ctx, int64_t n, const float *y, const float *x, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEVGEN_H_ */

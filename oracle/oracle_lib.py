@@ -1,0 +1,191 @@
+"""ctypes wrapper around the CPU oracle (oracle/bevgen_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product (point-cloud-preprocessing-tools_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+GRID = 224
+LAYERS = 24
+SECT_R, SECT_C = 75, 50
+
+
+class Sensor(C.Structure):
+    _fields_ = [("n_scan", C.c_int32), ("horizon_scan", C.c_int32), ("ground_upper_scan", C.c_int32),
+                ("height_res", C.c_float)]
+
+    @property
+    def S(self):
+        return self.n_scan * self.horizon_scan
+
+
+def build(force=False):
+    """Compile the oracle (and oracle/_ref when /root/reference exists). Building the checker is not using it."""
+    so = os.path.join(_HERE, "libbevgen_oracle.so")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "bevgen_oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
+    return so
+
+
+_libs = {}
+
+
+def lib(double_libm=False):
+    key = "dbl" if double_libm else "flt"
+    if key not in _libs:
+        build()
+        name = "libbevgen_oracle_dbl.so" if double_libm else "libbevgen_oracle.so"
+        _libs[key] = C.CDLL(os.path.join(_HERE, name))
+        _libs[key].oracle_select_major.restype = C.c_int
+        _libs[key].oracle_sensor_params.restype = C.c_int
+        _libs[key].oracle_atan2f.restype = C.c_float
+        _libs[key].oracle_atan2f.argtypes = [C.c_float, C.c_float]
+        _libs[key].oracle_angle_deg.restype = C.c_float
+        _libs[key].oracle_angle_deg.argtypes = [C.c_float, C.c_float, C.c_float]
+    return _libs[key]
+
+
+def ref_lib():
+    """oracle/_ref/libnanoflann_ref.so — the reference's own vendored KD-tree, or None if it was never built."""
+    p = os.path.join(_HERE, "_ref", "libnanoflann_ref.so")
+    if not os.path.exists(p):
+        return None
+    if "ref" not in _libs:
+        _libs["ref"] = C.CDLL(p)
+        _libs["ref"].ref_knn.restype = C.c_int
+    return _libs["ref"]
+
+
+def sensor(name):
+    s = Sensor()
+    rc = lib().oracle_sensor_params(name.encode(), C.byref(s))
+    if rc < 0:
+        raise ValueError("Unknown sensor type: %s!" % name)
+    return s
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _f(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, _p(a, C.c_float)
+
+
+def order(sp, x, y, z, intensity, row, col, label):
+    S = sp.S
+    x, px = _f(x); y, py = _f(y); z, pz = _f(z); it, pi = _f(intensity)
+    row = np.ascontiguousarray(row, np.uint16); col = np.ascontiguousarray(col, np.uint16)
+    label = np.ascontiguousarray(label, np.int16)
+    out = {k: np.empty(S, np.float32) for k in ("x", "y", "z", "intensity")}
+    out["label"] = np.empty(S, np.int16); out["owner"] = np.empty(S, np.uint32)
+    lib().oracle_order(C.byref(sp), C.c_int64(len(x)), px, py, pz, pi, _p(row, C.c_uint16), _p(col, C.c_uint16),
+                       _p(label, C.c_int16), _p(out["x"], C.c_float), _p(out["y"], C.c_float), _p(out["z"], C.c_float),
+                       _p(out["intensity"], C.c_float), _p(out["label"], C.c_int16), _p(out["owner"], C.c_uint32))
+    return out
+
+
+def mark_ground(sp, oc, double_libm=False):
+    """oc = dict from order(); returns (label_out, gm_after_loop1, gm_final, avg[75,50]); oc is not modified."""
+    S = sp.S
+    lab = oc["label"].copy()
+    gm = np.empty(S, np.int8); gmf = np.empty(S, np.int8); avg = np.empty(SECT_R * SECT_C, np.float32)
+    lib(double_libm).oracle_mark_ground(C.byref(sp), _p(oc["x"], C.c_float), _p(oc["y"], C.c_float), _p(oc["z"], C.c_float),
+                                        _p(oc["intensity"], C.c_float), _p(lab, C.c_int16), _p(gm, C.c_int8),
+                                        _p(gmf, C.c_int8), _p(avg, C.c_float))
+    return lab, gm.reshape(sp.n_scan, sp.horizon_scan), gmf.reshape(sp.n_scan, sp.horizon_scan), avg.reshape(SECT_R, SECT_C)
+
+
+def multi_bev(sp, oc, label):
+    m = np.empty(LAYERS * GRID * GRID, np.uint8)
+    label = np.ascontiguousarray(label, np.int16)
+    lib().oracle_multi_bev(C.byref(sp), _p(oc["x"], C.c_float), _p(oc["y"], C.c_float), _p(oc["z"], C.c_float),
+                           _p(label, C.c_int16), _p(m, C.c_uint8))
+    return m.reshape(LAYERS, GRID, GRID)
+
+
+def single_bev(sp, oc, label):
+    m = np.empty(GRID * GRID, np.uint8)
+    label = np.ascontiguousarray(label, np.int16)
+    lib().oracle_single_bev(C.byref(sp), _p(oc["x"], C.c_float), _p(oc["y"], C.c_float), _p(oc["z"], C.c_float),
+                            _p(label, C.c_int16), _p(m, C.c_uint8))
+    return m.reshape(GRID, GRID)
+
+
+def frames(sp, offsets, x, y, z, intensity, row, col, label, n_threads=1, double_libm=False):
+    """Batch of frames (concatenated SoA + offsets[F+1]) -> dict(label, owner, single, multi)."""
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    F = len(offsets) - 1
+    S = sp.S
+    x, px = _f(x); y, py = _f(y); z, pz = _f(z); it, pi = _f(intensity)
+    row = np.ascontiguousarray(row, np.uint16); col = np.ascontiguousarray(col, np.uint16)
+    label = np.ascontiguousarray(label, np.int16)
+    out = dict(label=np.empty((F, S), np.int16), owner=np.empty((F, S), np.uint32),
+               single=np.empty((F, GRID, GRID), np.uint8), multi=np.empty((F, LAYERS, GRID, GRID), np.uint8))
+    lib(double_libm).oracle_frames(C.byref(sp), C.c_int(F), _p(offsets, C.c_int64), px, py, pz, pi, _p(row, C.c_uint16),
+                                   _p(col, C.c_uint16), _p(label, C.c_int16), _p(out["label"], C.c_int16),
+                                   _p(out["owner"], C.c_uint32), _p(out["single"], C.c_uint8), _p(out["multi"], C.c_uint8),
+                                   C.c_int(n_threads))
+    return out
+
+
+def frame(sp, x, y, z, intensity, row, col, label, **kw):
+    o = frames(sp, [0, len(x)], x, y, z, intensity, row, col, label, **kw)
+    return {k: v[0] for k, v in o.items()}
+
+
+def select_major(xyz):
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    K = len(xyz)
+    mi = np.empty(max(K, 1), np.int32); ov = np.empty(max(K, 1), np.int32)
+    M = lib().oracle_select_major(C.c_int(K), _p(xyz, C.c_float), _p(mi, C.c_int32), _p(ov, C.c_int32))
+    return mi[:M].copy(), ov[:K].copy()
+
+
+def labels(xyz, major_idx):
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    major_idx = np.ascontiguousarray(major_idx, np.int32)
+    K, M = len(xyz), len(major_idx)
+    lab = np.empty((K, M), np.float32); nn = np.empty((K, 2), np.int32); w = np.empty((K, 2), np.float32)
+    lib().oracle_labels(C.c_int(K), _p(xyz, C.c_float), C.c_int(M), _p(major_idx, C.c_int32), _p(lab, C.c_float),
+                        _p(nn, C.c_int32), _p(w, C.c_float))
+    return lab, nn, w
+
+
+def transform(rt, x, y, z):
+    rt = np.ascontiguousarray(rt, np.float32).reshape(12)
+    x, px = _f(x); y, py = _f(y); z, pz = _f(z)
+    o = [np.empty(len(x), np.float32) for _ in range(3)]
+    lib().oracle_transform(C.c_int64(len(x)), _p(rt, C.c_float), px, py, pz, *[_p(a, C.c_float) for a in o])
+    return o
+
+
+def save_as_mat(x, y, z):
+    x, px = _f(x); y, py = _f(y); z, pz = _f(z)
+    m = np.empty(201 * 201, np.float32)
+    lib().oracle_save_as_mat(C.c_int64(len(x)), px, py, pz, _p(m, C.c_float))
+    return m.reshape(201, 201)
+
+
+# ---- reference KD-tree (oracle/_ref) ---------------------------------------------------------------
+def ref_knn_many(pts, qs, k):
+    r = ref_lib()
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3); qs = np.ascontiguousarray(qs, np.float32).reshape(-1, 3)
+    idx = np.zeros((len(qs), k), np.uint64); d = np.zeros((len(qs), k), np.float32)
+    r.ref_knn_many(_p(pts, C.c_float), C.c_int(len(pts)), _p(qs, C.c_float), C.c_int(len(qs)), C.c_int(k),
+                   _p(idx, C.c_uint64), _p(d, C.c_float))
+    return idx.astype(np.int64), d
+
+
+def ref_knn(pts, q, k):
+    r = ref_lib()
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3); q = np.ascontiguousarray(q, np.float32).reshape(3)
+    idx = np.zeros(k, np.uint64); d = np.zeros(k, np.float32)
+    r.ref_knn(_p(pts, C.c_float), C.c_int(len(pts)), _p(q, C.c_float), C.c_int(k), _p(idx, C.c_uint64), _p(d, C.c_float))
+    return idx.astype(np.int64), d

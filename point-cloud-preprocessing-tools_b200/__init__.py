@@ -1,0 +1,258 @@
+"""point-cloud-preprocessing-tools_b200 — B200 (sm_100a) implementation of the `batch_multi_bev_gen` hot path of
+soytony/Point-Cloud-Preprocessing-Tools (BatchMultiBevGen.cpp).
+
+The product is the C-ABI library lib/libbevgen_cuda.so (include/bevgen.h) and the C++ CLIs in bin/.  This module is
+only a thin ctypes mirror of that C-ABI for tests and bench.py: it holds no compute of its own and it fails loudly
+when the CUDA library is missing or unusable — there is no CPU fallback.
+
+The directory name is not a Python identifier; load it with `_load_pkg.py` at the repo root (alias `pcpt_b200`).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libbevgen_cuda.so")
+CLI_PATH = os.path.join(_HERE, "bin", "batch_multi_bev_gen")
+CLOUD_MANIP_PATH = os.path.join(_HERE, "bin", "cloud_manip")
+GRID, LAYERS, CELLS = 224, 24, 224 * 224
+N_STAGES = 8
+
+
+class Params(C.Structure):
+    _fields_ = [("n_scan", C.c_int32), ("horizon_scan", C.c_int32), ("ground_upper_scan", C.c_int32),
+                ("height_res", C.c_float), ("grid_size", C.c_int32), ("max_range", C.c_int32), ("n_layers", C.c_int32),
+                ("lidar_to_ground", C.c_float), ("rt", C.c_float * 12), ("has_transform", C.c_int32)]
+
+    @property
+    def S(self):
+        return self.n_scan * self.horizon_scan
+
+
+class Points(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p), ("intensity", C.c_void_p),
+                ("row", C.c_void_p), ("col", C.c_void_p), ("label", C.c_void_p)]
+
+
+class Outputs(C.Structure):
+    _fields_ = [("label", C.c_void_p), ("owner", C.c_void_p), ("single_bev", C.c_void_p), ("multi_bev", C.c_void_p)]
+
+
+EXPORTS = ["bevgen_sensor_params", "bevgen_create", "bevgen_destroy", "bevgen_last_error", "bevgen_host_alloc",
+           "bevgen_host_free", "bevgen_process_host", "bevgen_process_device", "bevgen_sync", "bevgen_submit",
+           "bevgen_collect", "bevgen_select_major", "bevgen_labels", "bevgen_cloud_manip", "bevgen_set_profiling",
+           "bevgen_stage_ms", "bevgen_kernel_launches", "bevgen_compute_stream", "bevgen_stage_name",
+           "bevgen_debug_atan2f"]
+
+
+def build(verbose=False):
+    """make -C <package>: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... (cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", _HERE, "all"], stdout=out)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libbevgen_cuda.so is not built (%s); run __graft_entry__.build() — there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.bevgen_last_error.restype = C.c_char_p
+        L.bevgen_stage_name.restype = C.c_char_p
+        L.bevgen_host_alloc.restype = C.c_void_p
+        L.bevgen_host_alloc.argtypes = [C.c_size_t]
+        L.bevgen_host_free.argtypes = [C.c_void_p]
+        L.bevgen_kernel_launches.restype = C.c_int64
+        L.bevgen_kernel_launches.argtypes = [C.c_void_p]
+        L.bevgen_compute_stream.restype = C.c_void_p
+        L.bevgen_compute_stream.argtypes = [C.c_void_p]
+        L.bevgen_destroy.argtypes = [C.c_void_p]
+        L.bevgen_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+class BevgenError(RuntimeError):
+    pass
+
+
+def _ck(rc):
+    if rc < 0:
+        raise BevgenError(lib().bevgen_last_error().decode())
+    return rc
+
+
+def sensor_params(name):
+    p = Params()
+    rc = lib().bevgen_sensor_params(name.encode(), C.byref(p))
+    if rc < 0:
+        raise BevgenError(lib().bevgen_last_error().decode())
+    return p
+
+
+def _ptr(a):
+    """host numpy array or integer device pointer -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return C.c_void_p(a.ctypes.data)
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by cudaHostAlloc memory (freed when the array's base capsule dies)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = lib().bevgen_host_alloc(max(n, 1))
+    if not p:
+        raise BevgenError(lib().bevgen_last_error().decode())
+    buf = (C.c_char * max(n, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.__array_interface__["data"][0]] = p
+    return arr
+
+
+_PINNED = {}
+
+
+def pinned_free(arr):
+    p = _PINNED.pop(arr.__array_interface__["data"][0], None)
+    if p:
+        lib().bevgen_host_free(C.c_void_p(p))
+
+
+class BevGen:
+    """One context = one GPU (bevgen_ctx).  Mirrors the hot loop body of BatchMultiBevGen.cpp:727-757."""
+
+    def __init__(self, sensor="HDL_64E", device=0, max_points_per_frame=None, max_frames_per_batch=64, rt=None):
+        self.params = sensor_params(sensor) if isinstance(sensor, str) else sensor
+        if rt is not None:
+            rt = np.ascontiguousarray(rt, np.float32).reshape(12)
+            for i in range(12):
+                self.params.rt[i] = float(rt[i])
+            self.params.has_transform = 1
+        self.S = self.params.S
+        self.max_pts = int(max_points_per_frame or self.S + 4096)
+        self.max_frames = int(max_frames_per_batch)
+        self._ctx = C.c_void_p()
+        _ck(lib().bevgen_create(C.byref(self._ctx), C.c_int(device), C.byref(self.params), C.c_int(self.max_pts),
+                                C.c_int(self.max_frames)))
+
+    def close(self):
+        if self._ctx:
+            lib().bevgen_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- hot loop -------------------------------------------------------------------------------------------
+    def alloc_outputs(self, F, pinned=False):
+        mk = pinned_empty if pinned else np.empty
+        return dict(label=mk((F, self.S), np.int16), owner=mk((F, self.S), np.uint32),
+                    single=mk((F, GRID, GRID), np.uint8), multi=mk((F, LAYERS, GRID, GRID), np.uint8))
+
+    def process_host(self, batch, out=None):
+        """batch: dict x,y,z,intensity,row,col,label (+offsets int64[F+1]) of HOST numpy arrays."""
+        offs = np.ascontiguousarray(batch["offsets"], np.int64)
+        F = len(offs) - 1
+        out = out or self.alloc_outputs(F)
+        arrs = [_as(batch[k], t) for k, t in _FIELDS]      # keep converted temporaries alive across the call
+        pts = Points(*[_ptr(a) for a in arrs])
+        o = Outputs(_ptr(out["label"]), _ptr(out["owner"]), _ptr(out["single"]), _ptr(out["multi"]))
+        _ck(lib().bevgen_process_host(self._ctx, C.c_int(F), _ptr(offs), C.byref(pts), C.byref(o)))
+        return out
+
+    def process_device(self, F, offsets, dev_in, dev_out):
+        """dev_in / dev_out: dicts of integer DEVICE pointers (same keys as the host form); async on the compute stream."""
+        offs = np.ascontiguousarray(offsets, np.int64)
+        pts = Points(*[C.c_void_p(int(dev_in[k])) for k, _ in _FIELDS])
+        o = Outputs(C.c_void_p(int(dev_out["label"])), C.c_void_p(int(dev_out["owner"])), C.c_void_p(int(dev_out["single"])),
+                    C.c_void_p(int(dev_out["multi"])))
+        _ck(lib().bevgen_process_device(self._ctx, C.c_int(F), _ptr(offs), C.byref(pts), C.byref(o)))
+
+    def sync(self):
+        _ck(lib().bevgen_sync(self._ctx))
+
+    def submit(self, frame_id, f):
+        n = len(f["x"])
+        a = [_as(f[k], t) for k, t in _FIELDS]
+        _ck(lib().bevgen_submit(self._ctx, C.c_int(frame_id), C.c_int(n), *[_ptr(v) for v in a]))
+
+    def collect(self, frame_id):
+        out = self.alloc_outputs(1)
+        _ck(lib().bevgen_collect(self._ctx, C.c_int(frame_id), _ptr(out["label"]), _ptr(out["owner"]), _ptr(out["single"]),
+                                 _ptr(out["multi"])))
+        return {k: v[0] for k, v in out.items()}
+
+    # ---- labels ---------------------------------------------------------------------------------------------
+    def select_major(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        K = len(xyz)
+        mi = np.empty(max(K, 1), np.int32); ov = np.empty(max(K, 1), np.int32); M = C.c_int32(0)
+        _ck(lib().bevgen_select_major(self._ctx, C.c_int(K), _ptr(xyz), _ptr(mi), C.byref(M), _ptr(ov)))
+        return mi[:M.value].copy(), ov[:K].copy()
+
+    def labels(self, xyz, major_idx, row_begin=0, row_end=None, dense=True):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        major_idx = np.ascontiguousarray(major_idx, np.int32)
+        K, M = len(xyz), len(major_idx)
+        row_end = K if row_end is None else row_end
+        rows = row_end - row_begin
+        lab = np.empty((rows, M), np.float32) if dense else None
+        nn = np.empty((rows, 2), np.int32); w = np.empty((rows, 2), np.float32)
+        _ck(lib().bevgen_labels(self._ctx, C.c_int(K), _ptr(xyz), C.c_int(M), _ptr(major_idx), C.c_int(row_begin),
+                                C.c_int(row_end), _ptr(lab), _ptr(nn), _ptr(w)))
+        return lab, nn, w
+
+    # ---- cloud_manip ------------------------------------------------------------------------------------------
+    def cloud_manip(self, rt, x, y, z):
+        rt = np.ascontiguousarray(rt, np.float32).reshape(12)
+        x = _as(x, np.float32); y = _as(y, np.float32); z = _as(z, np.float32)
+        n = len(x)
+        t = [np.empty(n, np.float32) for _ in range(3)]
+        bi = np.empty((201, 201), np.float32); bo = np.empty((201, 201), np.float32)
+        _ck(lib().bevgen_cloud_manip(self._ctx, C.c_int64(n), _ptr(rt), _ptr(x), _ptr(y), _ptr(z), _ptr(t[0]), _ptr(t[1]),
+                                     _ptr(t[2]), _ptr(bi), _ptr(bo)))
+        return t, bi, bo
+
+    # ---- introspection ----------------------------------------------------------------------------------------
+    def set_profiling(self, on):
+        _ck(lib().bevgen_set_profiling(self._ctx, C.c_int(1 if on else 0)))
+
+    def stage_ms(self):
+        ms = (C.c_float * N_STAGES)(); ln = (C.c_int64 * N_STAGES)()
+        _ck(lib().bevgen_stage_ms(self._ctx, ms, ln))
+        return {lib().bevgen_stage_name(i).decode(): (ms[i], ln[i]) for i in range(N_STAGES)}
+
+    def kernel_launches(self):
+        return int(lib().bevgen_kernel_launches(self._ctx))
+
+    def compute_stream(self):
+        return int(lib().bevgen_compute_stream(self._ctx) or 0)
+
+    def debug_atan2f(self, y, x):
+        y = _as(y, np.float32); x = _as(x, np.float32)
+        out = np.empty(len(y), np.float32)
+        _ck(lib().bevgen_debug_atan2f(self._ctx, C.c_int64(len(y)), _ptr(y), _ptr(x), _ptr(out)))
+        return out
+
+
+_FIELDS = [("x", np.float32), ("y", np.float32), ("z", np.float32), ("intensity", np.float32), ("row", np.uint16),
+           ("col", np.uint16), ("label", np.int16)]
+
+
+def _as(a, t):
+    a = np.asarray(a)
+    if a.dtype != t or not a.flags["C_CONTIGUOUS"]:
+        a = np.ascontiguousarray(a, t)
+    return a

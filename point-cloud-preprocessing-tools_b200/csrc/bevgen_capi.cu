@@ -1,0 +1,537 @@
+// bevgen_capi.cu — C-ABI (include/bevgen.h) over the sm_100a kernels in bevgen_kernels.cuh.
+// Host side of the library: context, streams, device scratch, chunked H2D / compute / D2H pipeline.
+// No PyTorch, no Triton, no CPU fallback: every entry point that computes launches CUDA kernels or fails.
+#include "../../include/bevgen.h"
+#include "bevgen_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace bevgen;
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char b_[512];                                                                                \
+      snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));  \
+      g_err = b_;                                                                                  \
+      return -1;                                                                                   \
+    }                                                                                              \
+  } while (0)
+
+namespace {
+
+struct DevIn { float *x = 0, *y = 0, *z = 0, *inten = 0; uint16_t *row = 0, *col = 0; int16_t* label = 0; };
+struct DevOut { int16_t* label = 0; uint32_t* owner = 0; uint8_t* single = 0; uint8_t* multi = 0; };
+
+struct Scratch {            // device scratch for one wave of up to `frames` frames
+  float4* rec = 0; uint16_t* gkey = 0; float* gz = 0; uint32_t* cnt = 0; float* avg = 0;
+};
+
+struct Lane {               // host-path double buffer: device staging of inputs/outputs + scratch
+  Scratch sc; DevIn in; DevOut out;
+  cudaEvent_t ev_h2d = 0, ev_comp = 0, ev_d2h = 0;
+  bool used = false;
+};
+
+struct Slot {               // submit/collect ring entry: one frame, own stream, pinned staging
+  Scratch sc; DevIn in; DevOut out;
+  char* pin_in = 0; char* pin_out = 0; int64_t* offs_d = 0;
+  cudaStream_t st = 0; cudaEvent_t done = 0;
+  int frame_id = -1; bool busy = false;
+};
+
+}  // namespace
+
+struct bevgen_ctx {
+  int device = 0;
+  bevgen_params p{};
+  SensorDev sp{};
+  Xform xf{};
+  int max_pts = 0, max_frames = 0;
+  cudaStream_t s_copy = 0, s_comp = 0, s_d2h = 0;
+  float* cnt_lut = 0;
+  Scratch sc_dev;            // scratch of the device path
+  int64_t* offs_d = 0; size_t offs_cap = 0;
+  bool lanes_ready = false; Lane lanes[2];
+  std::vector<Slot> slots;
+  // profiling
+  bool prof = false;
+  cudaEvent_t pev[BEVGEN_N_STAGES + 1]{};
+  double stage_ms[BEVGEN_N_STAGES]{};
+  int64_t stage_launches[BEVGEN_N_STAGES]{};
+  int64_t launches = 0;
+};
+
+static const char* kStageNames[BEVGEN_N_STAGES] = {"clear", "order_claim", "order_fill", "ground_mark",
+                                                   "sector_mean", "finalize_bin_scatter", "reserved6", "reserved7"};
+
+// ---- params ---------------------------------------------------------------------------------------------------
+extern "C" int bevgen_sensor_params(const char* s, bevgen_params* out) {
+  if (!s || !out) return fail("bevgen_sensor_params: null argument");
+  memset(out, 0, sizeof *out);
+  out->grid_size = BEVGEN_GRID_SIZE; out->max_range = BEVGEN_MAX_RANGE; out->n_layers = BEVGEN_NUM_LAYERS;
+  out->lidar_to_ground = 2.0f;
+  out->rt[0] = out->rt[5] = out->rt[10] = 1.0f; out->has_transform = 0;
+  // src/Utility.cpp:72-89: substring match, tested in this order; :92-124 the table
+  if (strstr(s, "HDL_32E")) { out->n_scan = 32; out->horizon_scan = 1056; out->ground_upper_scan = 20; out->height_res = 0.5f; return 0; }
+  if (strstr(s, "HDL_64E")) { out->n_scan = 64; out->horizon_scan = 2083; out->ground_upper_scan = 50; out->height_res = 0.25f; return 1; }
+  if (strstr(s, "OS1_64")) { out->n_scan = 64; out->horizon_scan = 1024; out->ground_upper_scan = 31; out->height_res = 1.0f; return 2; }
+  fail(std::string("Unknown sensor type: ") + s + "!");
+  return -1;
+}
+
+extern "C" const char* bevgen_last_error(void) { return g_err.c_str(); }
+extern "C" const char* bevgen_stage_name(int s) { return (s >= 0 && s < BEVGEN_N_STAGES) ? kStageNames[s] : ""; }
+
+extern "C" void* bevgen_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+  return p;
+}
+extern "C" void bevgen_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- allocation helpers ---------------------------------------------------------------------------------------
+static int alloc_scratch(Scratch& s, size_t frames, size_t S) {
+  CK(cudaMalloc(&s.rec, frames * S * sizeof(float4)));
+  CK(cudaMalloc(&s.gkey, frames * S * sizeof(uint16_t)));
+  CK(cudaMalloc(&s.gz, frames * S * sizeof(float)));
+  CK(cudaMalloc(&s.cnt, frames * NSECT * sizeof(uint32_t)));
+  CK(cudaMalloc(&s.avg, frames * NSECT * sizeof(float)));
+  return 0;
+}
+static void free_scratch(Scratch& s) { cudaFree(s.rec); cudaFree(s.gkey); cudaFree(s.gz); cudaFree(s.cnt); cudaFree(s.avg); s = Scratch(); }
+static int alloc_io(DevIn& in, DevOut& out, size_t frames, size_t pts, size_t S) {
+  const size_t n = frames * pts;
+  CK(cudaMalloc(&in.x, n * 4)); CK(cudaMalloc(&in.y, n * 4)); CK(cudaMalloc(&in.z, n * 4)); CK(cudaMalloc(&in.inten, n * 4));
+  CK(cudaMalloc(&in.row, n * 2)); CK(cudaMalloc(&in.col, n * 2)); CK(cudaMalloc(&in.label, n * 2));
+  CK(cudaMalloc(&out.label, frames * S * 2)); CK(cudaMalloc(&out.owner, frames * S * 4));
+  CK(cudaMalloc(&out.single, frames * CELLS)); CK(cudaMalloc(&out.multi, frames * (size_t)LAYERS * CELLS));
+  return 0;
+}
+static void free_io(DevIn& in, DevOut& out) {
+  cudaFree(in.x); cudaFree(in.y); cudaFree(in.z); cudaFree(in.inten); cudaFree(in.row); cudaFree(in.col); cudaFree(in.label);
+  cudaFree(out.label); cudaFree(out.owner); cudaFree(out.single); cudaFree(out.multi);
+  in = DevIn(); out = DevOut();
+}
+
+// ---- create / destroy -----------------------------------------------------------------------------------------
+extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* p, int max_pts, int max_frames) {
+  if (!out || !p) return fail("bevgen_create: null argument");
+  if (p->grid_size != BEVGEN_GRID_SIZE || p->max_range != BEVGEN_MAX_RANGE || p->n_layers != BEVGEN_NUM_LAYERS ||
+      p->lidar_to_ground != 2.0f)
+    return fail("bevgen_create: grid_size/max_range/n_layers/lidar_to_ground must be 224/112/24/2.0 (BatchMultiBevGen.cpp:266-269)");
+  if (p->n_scan <= 0 || p->horizon_scan <= 2 || p->ground_upper_scan <= 0 || p->n_scan - p->ground_upper_scan - 1 < 1 ||
+      !(p->height_res > 0.0f))
+    return fail("bevgen_create: invalid sensor params (need n_scan - ground_upper_scan >= 2)");
+  if ((int64_t)p->n_scan * p->horizon_scan > (1 << 24)) return fail("bevgen_create: range image too large");
+  if (max_pts <= 0 || max_frames <= 0) return fail("bevgen_create: max_points_per_frame / max_frames_per_batch must be > 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("bevgen_create: no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail("bevgen_create: bad device index");
+  CK(cudaSetDevice(device));
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, k_finalize_bin) != cudaSuccess)
+    return fail("bevgen_create: no sm_100a kernel image usable on this device (library is built for B200 only)");
+
+  bevgen_ctx* c = new bevgen_ctx();
+  c->device = device; c->p = *p; c->max_pts = max_pts; c->max_frames = max_frames;
+  SensorDev& sp = c->sp;
+  sp.N = p->n_scan; sp.H = p->horizon_scan; sp.G = p->ground_upper_scan; sp.S = sp.N * sp.H;
+  sp.band_row0 = sp.N - sp.G - 1;
+  sp.height_res = p->height_res; sp.inv_height_res = 1.0f / p->height_res;
+  { int e; float m = frexpf(p->height_res, &e); sp.hr_pow2 = (m == 0.5f); }
+  // t_star: largest float t with (float)((double)t * 180.0 / M_PI) <= 10.0f  (BatchMultiBevGen.cpp:173,179); bisection on
+  // the bit pattern of a monotone function.  A constant of the criterion, not data-dependent compute.
+  {
+    uint32_t lo, hi; float a = 0.1f, b = 0.2f; memcpy(&lo, &a, 4); memcpy(&hi, &b, 4);
+    while (hi - lo > 1) {
+      uint32_t mid = lo + (hi - lo) / 2; float t; memcpy(&t, &mid, 4);
+      float ang = (float)((double)t * 180.0 / M_PI);
+      if (ang <= 10.0f) lo = mid; else hi = mid;
+    }
+    memcpy(&sp.t_star, &lo, 4);
+    double tt = tan((double)sp.t_star);
+    sp.q_lo = (float)(tt * (1.0 - 1e-5)); sp.q_hi = (float)(tt * (1.0 + 1e-5));
+  }
+  memcpy(c->xf.m, p->rt, sizeof c->xf.m); c->xf.on = p->has_transform ? 1 : 0;
+
+  CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  for (auto& e : c->pev) CK(cudaEventCreate(&e));
+  CK(cudaFuncSetAttribute(k_finalize_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BIN));
+  CK(cudaMalloc(&c->cnt_lut, ((size_t)sp.S + 1) * sizeof(float)));
+  k_build_cnt_lut<<<1, 32, 0, c->s_comp>>>(sp.S, c->cnt_lut);
+  CK(cudaGetLastError());
+  c->launches++;
+  if (alloc_scratch(c->sc_dev, max_frames, sp.S)) { delete c; return -1; }
+  CK(cudaStreamSynchronize(c->s_comp));
+  *out = c;
+  return 0;
+}
+
+extern "C" void bevgen_destroy(bevgen_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_scratch(c->sc_dev);
+  if (c->lanes_ready) for (auto& l : c->lanes) { free_scratch(l.sc); free_io(l.in, l.out); cudaEventDestroy(l.ev_h2d); cudaEventDestroy(l.ev_comp); cudaEventDestroy(l.ev_d2h); }
+  for (auto& s : c->slots) { free_scratch(s.sc); free_io(s.in, s.out); cudaFreeHost(s.pin_in); cudaFreeHost(s.pin_out); cudaFree(s.offs_d); cudaStreamDestroy(s.st); cudaEventDestroy(s.done); }
+  cudaFree(c->cnt_lut); cudaFree(c->offs_d);
+  for (auto& e : c->pev) cudaEventDestroy(e);
+  cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h);
+  delete c;
+}
+
+// ---- one wave of frames on a stream ---------------------------------------------------------------------------
+// offs_d: device offsets of the wave (nf+1 entries); `base` is subtracted so that `in` may be a staging buffer that
+// starts at the wave's first point.  max_n: largest frame of the wave (host-known).
+static int run_wave(bevgen_ctx* c, cudaStream_t st, const Scratch& sc, int nf, const int64_t* offs_d, int64_t base, int max_n,
+                    const DevIn& in, const DevOut& out, bool prof) {
+  const SensorDev& sp = c->sp;
+  const size_t S = sp.S;
+  auto mark = [&](int i) { if (prof) cudaEventRecord(c->pev[i], st); };
+  // inputs are indexed with the caller's offsets: shift the pointers instead of the offsets
+  const float *x = in.x - base, *y = in.y - base, *z = in.z - base, *it = in.inten - base;
+  const uint16_t *row = in.row - base, *col = in.col - base;
+  const int16_t* lab = in.label - base;
+
+  mark(0);
+  CK(cudaMemsetAsync(out.owner, 0, (size_t)nf * S * sizeof(uint32_t), st));
+  CK(cudaMemsetAsync(sc.cnt, 0, (size_t)nf * NSECT * sizeof(uint32_t), st));
+  mark(1);
+  if (max_n > 0) {
+    dim3 g((max_n + 255) / 256, nf);
+    k_order_claim<<<g, 256, 0, st>>>(sp, offs_d, row, col, out.owner);
+  }
+  mark(2);
+  {
+    dim3 g((std::max<int>(max_n, (int)S) + 255) / 256, nf);
+    k_order_fill<<<g, 256, 0, st>>>(sp, c->xf, offs_d, x, y, z, it, row, col, lab, out.owner, sc.rec);
+  }
+  mark(3);
+  {
+    dim3 g((sp.H + 127) / 128, nf);
+    k_ground_mark<<<g, 128, 0, st>>>(sp, sc.rec, sc.gkey, sc.gz, sc.cnt);
+  }
+  mark(4);
+  k_sector_mean<<<nf, 32, NSECT * sizeof(float), st>>>(sp, sc.gkey, sc.gz, sc.cnt, c->cnt_lut, sc.avg);
+  mark(5);
+  k_finalize_bin<<<nf, 1024, SMEM_BIN, st>>>(sp, sc.rec, sc.gkey, sc.avg, out.label, out.single, out.multi);
+  mark(6);
+  CK(cudaGetLastError());
+  c->launches += (max_n > 0 ? 5 : 4);
+  if (prof) {
+    CK(cudaEventSynchronize(c->pev[6]));
+    for (int i = 0; i < 6; i++) {
+      float ms = 0; CK(cudaEventElapsedTime(&ms, c->pev[i], c->pev[i + 1]));
+      c->stage_ms[i] += ms;
+      c->stage_launches[i] += (i == 0) ? 2 : ((i == 1 && max_n == 0) ? 0 : 1);
+    }
+  }
+  return 0;
+}
+
+static int upload_offsets(bevgen_ctx* c, int nf, const int64_t* offsets, cudaStream_t st, int* max_n_out) {
+  if ((size_t)nf + 1 > c->offs_cap) {
+    CK(cudaStreamSynchronize(c->s_comp)); CK(cudaStreamSynchronize(c->s_copy));
+    cudaFree(c->offs_d); c->offs_d = 0;
+    c->offs_cap = (size_t)nf + 1 + 1024;
+    CK(cudaMalloc(&c->offs_d, c->offs_cap * sizeof(int64_t)));
+  }
+  int64_t mx = 0;
+  for (int f = 0; f < nf; f++) {
+    int64_t n = offsets[f + 1] - offsets[f];
+    if (n < 0) return fail("offsets must be non-decreasing");
+    if (n > 0x7ffffff0) return fail("frame too large");
+    mx = std::max(mx, n);
+  }
+  *max_n_out = (int)mx;
+  CK(cudaMemcpyAsync(c->offs_d, offsets, ((size_t)nf + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+// ---- device-resident path -------------------------------------------------------------------------------------
+extern "C" int bevgen_process_device(bevgen_ctx* c, int nf, const int64_t* offsets, const bevgen_points* in, const bevgen_outputs* out) {
+  if (!c || !offsets || !in || !out) return fail("bevgen_process_device: null argument");
+  if (nf <= 0) return 0;
+  CK(cudaSetDevice(c->device));
+  int max_n_all = 0;
+  if (upload_offsets(c, nf, offsets, c->s_comp, &max_n_all)) return -1;
+  const size_t S = c->sp.S;
+  DevIn di; di.x = (float*)in->x; di.y = (float*)in->y; di.z = (float*)in->z; di.inten = (float*)in->intensity;
+  di.row = (uint16_t*)in->row; di.col = (uint16_t*)in->col; di.label = (int16_t*)in->label;
+  for (int f0 = 0; f0 < nf; f0 += c->max_frames) {
+    const int n = std::min(c->max_frames, nf - f0);
+    int max_n = 0;
+    for (int f = f0; f < f0 + n; f++) max_n = std::max<int64_t>(max_n, offsets[f + 1] - offsets[f]);
+    DevOut dout; dout.label = out->label + (size_t)f0 * S; dout.owner = out->owner + (size_t)f0 * S;
+    dout.single = out->single_bev + (size_t)f0 * CELLS; dout.multi = out->multi_bev + (size_t)f0 * LAYERS * CELLS;
+    if (run_wave(c, c->s_comp, c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout, c->prof)) return -1;
+  }
+  return 0;
+}
+
+extern "C" int bevgen_sync(bevgen_ctx* c) {
+  if (!c) return fail("bevgen_sync: null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->s_copy)); CK(cudaStreamSynchronize(c->s_comp)); CK(cudaStreamSynchronize(c->s_d2h));
+  return 0;
+}
+
+// ---- host-buffer path: H2D (copy stream) | kernels (compute stream) | D2H (third stream), double-buffered ------
+static int ensure_lanes(bevgen_ctx* c) {
+  if (c->lanes_ready) return 0;
+  for (auto& l : c->lanes) {
+    if (alloc_scratch(l.sc, c->max_frames, c->sp.S)) return -1;
+    if (alloc_io(l.in, l.out, c->max_frames, c->max_pts, c->sp.S)) return -1;
+    CK(cudaEventCreateWithFlags(&l.ev_h2d, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&l.ev_comp, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&l.ev_d2h, cudaEventDisableTiming));
+  }
+  c->lanes_ready = true;
+  return 0;
+}
+
+extern "C" int bevgen_process_host(bevgen_ctx* c, int nf, const int64_t* offsets, const bevgen_points* in, const bevgen_outputs* out) {
+  if (!c || !offsets || !in || !out) return fail("bevgen_process_host: null argument");
+  if (nf <= 0) return 0;
+  CK(cudaSetDevice(c->device));
+  if (ensure_lanes(c)) return -1;
+  int max_n_all = 0;
+  if (upload_offsets(c, nf, offsets, c->s_comp, &max_n_all)) return -1;
+  if (max_n_all > c->max_pts) return fail("bevgen_process_host: a frame exceeds max_points_per_frame");
+  const size_t S = c->sp.S;
+  int k = 0;
+  for (int f0 = 0; f0 < nf; f0 += c->max_frames, k++) {
+    Lane& l = c->lanes[k & 1];
+    const int n = std::min(c->max_frames, nf - f0);
+    const int64_t base = offsets[f0];
+    const size_t np = (size_t)(offsets[f0 + n] - base);
+    int max_n = 0;
+    for (int f = f0; f < f0 + n; f++) max_n = std::max<int64_t>(max_n, offsets[f + 1] - offsets[f]);
+    // inputs of this lane may be overwritten once the kernels of its previous wave are done
+    if (l.used) CK(cudaStreamWaitEvent(c->s_copy, l.ev_comp, 0));
+    CK(cudaMemcpyAsync(l.in.x, in->x + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
+    CK(cudaMemcpyAsync(l.in.y, in->y + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
+    CK(cudaMemcpyAsync(l.in.z, in->z + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
+    CK(cudaMemcpyAsync(l.in.inten, in->intensity + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
+    CK(cudaMemcpyAsync(l.in.row, in->row + base, np * 2, cudaMemcpyHostToDevice, c->s_copy));
+    CK(cudaMemcpyAsync(l.in.col, in->col + base, np * 2, cudaMemcpyHostToDevice, c->s_copy));
+    CK(cudaMemcpyAsync(l.in.label, in->label + base, np * 2, cudaMemcpyHostToDevice, c->s_copy));
+    CK(cudaEventRecord(l.ev_h2d, c->s_copy));
+    CK(cudaStreamWaitEvent(c->s_comp, l.ev_h2d, 0));
+    if (l.used) CK(cudaStreamWaitEvent(c->s_comp, l.ev_d2h, 0));   // outputs of the previous wave have left
+    if (run_wave(c, c->s_comp, l.sc, n, c->offs_d + f0, base, max_n, l.in, l.out, false)) return -1;
+    CK(cudaEventRecord(l.ev_comp, c->s_comp));
+    CK(cudaStreamWaitEvent(c->s_d2h, l.ev_comp, 0));
+    CK(cudaMemcpyAsync(out->label + (size_t)f0 * S, l.out.label, (size_t)n * S * 2, cudaMemcpyDeviceToHost, c->s_d2h));
+    CK(cudaMemcpyAsync(out->owner + (size_t)f0 * S, l.out.owner, (size_t)n * S * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    CK(cudaMemcpyAsync(out->single_bev + (size_t)f0 * CELLS, l.out.single, (size_t)n * CELLS, cudaMemcpyDeviceToHost, c->s_d2h));
+    CK(cudaMemcpyAsync(out->multi_bev + (size_t)f0 * LAYERS * CELLS, l.out.multi, (size_t)n * LAYERS * CELLS, cudaMemcpyDeviceToHost, c->s_d2h));
+    CK(cudaEventRecord(l.ev_d2h, c->s_d2h));
+    l.used = true;
+  }
+  CK(cudaStreamSynchronize(c->s_d2h));
+  CK(cudaStreamSynchronize(c->s_comp));
+  CK(cudaStreamSynchronize(c->s_copy));
+  return 0;
+}
+
+// ---- submit / collect (single frames in flight, one stream per ring slot) ---------------------------------------
+static size_t in_bytes(size_t n) { return n * 22; }
+static int ensure_slots(bevgen_ctx* c) {
+  if (!c->slots.empty()) return 0;
+  const int ns = std::min(c->max_frames, 8);
+  c->slots.resize(ns);
+  const size_t S = c->sp.S;
+  for (auto& s : c->slots) {
+    if (alloc_scratch(s.sc, 1, S)) return -1;
+    if (alloc_io(s.in, s.out, 1, c->max_pts, S)) return -1;
+    CK(cudaHostAlloc((void**)&s.pin_in, in_bytes(c->max_pts) + 16, cudaHostAllocPortable));
+    CK(cudaHostAlloc((void**)&s.pin_out, S * 6 + CELLS + (size_t)LAYERS * CELLS, cudaHostAllocPortable));
+    CK(cudaMalloc(&s.offs_d, 2 * sizeof(int64_t)));
+    CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+extern "C" int bevgen_submit(bevgen_ctx* c, int frame_id, int n_in, const float* x, const float* y, const float* z,
+                             const float* intensity, const uint16_t* row, const uint16_t* col, const int16_t* label) {
+  if (!c) return fail("bevgen_submit: null ctx");
+  if (n_in < 0 || n_in > c->max_pts) return fail("bevgen_submit: n_in exceeds max_points_per_frame");
+  CK(cudaSetDevice(c->device));
+  if (ensure_slots(c)) return -1;
+  Slot* s = nullptr;
+  for (auto& t : c->slots) { if (t.busy && t.frame_id == frame_id) return fail("bevgen_submit: frame_id already in flight"); }
+  for (auto& t : c->slots) if (!t.busy) { s = &t; break; }
+  if (!s) return fail("bevgen_submit: ring full — collect a frame first");
+  const size_t n = (size_t)n_in, S = c->sp.S;
+  // pinned staging: [x|y|z|intensity|row|col|label] SoA, then the two offsets
+  char* p = s->pin_in;
+  float* px = (float*)p; float* py = px + n; float* pz = py + n; float* pi = pz + n;
+  uint16_t* pr = (uint16_t*)(pi + n); uint16_t* pc = pr + n; int16_t* pl = (int16_t*)(pc + n);
+  memcpy(px, x, n * 4); memcpy(py, y, n * 4); memcpy(pz, z, n * 4); memcpy(pi, intensity, n * 4);
+  memcpy(pr, row, n * 2); memcpy(pc, col, n * 2); memcpy(pl, label, n * 2);
+  int64_t* po = (int64_t*)(s->pin_out);   // offsets live at the head of pin_out until the kernels ran
+  po[0] = 0; po[1] = n_in;
+  CK(cudaMemcpyAsync(s->offs_d, po, 16, cudaMemcpyHostToDevice, s->st));
+  CK(cudaMemcpyAsync(s->in.x, px, n * 4, cudaMemcpyHostToDevice, s->st));
+  CK(cudaMemcpyAsync(s->in.y, py, n * 4, cudaMemcpyHostToDevice, s->st));
+  CK(cudaMemcpyAsync(s->in.z, pz, n * 4, cudaMemcpyHostToDevice, s->st));
+  CK(cudaMemcpyAsync(s->in.inten, pi, n * 4, cudaMemcpyHostToDevice, s->st));
+  CK(cudaMemcpyAsync(s->in.row, pr, n * 2, cudaMemcpyHostToDevice, s->st));
+  CK(cudaMemcpyAsync(s->in.col, pc, n * 2, cudaMemcpyHostToDevice, s->st));
+  CK(cudaMemcpyAsync(s->in.label, pl, n * 2, cudaMemcpyHostToDevice, s->st));
+  if (run_wave(c, s->st, s->sc, 1, s->offs_d, 0, n_in, s->in, s->out, false)) return -1;
+  char* q = s->pin_out;
+  CK(cudaMemcpyAsync(q, s->out.owner, S * 4, cudaMemcpyDeviceToHost, s->st)); q += S * 4;
+  CK(cudaMemcpyAsync(q, s->out.label, S * 2, cudaMemcpyDeviceToHost, s->st)); q += S * 2;
+  CK(cudaMemcpyAsync(q, s->out.single, CELLS, cudaMemcpyDeviceToHost, s->st)); q += CELLS;
+  CK(cudaMemcpyAsync(q, s->out.multi, (size_t)LAYERS * CELLS, cudaMemcpyDeviceToHost, s->st));
+  CK(cudaEventRecord(s->done, s->st));
+  s->busy = true; s->frame_id = frame_id;
+  return 0;
+}
+
+extern "C" int bevgen_collect(bevgen_ctx* c, int frame_id, int16_t* label_out, uint32_t* owner_out, uint8_t* single_bev, uint8_t* multi_bev) {
+  if (!c) return fail("bevgen_collect: null ctx");
+  CK(cudaSetDevice(c->device));
+  for (auto& s : c->slots) {
+    if (!s.busy || s.frame_id != frame_id) continue;
+    CK(cudaEventSynchronize(s.done));
+    const size_t S = c->sp.S;
+    const char* q = s.pin_out;
+    if (owner_out) memcpy(owner_out, q, S * 4); q += S * 4;
+    if (label_out) memcpy(label_out, q, S * 2); q += S * 2;
+    if (single_bev) memcpy(single_bev, q, CELLS); q += CELLS;
+    if (multi_bev) memcpy(multi_bev, q, (size_t)LAYERS * CELLS);
+    s.busy = false; s.frame_id = -1;
+    return 0;
+  }
+  return fail("bevgen_collect: frame_id not in flight");
+}
+
+// ---- labels ---------------------------------------------------------------------------------------------------
+namespace bevgen {
+__global__ void k_gather_mpos(int M, const float* __restrict__ xyz, const int32_t* __restrict__ major_idx, float* __restrict__ mpos) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < M) { int i = major_idx[j]; mpos[3 * j] = xyz[3 * i]; mpos[3 * j + 1] = xyz[3 * i + 1]; mpos[3 * j + 2] = xyz[3 * i + 2]; }
+}
+}  // namespace bevgen
+
+extern "C" int bevgen_select_major(bevgen_ctx* c, int K, const float* xyz, int32_t* major_idx, int32_t* n_major, int32_t* overlap_nn) {
+  if (!c || !xyz || !major_idx || !n_major) return fail("bevgen_select_major: null argument");
+  if (K <= 0) { *n_major = 0; return 0; }
+  CK(cudaSetDevice(c->device));
+  float *d_xyz = 0, *d_mpos = 0; int32_t *d_mi = 0, *d_ov = 0, *d_n = 0;
+  CK(cudaMalloc(&d_xyz, (size_t)K * 12)); CK(cudaMalloc(&d_mpos, (size_t)K * 12));
+  CK(cudaMalloc(&d_mi, (size_t)K * 4)); CK(cudaMalloc(&d_ov, (size_t)K * 4)); CK(cudaMalloc(&d_n, 4));
+  CK(cudaMemcpyAsync(d_xyz, xyz, (size_t)K * 12, cudaMemcpyHostToDevice, c->s_comp));
+  k_select_major<<<1, 32, 0, c->s_comp>>>(K, d_xyz, d_mpos, d_mi, d_ov, d_n);
+  CK(cudaGetLastError()); c->launches++;
+  int32_t M = 0;
+  CK(cudaMemcpyAsync(&M, d_n, 4, cudaMemcpyDeviceToHost, c->s_comp));
+  CK(cudaStreamSynchronize(c->s_comp));
+  CK(cudaMemcpy(major_idx, d_mi, (size_t)M * 4, cudaMemcpyDeviceToHost));
+  if (overlap_nn) CK(cudaMemcpy(overlap_nn, d_ov, (size_t)K * 4, cudaMemcpyDeviceToHost));
+  *n_major = M;
+  cudaFree(d_xyz); cudaFree(d_mpos); cudaFree(d_mi); cudaFree(d_ov); cudaFree(d_n);
+  return 0;
+}
+
+extern "C" int bevgen_labels(bevgen_ctx* c, int K, const float* xyz, int M, const int32_t* major_idx, int row_begin, int row_end,
+                             float* labels_out, int32_t* nn_idx, float* nn_w) {
+  if (!c || !xyz || !major_idx) return fail("bevgen_labels: null argument");
+  if (K <= 0 || M <= 0) return fail("bevgen_labels: K and M must be > 0");
+  if (row_begin < 0 || row_end > K || row_begin > row_end) return fail("bevgen_labels: bad row range");
+  for (int j = 0; j < M; j++) if (major_idx[j] < 0 || major_idx[j] >= K) return fail("bevgen_labels: major index out of range");
+  const int rows = row_end - row_begin;
+  if (rows == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  float *d_xyz = 0, *d_mpos = 0, *d_w = 0, *d_dense = 0; int32_t *d_mi = 0, *d_nn = 0;
+  CK(cudaMalloc(&d_xyz, (size_t)K * 12)); CK(cudaMalloc(&d_mpos, (size_t)M * 12)); CK(cudaMalloc(&d_mi, (size_t)M * 4));
+  CK(cudaMalloc(&d_nn, (size_t)rows * 8)); CK(cudaMalloc(&d_w, (size_t)rows * 8));
+  if (labels_out) { CK(cudaMalloc(&d_dense, (size_t)rows * M * 4)); CK(cudaMemsetAsync(d_dense, 0, (size_t)rows * M * 4, c->s_comp)); }
+  CK(cudaMemcpyAsync(d_xyz, xyz, (size_t)K * 12, cudaMemcpyHostToDevice, c->s_comp));
+  CK(cudaMemcpyAsync(d_mi, major_idx, (size_t)M * 4, cudaMemcpyHostToDevice, c->s_comp));
+  k_gather_mpos<<<(M + 127) / 128, 128, 0, c->s_comp>>>(M, d_xyz, d_mi, d_mpos);
+  k_labels<<<(rows + 127) / 128, 128, 0, c->s_comp>>>(K, d_xyz, M, d_mi, d_mpos, row_begin, row_end, d_nn, d_w, d_dense);
+  CK(cudaGetLastError()); c->launches += 2;
+  CK(cudaStreamSynchronize(c->s_comp));
+  if (labels_out) CK(cudaMemcpy(labels_out, d_dense, (size_t)rows * M * 4, cudaMemcpyDeviceToHost));
+  if (nn_idx) CK(cudaMemcpy(nn_idx, d_nn, (size_t)rows * 8, cudaMemcpyDeviceToHost));
+  if (nn_w) CK(cudaMemcpy(nn_w, d_w, (size_t)rows * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d_xyz); cudaFree(d_mpos); cudaFree(d_mi); cudaFree(d_nn); cudaFree(d_w); cudaFree(d_dense);
+  return 0;
+}
+
+// ---- cloud_manip ------------------------------------------------------------------------------------------------
+extern "C" int bevgen_cloud_manip(bevgen_ctx* c, int64_t n, const float* rt, const float* x, const float* y, const float* z,
+                                  float* tx, float* ty, float* tz, float* bev_in, float* bev_out) {
+  if (!c || !rt || !x || !y || !z) return fail("bevgen_cloud_manip: null argument");
+  if (n < 0) return fail("bevgen_cloud_manip: n < 0");
+  CK(cudaSetDevice(c->device));
+  const size_t nb = (size_t)std::max<int64_t>(n, 1) * 4;
+  float* d[6] = {0, 0, 0, 0, 0, 0}; int* g[2] = {0, 0};
+  for (int i = 0; i < 6; i++) CK(cudaMalloc(&d[i], nb));
+  for (int i = 0; i < 2; i++) { CK(cudaMalloc(&g[i], MGRID * MGRID * 4)); CK(cudaMemsetAsync(g[i], 0, MGRID * MGRID * 4, c->s_comp)); }
+  CK(cudaMemcpyAsync(d[0], x, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
+  CK(cudaMemcpyAsync(d[1], y, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
+  CK(cudaMemcpyAsync(d[2], z, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
+  Xform xf; memcpy(xf.m, rt, sizeof xf.m); xf.on = 1;
+  if (n > 0) {
+    int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    k_cloud_manip<<<blocks, 256, 0, c->s_comp>>>(n, xf, d[0], d[1], d[2], d[3], d[4], d[5], bev_in ? g[0] : nullptr, bev_out ? g[1] : nullptr);
+    CK(cudaGetLastError()); c->launches++;
+  }
+  CK(cudaStreamSynchronize(c->s_comp));
+  if (tx && ty && tz) {
+    CK(cudaMemcpy(tx, d[3], (size_t)n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(ty, d[4], (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tz, d[5], (size_t)n * 4, cudaMemcpyDeviceToHost));
+  }
+  if (bev_in) CK(cudaMemcpy(bev_in, g[0], MGRID * MGRID * 4, cudaMemcpyDeviceToHost));
+  if (bev_out) CK(cudaMemcpy(bev_out, g[1], MGRID * MGRID * 4, cudaMemcpyDeviceToHost));
+  for (auto p : d) cudaFree(p);
+  for (auto p : g) cudaFree(p);
+  return 0;
+}
+
+// ---- introspection ----------------------------------------------------------------------------------------------
+extern "C" int bevgen_set_profiling(bevgen_ctx* c, int on) {
+  if (!c) return fail("null ctx");
+  c->prof = on != 0;
+  for (auto& m : c->stage_ms) m = 0; for (auto& l : c->stage_launches) l = 0;
+  return 0;
+}
+extern "C" int bevgen_stage_ms(bevgen_ctx* c, float* ms, int64_t* launches) {
+  if (!c) return fail("null ctx");
+  for (int i = 0; i < BEVGEN_N_STAGES; i++) { if (ms) ms[i] = (float)c->stage_ms[i]; if (launches) launches[i] = c->stage_launches[i]; }
+  return 0;
+}
+extern "C" int64_t bevgen_kernel_launches(bevgen_ctx* c) { return c ? c->launches : 0; }
+extern "C" void* bevgen_compute_stream(bevgen_ctx* c) { return c ? (void*)c->s_comp : nullptr; }
+
+extern "C" int bevgen_debug_atan2f(bevgen_ctx* c, int64_t n, const float* y, const float* x, float* out) {
+  if (!c || !y || !x || !out) return fail("bevgen_debug_atan2f: null argument");
+  CK(cudaSetDevice(c->device));
+  float *dy = 0, *dx = 0, *dout = 0;
+  CK(cudaMalloc(&dy, n * 4)); CK(cudaMalloc(&dx, n * 4)); CK(cudaMalloc(&dout, n * 4));
+  CK(cudaMemcpy(dy, y, n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice));
+  k_debug_atan2f<<<(unsigned)((n + 255) / 256), 256, 0, c->s_comp>>>(n, dy, dx, dout);
+  CK(cudaGetLastError()); c->launches++;
+  CK(cudaStreamSynchronize(c->s_comp));
+  CK(cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dy); cudaFree(dx); cudaFree(dout);
+  return 0;
+}

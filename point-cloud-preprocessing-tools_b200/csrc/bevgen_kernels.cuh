@@ -1,0 +1,558 @@
+// bevgen_kernels.cuh — sm_100a kernels of the batch_multi_bev_gen hot path (hand-written; no libraries).
+//
+// Reference being replaced: soytony/Point-Cloud-Preprocessing-Tools @ d94040e, BatchMultiBevGen.cpp.
+// All float arithmetic that feeds a rounding/threshold decision is written with explicit round-to-nearest
+// intrinsics (and the TU is compiled --fmad=false) because the reference is x86-64 SSE2 code without FMA
+// (CMakeLists.txt:10): every float op there is an individually rounded IEEE op.
+//
+// HBM layout per frame f of a batch (S = N_SCAN * Horizon_SCAN slots):
+//   owner [f][S]  u32   1 + winning input index per slot (0 = empty)        — output
+//   rec   [f][S]  f32x4 ordered cloud: x, y, z, w = {label:16 | I==-1:1 | owned:1} — scratch, written once
+//   gkey  [f][S]  u16   sector id (row*50+col) of slots with ground_mat == 1 after loop 1, else 0xFFFF — scratch
+//   gz    [f][S]  f32   z of those slots (0 elsewhere)                       — scratch
+//   cnt   [f][3750] u32 ground points per sector;  avg [f][3750] f32 sector mean heights — scratch
+//   label [f][S] i16, single [f][224*224] u8, multi [f][24][224*224] u8      — outputs
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bevgen {
+
+constexpr int GRID = 224;
+constexpr int CELLS = GRID * GRID;        // 50176
+constexpr int CELL_WORDS = CELLS / 4;     // 12544 u32 words of 4 cell-bytes
+constexpr int LAYERS = 24;
+constexpr int SECT_R = 75, SECT_C = 50, NSECT = SECT_R * SECT_C;
+constexpr unsigned NO_KEY = 0xFFFFu;
+constexpr unsigned W_NEG1 = 1u << 16;     // rec.w flag: intensity == -1
+constexpr unsigned W_OWNED = 1u << 17;    // rec.w flag: slot written by an input point
+
+struct SensorDev {
+  int N, H, G, S;
+  int band_row0;        // N - G - 1: first row that can carry ground_mat == 1
+  float height_res;
+  float inv_height_res; // exact when height_res is a power of two (all three sensors)
+  int hr_pow2;
+  // ground criterion constants (computed on the host at context creation, see bevgen_capi.cu)
+  float t_star;         // largest float t with (float)((double)t*180.0/M_PI) <= 10.0f   (BatchMultiBevGen.cpp:173,179)
+  float q_lo, q_hi;     // tan(t_star)*(1 -/+ 1e-5): outside [q_lo,q_hi] the decision needs no atan2f
+};
+
+struct Xform { float m[12]; int on; };
+
+// ------------------------------------------------------------------------------------------------------------
+// glibc 2.39 float atan2f / atanf (sysdeps/ieee754/flt-32/e_atan2f.c, s_atanf.c — the fdlibm algorithm),
+// restated with individually rounded float ops.  tests/test_gpu_parity.py::test_atan2f_bit_exact checks it
+// against the host libm bit for bit; oracle/ probes showed 0 mismatches in 4e8 samples for the C mirror.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float atanf_glibc(float x) {
+  const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+  const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+  const float aT0 = 3.3333334327e-01f, aT1 = -2.0000000298e-01f, aT2 = 1.4285714924e-01f, aT3 = -1.1111110449e-01f,
+              aT4 = 9.0908870101e-02f, aT5 = -7.6918758452e-02f, aT6 = 6.6610731184e-02f, aT7 = -5.8335702866e-02f,
+              aT8 = 4.9768779427e-02f, aT9 = -3.6531571299e-02f, aT10 = 1.6285819933e-02f;
+  int hx = __float_as_int(x);
+  int ix = hx & 0x7fffffff;
+  int id;
+  if (ix >= 0x4c000000) {  // |x| >= 2^25
+    if (ix > 0x7f800000) return __fadd_rn(x, x);
+    float r = __fadd_rn(atanhi[3], atanlo[3]);
+    return hx > 0 ? r : -r;
+  }
+  if (ix < 0x3ee00000) {   // |x| < 0.4375
+    if (ix < 0x31000000) return x;  // |x| < 2^-29
+    id = -1;
+  } else {
+    x = fabsf(x);
+    if (ix < 0x3f980000) {
+      if (ix < 0x3f300000) { id = 0; x = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, x), 1.0f), __fadd_rn(2.0f, x)); }
+      else                 { id = 1; x = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f)); }
+    } else {
+      if (ix < 0x401c0000) { id = 2; x = __fdiv_rn(__fsub_rn(x, 1.5f), __fadd_rn(1.0f, __fmul_rn(1.5f, x))); }
+      else                 { id = 3; x = __fdiv_rn(-1.0f, x); }
+    }
+  }
+  float z = __fmul_rn(x, x);
+  float w = __fmul_rn(z, z);
+  float s1 = __fmul_rn(z, __fadd_rn(aT0, __fmul_rn(w, __fadd_rn(aT2, __fmul_rn(w, __fadd_rn(aT4, __fmul_rn(w,
+             __fadd_rn(aT6, __fmul_rn(w, __fadd_rn(aT8, __fmul_rn(w, aT10)))))))))));
+  float s2 = __fmul_rn(w, __fadd_rn(aT1, __fmul_rn(w, __fadd_rn(aT3, __fmul_rn(w, __fadd_rn(aT5, __fmul_rn(w,
+             __fadd_rn(aT7, __fmul_rn(w, aT9)))))))));
+  float s = __fadd_rn(s1, s2);
+  if (id < 0) return __fsub_rn(x, __fmul_rn(x, s));
+  float hi = id == 0 ? atanhi[0] : id == 1 ? atanhi[1] : id == 2 ? atanhi[2] : atanhi[3];
+  float lo = id == 0 ? atanlo[0] : id == 1 ? atanlo[1] : id == 2 ? atanlo[2] : atanlo[3];
+  z = __fsub_rn(hi, __fsub_rn(__fsub_rn(__fmul_rn(x, s), lo), x));
+  return hx < 0 ? -z : z;
+}
+
+__device__ __forceinline__ float atan2f_glibc(float y, float x) {
+  const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f,
+              pi_lo = -8.7422776573e-08f;
+  int hx = __float_as_int(x), hy = __float_as_int(y);
+  int ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+  if (ix > 0x7f800000 || iy > 0x7f800000) return __fadd_rn(x, y);
+  if (hx == 0x3f800000) return atanf_glibc(y);
+  int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+  if (iy == 0) {
+    if (m < 2) return y;
+    return m == 2 ? __fadd_rn(pi, tiny) : __fsub_rn(-pi, tiny);
+  }
+  if (ix == 0) return hy < 0 ? __fsub_rn(-pi_o_2, tiny) : __fadd_rn(pi_o_2, tiny);
+  if (ix == 0x7f800000) {
+    if (iy == 0x7f800000) {
+      switch (m) {
+        case 0: return __fadd_rn(pi_o_4, tiny);
+        case 1: return __fsub_rn(-pi_o_4, tiny);
+        case 2: return __fadd_rn(__fmul_rn(3.0f, pi_o_4), tiny);
+        default: return __fsub_rn(__fmul_rn(-3.0f, pi_o_4), tiny);
+      }
+    } else {
+      switch (m) {
+        case 0: return 0.0f;
+        case 1: return -0.0f;
+        case 2: return __fadd_rn(pi, tiny);
+        default: return __fsub_rn(-pi, tiny);
+      }
+    }
+  }
+  if (iy == 0x7f800000) return hy < 0 ? __fsub_rn(-pi_o_2, tiny) : __fadd_rn(pi_o_2, tiny);
+  int k = (iy - ix) >> 23;
+  float z;
+  if (k > 60) z = __fadd_rn(pi_o_2, __fmul_rn(0.5f, pi_lo));
+  else if (hx < 0 && k < -60) z = 0.0f;
+  else z = atanf_glibc(fabsf(__fdiv_rn(y, x)));
+  switch (m) {
+    case 0: return z;
+    case 1: return -z;
+    case 2: return __fsub_rn(pi, __fsub_rn(z, pi_lo));
+    default: return __fsub_rn(__fsub_rn(z, pi_lo), pi);
+  }
+}
+
+__global__ void k_debug_atan2f(int64_t n, const float* __restrict__ y, const float* __restrict__ x, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = atan2f_glibc(y[i], x[i]);
+}
+
+// x86 cvttsd2si: what the reference binary executes for (int)double — INT_MIN for NaN / out of range.
+__device__ __forceinline__ int cvtt_x86(double v) {
+  return (v > -2147483649.0 && v < 2147483648.0) ? __double2int_rz(v) : INT32_MIN;
+}
+
+// getBelongingGrid, BatchMultiBevGen.h:73-99 -> sector id row*50+col.
+__device__ __forceinline__ unsigned sector_of(float px, float py) {
+  float nx = __double2float_rn((double)px + 75.0);   // float + double literal, stored to float (:78)
+  float ny = __double2float_rn((double)py + 50.0);
+  int sr = cvtt_x86(floor((double)nx * 0.5));        // /2.0 is exact, so is *0.5
+  int sc = cvtt_x86(floor((double)ny * 0.5));
+  sr = sr >= SECT_R ? SECT_R - 1 : sr; sr = sr < 0 ? 0 : sr;
+  sc = sc >= SECT_C ? SECT_C - 1 : sc; sc = sc < 0 ? 0 : sc;
+  return (unsigned)(sr * SECT_C + sc);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K0a order_claim — getOrderedCloud (BatchMultiBevGen.cpp:94-117), pass 1: the serial loop makes the LAST input
+// point of a slot win; atomicMax over (input index + 1) reproduces that deterministically.
+// grid (ceil(max_n/256), F), block 256.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_order_claim(SensorDev sp, const int64_t* __restrict__ offs,
+                                                      const uint16_t* __restrict__ row, const uint16_t* __restrict__ col,
+                                                      uint32_t* __restrict__ owner) {
+  const int f = blockIdx.y;
+  const int64_t o = offs[f];
+  const int n = (int)(offs[f + 1] - o);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const unsigned r = row[o + i], c = col[o + i];
+  if (r >= (unsigned)sp.N || c >= (unsigned)sp.H) return;           // :106-111
+  atomicMax(&owner[(size_t)f * sp.S + r * sp.H + c], (uint32_t)(i + 1));
+}
+
+// K0b order_fill — pass 2: winners write their record, unowned slots get the value-initialised record (:98).
+// Optional rigid transform (pcl::transformPointCloud, PCL>=1.9 SSE order p0 + (p1 + (p2 + t)), CloudManip.cpp:128).
+// grid (ceil(max(max_n,S)/256), F), block 256.
+__global__ void __launch_bounds__(256) k_order_fill(SensorDev sp, Xform xf, const int64_t* __restrict__ offs,
+                                                     const float* __restrict__ x, const float* __restrict__ y,
+                                                     const float* __restrict__ z, const float* __restrict__ inten,
+                                                     const uint16_t* __restrict__ row, const uint16_t* __restrict__ col,
+                                                     const int16_t* __restrict__ label, const uint32_t* __restrict__ owner,
+                                                     float4* __restrict__ rec) {
+  const int f = blockIdx.y;
+  const int64_t o = offs[f];
+  const int n = (int)(offs[f + 1] - o);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const size_t fb = (size_t)f * sp.S;
+  if (i < sp.S && owner[fb + i] == 0) rec[fb + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n) {
+    const unsigned r = row[o + i], c = col[o + i];
+    if (r < (unsigned)sp.N && c < (unsigned)sp.H) {
+      const size_t slot = fb + r * sp.H + c;
+      if (owner[slot] == (uint32_t)(i + 1)) {
+        float px = x[o + i], py = y[o + i], pz = z[o + i];
+        if (xf.on) {
+          float ox = __fadd_rn(__fmul_rn(px, xf.m[0]), __fadd_rn(__fmul_rn(py, xf.m[1]), __fadd_rn(__fmul_rn(pz, xf.m[2]), xf.m[3])));
+          float oy = __fadd_rn(__fmul_rn(px, xf.m[4]), __fadd_rn(__fmul_rn(py, xf.m[5]), __fadd_rn(__fmul_rn(pz, xf.m[6]), xf.m[7])));
+          float oz = __fadd_rn(__fmul_rn(px, xf.m[8]), __fadd_rn(__fmul_rn(py, xf.m[9]), __fadd_rn(__fmul_rn(pz, xf.m[10]), xf.m[11])));
+          px = ox; py = oy; pz = oz;
+        }
+        unsigned w = (unsigned)(uint16_t)label[o + i] | W_OWNED | (inten[o + i] == -1.0f ? W_NEG1 : 0u);
+        rec[slot] = make_float4(px, py, pz, __uint_as_float(w));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1 ground_mark — markGroundPoints loop 1 (BatchMultiBevGen.cpp:139-184).  One thread per range-image column,
+// walking rows N-1 .. N-G like the reference; consecutive lanes = consecutive columns, so every record load is a
+// coalesced 512-byte warp access and the "upper" record is reused as the next "lower".
+// Closed form of the row-descending overwrite order:  gm[r] = -1 if invalid(r) else (ground(r) | ground(r+1)).
+// Emits gkey / gz for rows [N-G-1, N) and warp-aggregated per-sector counts (loop 2's `num`, :205).
+// grid (ceil(H/128), F), block 128.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_neg1(const float4& p) { return (__float_as_uint(p.w) & W_NEG1) != 0; }
+
+__device__ __forceinline__ bool ground_decision(const SensorDev& sp, const float4& up, const float4& lo) {
+  float dx = __fsub_rn(up.x, lo.x), dy = __fsub_rn(up.y, lo.y), dz = __fsub_rn(up.z, lo.z);      // :169-171
+  float hyp = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));                        // :173 sqrtf
+  float q = __fdiv_rn(fabsf(dz), hyp);
+  if (q <= sp.q_lo) return true;     // far inside 10 degrees: |atan2f| < t_star without evaluating it
+  if (q >= sp.q_hi) return false;    // far outside
+  float t = atan2f_glibc(dz, hyp);   // borderline / NaN / 0-over-0: the exact libm value decides
+  return fabsf(t) <= sp.t_star;      // <=> fabsf((float)((double)t*180.0/M_PI)) <= 10.0f  (:173,:179)
+}
+
+__global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4* __restrict__ rec,
+                                                      uint16_t* __restrict__ gkey, float* __restrict__ gz,
+                                                      uint32_t* __restrict__ cnt) {
+  const int f = blockIdx.y;
+  const int c0 = blockIdx.x * 128 + threadIdx.x;
+  const bool act = c0 < sp.H;
+  const int c = act ? c0 : sp.H - 1;
+  const int lane = threadIdx.x & 31;
+  const int H = sp.H, N = sp.N;
+  const size_t fb = (size_t)f * sp.S;
+  const float4* R = rec + fb;
+
+  auto emit = [&](int r, const float4& p, bool gm1) {
+    unsigned key = NO_KEY;
+    if (gm1) key = sector_of(p.x, p.y);
+    if (act) {
+      gkey[fb + (size_t)r * H + c] = (uint16_t)key;
+      gz[fb + (size_t)r * H + c] = gm1 ? p.z : 0.0f;
+    }
+    unsigned k2 = (act && gm1) ? key : (0x10000u | lane);   // inactive lanes never group
+    unsigned peers = __match_any_sync(0xffffffffu, k2);
+    if (act && gm1 && lane == __ffs(peers) - 1) atomicAdd(&cnt[(size_t)f * NSECT + key], (uint32_t)__popc(peers));
+  };
+
+  float4 lower = R[(size_t)(N - 1) * H + c];
+  bool ground_prev = false;
+  for (int r = N - 1; r > N - sp.G - 1; --r) {
+    const float4 direct = R[(size_t)(r - 1) * H + c];
+    float4 up = direct;
+    if (is_neg1(up)) up = R[(size_t)(r - 1) * H + ((c + 2) % H)];                 // :146-149
+    if (is_neg1(up)) up = R[(size_t)((r - 1) * H + (c - 2))];                     // :151-154, C++ % keeps c-2 negative for c<2
+    if (is_neg1(up) && r >= 2) up = R[(size_t)(r - 2) * H + c];                   // :157-160
+    const bool invalid = is_neg1(lower) || is_neg1(up);                           // :162
+    const bool ground = !invalid && ground_decision(sp, up, lower);
+    emit(r, lower, !invalid && (ground || ground_prev));
+    ground_prev = ground;
+    lower = direct;
+  }
+  emit(N - sp.G - 1, lower, ground_prev);   // row above the band only receives gm[row-1] = 1 (:181)
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2 sector_mean — markGroundPoints loop 2 + divide (:187-210).  The reference accumulates
+// ground_grid_avg_heights[sector] += z serially in row-major slot order: float addition is not associative, so the
+// per-sector order must be kept.  One warp sweeps one frame in slot order, 32 slots per step; inside a step each
+// sector group (match_any) is folded sequentially by its lowest lane from shared-memory accumulators.  Adding
+// +-0 never changes a (never -0) sum, so empty/zero-height ground slots are skipped; the count is order-free and
+// comes from K1.  num = 0.01f + 1 + 1 ... is a pure function of the count: cnt_lut[n].
+// grid F, block 32, dynamic smem NSECT*4.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t* __restrict__ gkey,
+                                                     const float* __restrict__ gz, const uint32_t* __restrict__ cnt,
+                                                     const float* __restrict__ cnt_lut, float* __restrict__ avg) {
+  extern __shared__ float ssum[];
+  __shared__ float zb[32];
+  const int f = blockIdx.x, lane = threadIdx.x;
+  for (int i = lane; i < NSECT; i += 32) ssum[i] = 0.0f;
+  __syncwarp();
+  const size_t fb = (size_t)f * sp.S;
+  const uint16_t* K = gkey + fb;
+  const float* Z = gz + fb;
+  constexpr int U = 4;
+  for (int base = sp.band_row0 * sp.H; base < sp.S; base += 32 * U) {
+    unsigned k[U]; float zz[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int idx = base + u * 32 + lane;
+      bool in = idx < sp.S;
+      k[u] = in ? (unsigned)K[idx] : NO_KEY;
+      zz[u] = in ? Z[idx] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const bool nz = (k[u] != NO_KEY) && (zz[u] != 0.0f);
+      if (__ballot_sync(0xffffffffu, nz) == 0) continue;
+      unsigned peers = __match_any_sync(0xffffffffu, nz ? k[u] : (0x10000u | lane));
+      zb[lane] = zz[u];
+      __syncwarp();
+      if (nz && lane == __ffs(peers) - 1) {
+        float acc = ssum[k[u]];
+        unsigned p = peers;
+        while (p) { int j = __ffs(p) - 1; p &= p - 1; acc = __fadd_rn(acc, zb[j]); }   // :198, in slot order
+        ssum[k[u]] = acc;
+      }
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < NSECT; i += 32)
+    avg[(size_t)f * NSECT + i] = __fdiv_rn(ssum[i], cnt_lut[cnt[(size_t)f * NSECT + i]]);   // :210 IEEE divide
+}
+
+// num_ground_grid_points replay (:135, :205): lut[n] = fl(...fl(fl(0.01f + 1) + 1)... + 1), n additions.
+__global__ void k_build_cnt_lut(int n_max, float* __restrict__ lut) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float c = (float)0.01;
+    lut[0] = c;
+    for (int i = 1; i <= n_max; i++) { c = __fadd_rn(c, 1.0f); lut[i] = c; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3+K4 finalize_bin_scatter — markGroundPoints loop 3 (:216-250) fused with the binning of both BEVs
+// (:278-292, :342-356), the scatter and the expansion to the reference's byte layout.
+// One CTA per frame owns the frame's whole 224x224 grid in shared memory:
+//   occ  3 planes x 50176 bytes: bit (layer&7) of plane (layer>>3) = cell occupied in that layer
+//   hgt  50176 bytes: running max height
+// updates are check-first (plain read, atomic only if it would change the word), OR / byte-max are order-free so
+// the result is deterministic.  Flush = coalesced 16-byte stores: single <- hgt, multi[layer] <- bit ? 255 : 0.
+// grid F, block 1024, dynamic smem SMEM_BIN.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SAVG_BYTES = 15008;                                   // 3750 floats, padded to 16
+constexpr int SMEM_BIN = SAVG_BYTES + 4 * CELLS;                    // 215,712 B
+
+__global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const float4* __restrict__ rec,
+                                                           const uint16_t* __restrict__ gkey, const float* __restrict__ avg,
+                                                           int16_t* __restrict__ label_out, uint8_t* __restrict__ single,
+                                                           uint8_t* __restrict__ multi) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* savg = reinterpret_cast<float*>(smem);
+  uint32_t* occ = reinterpret_cast<uint32_t*>(smem + SAVG_BYTES);   // [3][CELL_WORDS]
+  uint32_t* hgt = occ + 3 * CELL_WORDS;                             // [CELL_WORDS]
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const size_t fb = (size_t)f * sp.S;
+
+  for (int i = tid; i < CELL_WORDS; i += 1024) reinterpret_cast<uint4*>(occ)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < NSECT; i += 1024) savg[i] = avg[(size_t)f * NSECT + i];
+  __syncthreads();
+
+  const float4* R = rec + fb;
+  const uint16_t* K = gkey + fb;
+  const int first = sp.band_row0 * sp.H;
+  for (int slot = tid; slot < sp.S; slot += 1024) {
+    const float4 p = R[slot];
+    int16_t lab = (int16_t)(__float_as_uint(p.w) & 0xFFFFu);
+    if (slot >= first) {
+      const unsigned key = K[slot];
+      if (key != NO_KEY) {                       // ground_mat == 1 after loop 1
+        const int sr = key / SECT_C, sc = key - sr * SECT_C;
+        bool cleared = false;
+        // neighbour order (-1,0),(0,1),(0,-1),(1,0) (:73-84); (double)(z - avg) > 0.30  <=>  (z - avg) >= 0.3f
+        // because 0.3f is the smallest float above the double 0.30 (:236-237)
+        if (sr - 1 >= 0)      cleared = __fsub_rn(p.z, savg[key - SECT_C]) >= 0.3f;
+        if (!cleared && sc + 1 < SECT_C) cleared = __fsub_rn(p.z, savg[key + 1]) >= 0.3f;
+        if (!cleared && sc - 1 >= 0)     cleared = __fsub_rn(p.z, savg[key - 1]) >= 0.3f;
+        if (!cleared && sr + 1 < SECT_R) cleared = __fsub_rn(p.z, savg[key + SECT_C]) >= 0.3f;
+        if (!cleared) lab = 0;                   // :244-245
+      }
+    }
+    label_out[fb + slot] = lab;
+    if (lab == 0) continue;                      // :285 / :349
+    const float vx = __fadd_rn(p.x, 112.0f), vy = __fadd_rn(p.y, 112.0f);   // (pi.x + MAX_RANGE) / 1.0f
+    // x = round(v + 0.5) in double, valid 0..223  <=>  -1 < v < 223 and then x = floor(v) + 1   (:279-284)
+    if (!(vx > -1.0f && vx < 223.0f && vy > -1.0f && vy < 223.0f)) continue;
+    const int cell = (__float2int_rd(vx) + 1) * GRID + (__float2int_rd(vy) + 1);
+    const int sh = (cell & 3) * 8;
+    // single: height = clamp(int((z + 2.0f) * 4.0), 0, 255); the double product of a float by 4 is exact (:345-346)
+    const float b = __fmul_rn(__fadd_rn(p.z, 2.0f), 4.0f);
+    int h = 0;
+    if (b < 2147483648.0f && b > 0.0f) { h = __float2int_rz(b); h = h > 255 ? 255 : h; }
+    if (h > 0) {
+      uint32_t* wp = &hgt[cell >> 2];
+      uint32_t old = *reinterpret_cast<volatile uint32_t*>(wp);
+      while (((old >> sh) & 0xFFu) < (uint32_t)h) {
+        const uint32_t nw = (old & ~(0xFFu << sh)) | ((uint32_t)h << sh);
+        const uint32_t prev = atomicCAS(wp, old, nw);
+        if (prev == old) break;
+        old = prev;
+      }
+    }
+    // multi: layer = round(z / HEIGHT_RES + 2.0f), half away from zero, valid 0..23 <=> -0.5 < w < 23.5   (:281-284)
+    const float w = __fadd_rn(sp.hr_pow2 ? __fmul_rn(p.z, sp.inv_height_res) : __fdiv_rn(p.z, sp.height_res), 2.0f);
+    if (w > -0.5f && w < 23.5f) {
+      const float t = truncf(w);
+      const int layer = (int)t + (__fsub_rn(w, t) >= 0.5f ? 1 : 0);
+      uint32_t* wp = &occ[(layer >> 3) * CELL_WORDS + (cell >> 2)];
+      const uint32_t bit = (1u << (layer & 7)) << sh;
+      if (!(*reinterpret_cast<volatile uint32_t*>(wp) & bit)) atomicOr(wp, bit);
+    }
+  }
+  __syncthreads();
+
+  uint4* so = reinterpret_cast<uint4*>(single + (size_t)f * CELLS);
+  for (int i = tid; i < CELL_WORDS / 4; i += 1024) so[i] = reinterpret_cast<const uint4*>(hgt)[i];
+  uint4* mo = reinterpret_cast<uint4*>(multi + (size_t)f * LAYERS * CELLS);
+  constexpr int Q = CELL_WORDS / 4;   // uint4 per layer = 3136
+  for (int i = tid; i < LAYERS * Q; i += 1024) {
+    const int layer = i / Q, q = i - layer * Q;
+    const uint4 v = reinterpret_cast<const uint4*>(occ + (layer >> 3) * CELL_WORDS)[q];
+    const int l = layer & 7;
+    uint4 o;
+    o.x = ((v.x >> l) & 0x01010101u) * 255u; o.y = ((v.y >> l) & 0x01010101u) * 255u;
+    o.z = ((v.z >> l) & 0x01010101u) * 255u; o.w = ((v.w >> l) & 0x01010101u) * 255u;
+    mo[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K5 pose labels.  d2 = ((dx*dx) + dy*dy) + dz*dz with d = query - major, all float, exactly
+// nanoflann L2_Adaptor::evalMetric for dim 3 (include/nanoflann.hpp:383-407) and getDistance (src/Utility.cpp:43-49).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float d2_pose(float qx, float qy, float qz, const float* m) {
+  float dx = __fsub_rn(qx, m[0]), dy = __fsub_rn(qy, m[1]), dz = __fsub_rn(qz, m[2]);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// selectMajorFrames (BatchMultiBevGen.cpp:502-566): an inherently serial greedy scan over keyframes; one warp walks
+// it, the 1-NN over the current majors is split across lanes (lowest index wins ties).  grid 1, block 32.
+__global__ void __launch_bounds__(32) k_select_major(int K, const float* __restrict__ xyz, float* __restrict__ mpos,
+                                                      int32_t* __restrict__ major_idx, int32_t* __restrict__ overlap,
+                                                      int32_t* __restrict__ n_major) {
+  const int lane = threadIdx.x;
+  int M = 0;
+  if (K <= 0) { if (lane == 0) *n_major = 0; return; }
+  if (lane == 0) { major_idx[0] = 0; mpos[0] = xyz[0]; mpos[1] = xyz[1]; mpos[2] = xyz[2]; overlap[0] = -1; }
+  M = 1;
+  __syncwarp();
+  for (int i = 1; i < K; i++) {
+    const float qx = xyz[3 * i], qy = xyz[3 * i + 1], qz = xyz[3 * i + 2];
+    const float dl = __fsqrt_rn(d2_pose(qx, qy, qz, mpos + 3 * (M - 1)));   // getDistance to the last major (:527)
+    if (dl < 20.0f) { if (lane == 0) overlap[i] = -2; continue; }           // :528
+    float best = 3.402823466e+38f; int bj = 0x7fffffff;
+    for (int j = lane; j < M; j += 32) {
+      float d = d2_pose(qx, qy, qz, mpos + 3 * j);
+      if (d < best) { best = d; bj = j; }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, best, s); int oj = __shfl_xor_sync(0xffffffffu, bj, s);
+      if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+    }
+    if (best < 400.0f) { if (lane == 0) overlap[i] = bj; continue; }        // :552
+    if (lane == 0) { major_idx[M] = i; mpos[3 * M] = qx; mpos[3 * M + 1] = qy; mpos[3 * M + 2] = qz; overlap[i] = -1; }
+    M++;
+    __syncwarp();
+  }
+  if (lane == 0) *n_major = M;
+}
+
+// getKeyFrameLabel (BatchMultiBevGen.cpp:575-636): one thread per keyframe row, majors tiled through smem,
+// 2-NN with KNNResultSet semantics (strict '>' insertion => lowest index first on ties), weights in the
+// reference's float/double mix.  Writes the two non-zeros (sparse) and, if dense != NULL, scatters them into the
+// zero-filled dense rows.  grid ceil(rows/128), block 128.
+__global__ void __launch_bounds__(128) k_labels(int K, const float* __restrict__ xyz, int M, const int32_t* __restrict__ major_idx,
+                                                 const float* __restrict__ mpos, int row_begin, int row_end,
+                                                 int32_t* __restrict__ nn_idx, float* __restrict__ nn_w, float* __restrict__ dense) {
+  __shared__ float sm[128 * 3];
+  const int r = row_begin + blockIdx.x * 128 + threadIdx.x;
+  const bool act = r < row_end;
+  float qx = 0, qy = 0, qz = 0;
+  if (act) { qx = xyz[3 * r]; qy = xyz[3 * r + 1]; qz = xyz[3 * r + 2]; }
+  float d0 = 0.0f, d1 = 3.402823466e+38f;  // dists[capacity-1] = max (nanoflann.hpp:164-165); vectors value-init to 0
+  int c0 = 0, c1 = 0, count = 0;
+  for (int base = 0; base < M; base += 128) {
+    const int nt = min(128, M - base);
+    __syncthreads();
+    for (int t = threadIdx.x; t < nt * 3; t += 128) sm[t] = mpos[3 * base + t];
+    __syncthreads();
+    if (act) {
+      for (int j = 0; j < nt; j++) {
+        const float d = d2_pose(qx, qy, qz, sm + 3 * j);
+        if (!(d < d1)) continue;                       // `dist < worst_dist` gate (nanoflann.hpp:1358)
+        if (count == 0) { d0 = d; c0 = base + j; count = 1; }
+        else if (d0 > d) { d1 = d0; c1 = c0; d0 = d; c0 = base + j; count = 2; }
+        else { d1 = d; c1 = base + j; count = 2; }
+      }
+    }
+  }
+  if (!act) return;
+  const int o = r - row_begin;
+  float w0, w1; int i1 = c1;
+  if (r == major_idx[c0]) { w0 = 1.0f; w1 = 0.0f; i1 = -1; }                     // :616-618
+  else {
+    w0 = __double2float_rn(1.0 / ((double)d0 + 1e-5));                          // :623
+    w1 = __double2float_rn(1.0 / ((double)d1 + 1e-5));                          // :624
+    const float s = __fadd_rn(w0, w1);
+    w0 = __fdiv_rn(w0, s); w1 = __fdiv_rn(w1, s);
+  }
+  if (nn_idx) { nn_idx[2 * o] = c0; nn_idx[2 * o + 1] = i1; }
+  if (nn_w) { nn_w[2 * o] = w0; nn_w[2 * o + 1] = w1; }
+  if (dense) {
+    dense[(size_t)o * M + c0] = w0;                                             // :618 / :629
+    if (i1 >= 0) dense[(size_t)o * M + i1] = w1;                                // :630 (M == 1: overwrites index 0)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// cloud_manip (BASELINE config #5): rigid transform (CloudManip.cpp:128) + saveAsMat max grid (:79-95) of the input
+// and of the transformed cloud.  Cells start at 0 and only strictly larger values are stored, so stored values are
+// positive floats and an int atomicMax on the bit pattern is an exact, order-free float max.  Lanes that hit the
+// same cell are folded first (match_any + shuffle max) so hot cells cost one atomic per warp.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int MGRID = 201;
+
+__device__ __forceinline__ void manip_scatter(float px, float py, float pz, bool valid, int* __restrict__ grid) {
+  const float vx = __fadd_rn(px, 100.0f), vy = __fadd_rn(py, 100.0f);
+  const float v = __fadd_rn(pz, 2.0f);
+  const bool in = valid && vx > -1.0f && vx < 200.0f && vy > -1.0f && vy < 200.0f && v > 0.0f;
+  const int lane = threadIdx.x & 31;
+  const int cell = in ? (__float2int_rd(vx) + 1) * MGRID + (__float2int_rd(vy) + 1) : -1 - lane;
+  const unsigned peers = __match_any_sync(0xffffffffu, cell);
+  int m = __float_as_int(v);
+  // fold the group's max into its lowest lane: positive floats order like their int patterns
+  int best = m;
+  unsigned p = peers & ~(1u << lane);
+  while (__any_sync(0xffffffffu, p != 0)) {
+    const int j = p ? __ffs(p) - 1 : lane;
+    const int o = __shfl_sync(0xffffffffu, m, j);
+    if (p) { best = max(best, o); p &= p - 1; }
+  }
+  if (in && lane == __ffs(peers) - 1) {
+    if (*reinterpret_cast<volatile int*>(&grid[cell]) < best) atomicMax(&grid[cell], best);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cloud_manip(int64_t n, Xform xf, const float* __restrict__ x, const float* __restrict__ y,
+                                                      const float* __restrict__ z, float* __restrict__ tx, float* __restrict__ ty,
+                                                      float* __restrict__ tz, int* __restrict__ bev_in, int* __restrict__ bev_out) {
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  const int64_t n_pad = (n + 31) & ~(int64_t)31;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_pad; i += stride) {
+    const bool valid = i < n;
+    float px = 0, py = 0, pz = 0;
+    if (valid) { px = x[i]; py = y[i]; pz = z[i]; }
+    const float ox = __fadd_rn(__fmul_rn(px, xf.m[0]), __fadd_rn(__fmul_rn(py, xf.m[1]), __fadd_rn(__fmul_rn(pz, xf.m[2]), xf.m[3])));
+    const float oy = __fadd_rn(__fmul_rn(px, xf.m[4]), __fadd_rn(__fmul_rn(py, xf.m[5]), __fadd_rn(__fmul_rn(pz, xf.m[6]), xf.m[7])));
+    const float oz = __fadd_rn(__fmul_rn(px, xf.m[8]), __fadd_rn(__fmul_rn(py, xf.m[9]), __fadd_rn(__fmul_rn(pz, xf.m[10]), xf.m[11])));
+    if (valid && tx) { tx[i] = ox; ty[i] = oy; tz[i] = oz; }
+    if (bev_in) manip_scatter(px, py, pz, valid, bev_in);
+    if (bev_out) manip_scatter(ox, oy, oz, valid, bev_out);
+  }
+}
+
+}  // namespace bevgen
