@@ -277,7 +277,6 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
                                                      const float* __restrict__ gz, const uint32_t* __restrict__ cnt,
                                                      const float* __restrict__ cnt_lut, float* __restrict__ avg) {
   extern __shared__ float ssum[];
-  __shared__ float zb[32];
   const int f = blockIdx.x, lane = threadIdx.x;
   for (int i = lane; i < NSECT; i += 32) ssum[i] = 0.0f;
   __syncwarp();
@@ -285,28 +284,39 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
   const uint16_t* K = gkey + fb;
   const float* Z = gz + fb;
   constexpr int U = 4;
-  for (int base = sp.band_row0 * sp.H; base < sp.S; base += 32 * U) {
-    unsigned k[U]; float zz[U];
+  unsigned k[U], kn[U]; float zz[U], zn[U];
+  auto load = [&](int base, unsigned* kk, float* zv) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      int idx = base + u * 32 + lane;
-      bool in = idx < sp.S;
-      k[u] = in ? (unsigned)K[idx] : NO_KEY;
-      zz[u] = in ? Z[idx] : 0.0f;
+      const int idx = base + u * 32 + lane;
+      const bool in = idx < sp.S;
+      kk[u] = in ? (unsigned)K[idx] : NO_KEY;
+      zv[u] = in ? Z[idx] : 0.0f;
     }
+  };
+  int base = sp.band_row0 * sp.H;
+  load(base, kn, zn);
+  for (; base < sp.S; base += 32 * U) {
+#pragma unroll
+    for (int u = 0; u < U; u++) { k[u] = kn[u]; zz[u] = zn[u]; }
+    if (base + 32 * U < sp.S) load(base + 32 * U, kn, zn);     // next group's loads fly during this group's chains
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const bool nz = (k[u] != NO_KEY) && (zz[u] != 0.0f);
-      if (__ballot_sync(0xffffffffu, nz) == 0) continue;
-      unsigned peers = __match_any_sync(0xffffffffu, nz ? k[u] : (0x10000u | lane));
-      zb[lane] = zz[u];
-      __syncwarp();
-      if (nz && lane == __ffs(peers) - 1) {
-        float acc = ssum[k[u]];
-        unsigned p = peers;
-        while (p) { int j = __ffs(p) - 1; p &= p - 1; acc = __fadd_rn(acc, zb[j]); }   // :198, in slot order
-        ssum[k[u]] = acc;
+      unsigned m = __ballot_sync(0xffffffffu, nz);
+      if (m == 0) continue;
+      const unsigned peers = __match_any_sync(0xffffffffu, nz ? k[u] : (0x10000u | lane));
+      const bool leader = nz && lane == __ffs(peers) - 1;
+      float acc = leader ? ssum[k[u]] : 0.0f;
+      // warp-uniform walk over the contributing lanes in slot order; lane j's z is broadcast and only the leader of
+      // j's sector group folds it in: acc = fl(acc + z)   (:198)
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const float zj = __shfl_sync(0xffffffffu, zz[u], j);
+        if (leader && ((peers >> j) & 1u)) acc = __fadd_rn(acc, zj);
       }
+      if (leader) ssum[k[u]] = acc;
       __syncwarp();
     }
   }

@@ -1,0 +1,56 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol include/bevgen.h declares, and the
+product path fails loudly (no CPU fallback) when no GPU is present.  No compute calls here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "bevgen.h")).read()
+    return sorted(set(re.findall(r"BEVGEN_API[^;(]*?\b(bevgen_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    L = pkg.lib()
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(pkg.EXPORTS) == syms
+
+
+def test_sensor_params_match_reference_table(pkg):
+    for name, exp in (("HDL_32E", (32, 1056, 20, 0.5)), ("HDL_64E", (64, 2083, 50, 0.25)), ("OS1_64", (64, 1024, 31, 1.0)),
+                      ("my_HDL_64E_run", (64, 2083, 50, 0.25))):
+        p = pkg.sensor_params(name)
+        assert (p.n_scan, p.horizon_scan, p.ground_upper_scan, p.height_res) == exp
+        assert (p.grid_size, p.max_range, p.n_layers, p.lidar_to_ground, p.has_transform) == (224, 112, 24, 2.0, 0)
+    with pytest.raises(pkg.BevgenError, match="Unknown sensor type"):
+        pkg.sensor_params("VLP16")
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.BevgenError, match="no CUDA device"):
+        pkg.BevGen("HDL_64E")
+
+
+def test_product_does_not_touch_the_oracle():
+    """The product path must not import, link or execute anything under oracle/."""
+    pk = os.path.join(ROOT, "point-cloud-preprocessing-tools_b200")
+    for dp, _, fs in os.walk(pk):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                s = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle_lib" not in s and "bevgen_oracle" not in s and "load_oracle" not in s, os.path.join(dp, f)
+
+
+def test_cuda_sources_target_sm100a():
+    mk = open(os.path.join(ROOT, "point-cloud-preprocessing-tools_b200", "Makefile")).read()
+    assert "arch=compute_100a,code=sm_100a" in mk and "--fmad=false" in mk and "use_fast_math" not in mk

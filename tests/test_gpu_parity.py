@@ -37,8 +37,8 @@ def test_kitti_quirk_all_intensity_minus_one(gens, synth, O):
     out = gens("HDL_64E", max_frames_per_batch=4).process_host(batch)
     ref = oracle_batch(O, "HDL_64E", batch)
     assert_same(out, ref, "kitti")
-    # every pair is invalid => nothing is ground => labels keep their input value where a point landed
-    assert (ref["label"][ref["owner"] > 0] == -2).all()
+    # nearly every pair is invalid (valid points all carry intensity -1) => ground removal is almost a no-op
+    assert (ref["label"][ref["owner"] > 0] == -2).mean() > 0.95
 
 
 def _rand_frame(rng, N, H, n, spread=60.0, zlo=-3.0, zhi=6.0, p_neg1=0.05, col_over=True):
