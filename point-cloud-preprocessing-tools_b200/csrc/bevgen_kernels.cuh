@@ -242,15 +242,17 @@ __global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4*
       gkey[fb + (size_t)r * H + c] = (uint16_t)key;
       gz[fb + (size_t)r * H + c] = gm1 ? p.z : 0.0f;
     }
-    unsigned k2 = (act && gm1) ? key : (0x10000u | lane);   // inactive lanes never group
+    unsigned k2 = (act && gm1) ? key : 0x10000u;   // all non-ground lanes share one dummy group (never a leader)
     unsigned peers = __match_any_sync(0xffffffffu, k2);
     if (act && gm1 && lane == __ffs(peers) - 1) atomicAdd(&cnt[(size_t)f * NSECT + key], (uint32_t)__popc(peers));
   };
 
   float4 lower = R[(size_t)(N - 1) * H + c];
+  float4 nxt = R[(size_t)(N - 2) * H + c];
   bool ground_prev = false;
   for (int r = N - 1; r > N - sp.G - 1; --r) {
-    const float4 direct = R[(size_t)(r - 1) * H + c];
+    const float4 direct = nxt;
+    if (r - 2 >= 0) nxt = R[(size_t)(r - 2) * H + c];   // next iteration's upper: in flight during this row's math
     float4 up = direct;
     if (is_neg1(up)) up = R[(size_t)(r - 1) * H + ((c + 2) % H)];                 // :146-149
     if (is_neg1(up)) up = R[(size_t)((r - 1) * H + (c - 2))];                     // :151-154, C++ % keeps c-2 negative for c<2
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
       const bool nz = (k[u] != NO_KEY) && (zz[u] != 0.0f);
       unsigned m = __ballot_sync(0xffffffffu, nz);
       if (m == 0) continue;
-      const unsigned peers = __match_any_sync(0xffffffffu, nz ? k[u] : (0x10000u | lane));
+      const unsigned peers = __match_any_sync(0xffffffffu, nz ? k[u] : 0x10000u);   // MATCH cost grows with #distinct values
       const bool leader = nz && lane == __ffs(peers) - 1;
       float acc = leader ? ssum[k[u]] : 0.0f;
       // warp-uniform walk over the contributing lanes in slot order; lane j's z is broadcast and only the leader of
@@ -364,11 +366,23 @@ __global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const fl
   const float4* R = rec + fb;
   const uint16_t* K = gkey + fb;
   const int first = sp.band_row0 * sp.H;
-  for (int slot = tid; slot < sp.S; slot += 1024) {
-    const float4 p = R[slot];
+  constexpr int UB = 4;
+  for (int slot0 = tid; slot0 < sp.S; slot0 += 1024 * UB) {
+   float4 pv[UB]; unsigned kv[UB];
+#pragma unroll
+   for (int u = 0; u < UB; u++) {
+     const int sl = slot0 + u * 1024;
+     pv[u] = sl < sp.S ? R[sl] : make_float4(0.f, 0.f, 0.f, 0.f);
+     kv[u] = (sl < sp.S && sl >= first) ? (unsigned)K[sl] : NO_KEY;
+   }
+#pragma unroll
+   for (int u = 0; u < UB; u++) {
+    const int slot = slot0 + u * 1024;
+    if (slot >= sp.S) break;
+    const float4 p = pv[u];
     int16_t lab = (int16_t)(__float_as_uint(p.w) & 0xFFFFu);
-    if (slot >= first) {
-      const unsigned key = K[slot];
+    {
+      const unsigned key = kv[u];
       if (key != NO_KEY) {                       // ground_mat == 1 after loop 1
         const int sr = key / SECT_C, sc = key - sr * SECT_C;
         bool cleared = false;
@@ -411,6 +425,7 @@ __global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const fl
       const uint32_t bit = (1u << (layer & 7)) << sh;
       if (!(*reinterpret_cast<volatile uint32_t*>(wp) & bit)) atomicOr(wp, bit);
     }
+  }
   }
   __syncthreads();
 

@@ -158,11 +158,16 @@ def test_submit_collect_and_device_path(gens, synth, O, pkg):
     ref = oracle_batch(O, sensor, batch)
     g = gens(sensor, max_frames_per_batch=4, max_points_per_frame=33792 * 2)
     offs = batch["offsets"]
-    for f in range(5):
-        g.submit(100 + f, {k: batch[k][offs[f]:offs[f + 1]] for k in FIELDS})
-    for f in (4, 0, 2, 1, 3):
-        o = g.collect(100 + f)
-        assert_same({k: v[None] for k, v in o.items()}, {k: v[f:f + 1] for k, v in ref.items()}, "submit/collect %d" % f)
+    fr = lambda f: {k: batch[k][offs[f]:offs[f + 1]] for k in FIELDS}
+    chk = lambda f, o: assert_same({k: v[None] for k, v in o.items()}, {k: v[f:f + 1] for k, v in ref.items()}, "submit/collect %d" % f)
+    for f in range(4):                               # ring holds max_frames_per_batch (4) frames
+        g.submit(100 + f, fr(f))
+    with pytest.raises(pkg.BevgenError, match="ring full"):
+        g.submit(104, fr(4))
+    chk(2, g.collect(102))                           # out-of-order collect frees a slot
+    g.submit(104, fr(4))
+    for f in (4, 0, 1, 3):
+        chk(f, g.collect(100 + f))
     with pytest.raises(pkg.BevgenError):
         g.collect(999)
     # device-resident path: torch only owns the device memory
