@@ -1,0 +1,436 @@
+// batch_multi_bev_gen — drop-in replacement of the reference tool of the same name
+// (soytony/Point-Cloud-Preprocessing-Tools, BatchMultiBevGen.cpp:664-771): same positional arguments
+// `[keyframes_root_dir] [sensor_type]`, same inputs (keyframe_point_cloud/*.pcd, keyframe_pose.csv), same outputs
+// (non_ground_point_cloud/, output_multi_bev/{binary,image}/, output_single_bev/{csv,image}/, keyframe_label.csv) and
+// the same progress lines on stdout.  The per-frame arithmetic runs on B200 GPUs through the C-ABI of
+// libbevgen_cuda.so (include/bevgen.h); this file is only host plumbing:
+//   loader pool (PCD parse)  ->  per-GPU worker (pack into pinned SoA, bevgen_process_host)  ->  encode pool
+//   (bin / 25 PNG / CSV / PCD), so file encoding is off the GPU critical path.  Frames shard over GPUs by batch index;
+//   label rows are split per GPU and gathered on the host; no collective.
+// Extra trailing options (not in the reference): --gpus N, --batch B, --threads T, --no-encode, --no-pcd,
+//   --png-level L, --json-metrics FILE.
+#include <dirent.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <filesystem>
+#include <fstream>
+#include <functional>
+#include <future>
+#include <iostream>
+#include <iterator>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "bevgen.h"
+#include "image_io.h"
+#include "pcd_io.h"
+
+namespace fs = std::filesystem;
+using Clock = std::chrono::steady_clock;
+
+// ---------------------------------------------------------------------------------------------------------------
+struct ThreadPool {
+  std::vector<std::thread> th; std::deque<std::function<void()>> q; std::mutex mu; std::condition_variable cv, idle_cv;
+  bool stop = false; int active = 0;
+  explicit ThreadPool(int n) {
+    for (int i = 0; i < n; i++) th.emplace_back([this] {
+      for (;;) {
+        std::function<void()> f;
+        { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return stop || !q.empty(); }); if (q.empty()) return; f = std::move(q.front()); q.pop_front(); active++; }
+        f();
+        { std::lock_guard<std::mutex> l(mu); active--; if (q.empty() && active == 0) idle_cv.notify_all(); }
+      }
+    });
+  }
+  void submit(std::function<void()> f) { { std::lock_guard<std::mutex> l(mu); q.push_back(std::move(f)); } cv.notify_one(); }
+  void wait_idle() { std::unique_lock<std::mutex> l(mu); idle_cv.wait(l, [&] { return q.empty() && active == 0; }); }
+  ~ThreadPool() { { std::lock_guard<std::mutex> l(mu); stop = true; } cv.notify_all(); for (auto& t : th) t.join(); }
+};
+
+struct Options {
+  std::string root, sensor;
+  int gpus = 1, batch = 16, threads = 0, png_level = 1;
+  bool encode = true, write_pcd = true;
+  std::string json_metrics;
+};
+
+struct Dirs { std::string pcd_in, non_ground, multi_bin, multi_img, single_csv, single_img, pose_file, label_file; };
+
+static void usage_and_exit(const char* argv0) {   // BatchMultiBevGen.cpp:666-689
+  std::cout << "Usage: " << argv0 << " [keyframes_root_dir] [sensor_type]\n\n"
+            << "[keyframes_root_dir] should be organized as follows: \n"
+            << "[keyframes_root_dir]\n"
+            << "├ keyframe_point_cloud/ <- folder for selected point clouds in pcd format for each frame \n"
+            << "├ keyframe_pose.csv <- 6-DoF pose for each frame \n"
+            << "└ keyframe_pose_format.csv <- 6-DoF pose format description \n"
+            << "\n"
+            << "[sensor_type] could be HDL_32E, HDL_64E or OS1_64. \n"
+            << "\n"
+            << "This binary generates ground-removed point clouds, single & multi layer BEV images and creates geometric "
+               "distance-based labels for each point cloud. After running the binary, you will have files organized as follows: \n "
+            << "[keyframes_root_dir]\n "
+            << "├ ... \n "
+            << "├ non_ground_point_cloud/ <- folder for ground-removes point clouds in pcd format \n "
+            << "├ output_multi_bev/ <- folder for multi-layer BEV images \n "
+            << "└ output_single_bev <- folder for single-layer BEV images \n "
+            << std::endl;
+  exit(1);
+}
+
+static void reset_dir(const std::string& d) {   // `rm -rf` + `mkdir -p` (BatchMultiBevGen.cpp:49-70, :704-705) without forking a shell
+  std::error_code ec;
+  fs::remove_all(d, ec);
+  fs::create_directories(d, ec);
+}
+
+// getPcdFileNames, BatchMultiBevGen.cpp:469-494: suffix after the last '.' must be "pcd"; lexicographic sort.
+static std::vector<std::string> list_pcd(const std::string& path) {
+  std::vector<std::string> out;
+  DIR* d = opendir(path.c_str());
+  if (!d) { std::cerr << "Folder doesn't Exist!" << std::endl; return out; }
+  while (dirent* e = readdir(d)) {
+    std::string n = e->d_name;
+    if (n == "." || n == "..") continue;
+    if (n.substr(n.find_last_of('.') + 1) != "pcd") continue;
+    out.push_back(path.back() == '/' ? path + n : path + "/" + n);
+  }
+  closedir(d);
+  std::sort(out.begin(), out.end());
+  return out;
+}
+
+static std::string short_name_of(const std::string& f) {   // :739-742
+  int start_pos = (int)f.find_last_of('/') + 1;
+  int end_pos = (int)f.find_last_of('.') - 1;
+  return f.substr(start_pos, end_pos - start_pos + 1);
+}
+
+// readKeyframePose, BatchMultiBevGen.cpp:381-460: whitespace-separated entries, each split on ','; exactly 16 tokens
+// or stop; x,y,z = float(std::stod(token)).  Only x,y,z feed the label stage.
+static std::vector<float> read_poses(const std::string& file) {
+  std::ifstream f(file);
+  if (f.is_open()) std::cout << "loaded keyframe pose file: " << file << std::endl;
+  else { std::cerr << "failed to load keyframe pose file: " << file << std::endl; exit(1); }
+  std::vector<float> xyz;
+  std::string entry;
+  while (f >> entry) {
+    std::vector<std::string> tok; std::stringstream ss(entry); std::string s;
+    while (getline(ss, s, ',')) tok.push_back(s);
+    if (tok.size() != 16) { std::cerr << "Size of entry_token is: " << tok.size() << ", while expecting 16. " << std::endl; break; }
+    try {
+      for (int k = 1; k <= 3; k++) xyz.push_back((float)std::stod(tok[k]));
+      for (int k = 7; k < 16; k++) (void)std::stod(tok[k]);     // the reference parses the rotation too (and would throw here)
+    } catch (const std::exception& e) { std::cerr << "bad number in keyframe pose file: " << e.what() << std::endl; exit(1); }
+  }
+  std::cout << "Finish reading all keyframe pose, total " << xyz.size() / 3 << " entries. " << std::endl;
+  return xyz;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct PinnedSet {     // pinned staging of one batch: SoA inputs + outputs
+  size_t cap_pts = 0; int cap_frames = 0; size_t S = 0;
+  float *x = 0, *y = 0, *z = 0, *inten = 0; uint16_t *row = 0, *col = 0; int16_t* label = 0;
+  int16_t* o_label = 0; uint32_t* o_owner = 0; uint8_t *o_single = 0, *o_multi = 0;
+  bool alloc(size_t pts, int frames, size_t S_) {
+    release(); cap_pts = pts; cap_frames = frames; S = S_;
+    auto A = [](size_t n) { return bevgen_host_alloc(n); };
+    x = (float*)A(pts * 4); y = (float*)A(pts * 4); z = (float*)A(pts * 4); inten = (float*)A(pts * 4);
+    row = (uint16_t*)A(pts * 2); col = (uint16_t*)A(pts * 2); label = (int16_t*)A(pts * 2);
+    o_label = (int16_t*)A((size_t)frames * S * 2); o_owner = (uint32_t*)A((size_t)frames * S * 4);
+    o_single = (uint8_t*)A((size_t)frames * BEVGEN_GRID_SIZE * BEVGEN_GRID_SIZE);
+    o_multi = (uint8_t*)A((size_t)frames * BEVGEN_NUM_LAYERS * BEVGEN_GRID_SIZE * BEVGEN_GRID_SIZE);
+    return x && y && z && inten && row && col && label && o_label && o_owner && o_single && o_multi;
+  }
+  void release() {
+    for (void* p : {(void*)x, (void*)y, (void*)z, (void*)inten, (void*)row, (void*)col, (void*)label, (void*)o_label, (void*)o_owner, (void*)o_single, (void*)o_multi}) bevgen_host_free(p);
+    x = y = z = inten = 0; row = col = 0; label = 0; o_label = 0; o_owner = 0; o_single = o_multi = 0;
+  }
+};
+
+struct Batch {
+  int first = 0, count = 0;
+  std::vector<pcdio::Cloud> clouds;
+  std::vector<std::string> names;
+  std::vector<std::future<void>> loads;
+  PinnedSet* pin = nullptr;
+  std::atomic<int> pending_encodes{0};
+};
+
+struct Shared {
+  Options opt; Dirs dirs; bevgen_params params; size_t S = 0;
+  std::vector<std::string> files;
+  ThreadPool* pool = nullptr;
+  std::atomic<int> next_batch{0}; int n_batches = 0;
+  std::mutex print_mu;
+  std::atomic<long> frames_done{0};
+  std::atomic<bool> failed{false};
+};
+
+static void encode_frame(Shared& sh, const Batch& b, int k) {
+  const size_t S = sh.S; const int G = BEVGEN_GRID_SIZE, L = BEVGEN_NUM_LAYERS;
+  const PinnedSet& p = *b.pin;
+  const std::string& name = b.names[k];
+  const uint8_t* multi = p.o_multi + (size_t)k * L * G * G;
+  const uint8_t* single = p.o_single + (size_t)k * G * G;
+  if (sh.opt.encode) {
+    // .bin: 24 layers concatenated row-major (:294-314)
+    std::string bin = sh.dirs.multi_bin + name + ".bin";
+    if (!imgio::write_bytes(bin, multi, (size_t)L * G * G)) std::cerr << "Can not open file: " << bin << "\n";
+    std::string img_dir = sh.dirs.multi_img + name + "/";
+    mkdir(img_dir.c_str(), 0777);                                           // mkdir(2), not system("mkdir -p") (:303-306)
+    char nm[16];
+    for (int l = 0; l < L; l++) {
+      snprintf(nm, sizeof nm, "%02d.png", l);                               // "{:02d}.png" (:316-318)
+      imgio::write_png_gray8(img_dir + nm, multi + (size_t)l * G * G, G, G, sh.opt.png_level);
+    }
+    imgio::write_png_gray8(sh.dirs.single_img + name + ".png", single, G, G, sh.opt.png_level);   // :359-361
+    std::string csv = sh.dirs.single_csv + name + ".csv";
+    std::string txt = imgio::format_csv_u8(single, G, G);                   // :371
+    if (!imgio::write_bytes(csv, txt.data(), txt.size())) std::cerr << "Faied to export csv formatted BEV file: " << csv;
+  }
+  if (sh.opt.write_pcd) {
+    // savePCDFileBinary(non_ground/<name>.pcd, cloud_ordered) (:755-756): S slots; slot record = winning input record
+    // with its label replaced by the post-ground label, empty slots all-zero.
+    const pcdio::Cloud& c = b.clouds[k];
+    const uint32_t* owner = p.o_owner + (size_t)k * S; const int16_t* lab = p.o_label + (size_t)k * S;
+    std::string h = pcdio::header(S);
+    std::vector<uint8_t> out(h.size() + S * 26, 0);
+    memcpy(out.data(), h.data(), h.size());
+    uint8_t* rec = out.data() + h.size();
+    for (size_t s = 0; s < S; s++) {
+      uint32_t o = owner[s];
+      if (o) { size_t i = o - 1; pcdio::pack_record(rec + s * 26, c.x[i], c.y[i], c.z[i], c.intensity[i], c.row[i], c.col[i], c.t[i], lab[s]); }
+    }
+    if (!pcdio::write_file(sh.dirs.non_ground + name + ".pcd", out)) std::cerr << "Can not open file: " << sh.dirs.non_ground + name + ".pcd" << "\n";
+  }
+}
+
+struct GpuWorker {
+  Shared& sh; int dev; bevgen_ctx* ctx = nullptr; int ctx_max_pts = 0;
+  std::vector<PinnedSet> pins; std::vector<PinnedSet*> free_pins; std::mutex pin_mu; std::condition_variable pin_cv;
+  GpuWorker(Shared& s, int d) : sh(s), dev(d) {}
+
+  bool ensure_ctx(int max_pts) {
+    if (ctx && max_pts <= ctx_max_pts) return true;
+    if (ctx) bevgen_destroy(ctx);
+    ctx = nullptr;
+    ctx_max_pts = std::max<int>(max_pts + max_pts / 8, (int)sh.S + 4096);
+    if (bevgen_create(&ctx, dev, &sh.params, ctx_max_pts, sh.opt.batch) != 0) {
+      std::cerr << "bevgen_create(device " << dev << "): " << bevgen_last_error() << std::endl;
+      return false;
+    }
+    return true;
+  }
+
+  std::shared_ptr<Batch> grab() {
+    int b = sh.next_batch++;
+    if (b >= sh.n_batches) return nullptr;
+    auto bt = std::make_shared<Batch>();
+    bt->first = b * sh.opt.batch;
+    bt->count = std::min<int>(sh.opt.batch, (int)sh.files.size() - bt->first);
+    bt->clouds.resize(bt->count); bt->names.resize(bt->count);
+    for (int k = 0; k < bt->count; k++) {
+      auto pr = std::make_shared<std::promise<void>>();
+      bt->loads.push_back(pr->get_future());
+      Batch* raw = bt.get(); Shared* s = &sh;
+      sh.pool->submit([raw, s, k, pr, keep = bt] {
+        const std::string& f = s->files[raw->first + k];
+        raw->names[k] = short_name_of(f);
+        std::string err;
+        if (!pcdio::load(f, raw->clouds[k], &err)) std::cerr << "[pcd] " << err << std::endl;   // reference ignores the status (:730)
+        pr->set_value();
+      });
+    }
+    return bt;
+  }
+
+  PinnedSet* take_pin(size_t pts) {
+    std::unique_lock<std::mutex> l(pin_mu);
+    pin_cv.wait(l, [&] { return !free_pins.empty(); });
+    PinnedSet* p = free_pins.back(); free_pins.pop_back();
+    l.unlock();
+    if (p->cap_pts < pts || p->cap_frames < sh.opt.batch) {
+      if (!p->alloc(pts + pts / 4 + 1024, sh.opt.batch, sh.S)) { std::cerr << "pinned allocation failed" << std::endl; sh.failed = true; }
+    }
+    return p;
+  }
+  void give_pin(PinnedSet* p) { { std::lock_guard<std::mutex> l(pin_mu); free_pins.push_back(p); } pin_cv.notify_one(); }
+
+  void run() {
+    pins.resize(3);
+    for (auto& p : pins) free_pins.push_back(&p);
+    std::shared_ptr<Batch> next = grab();
+    while (next && !sh.failed) {
+      std::shared_ptr<Batch> cur = next;
+      next = grab();                                   // its PCD parsing overlaps this batch's GPU work
+      for (auto& f : cur->loads) f.get();
+      std::vector<int64_t> offs(cur->count + 1, 0);
+      int max_n = 0;
+      for (int k = 0; k < cur->count; k++) { offs[k + 1] = offs[k] + (int64_t)cur->clouds[k].size(); max_n = std::max<int>(max_n, (int)cur->clouds[k].size()); }
+      if (!ensure_ctx(max_n)) { sh.failed = true; break; }
+      PinnedSet* p = take_pin((size_t)offs[cur->count]);
+      if (sh.failed) break;
+      cur->pin = p;
+      for (int k = 0; k < cur->count; k++) {           // SoA staging into pinned memory
+        const pcdio::Cloud& c = cur->clouds[k]; size_t o = (size_t)offs[k], n = c.size();
+        if (!n) continue;
+        memcpy(p->x + o, c.x.data(), n * 4); memcpy(p->y + o, c.y.data(), n * 4); memcpy(p->z + o, c.z.data(), n * 4);
+        memcpy(p->inten + o, c.intensity.data(), n * 4); memcpy(p->row + o, c.row.data(), n * 2); memcpy(p->col + o, c.col.data(), n * 2);
+        memcpy(p->label + o, c.label.data(), n * 2);
+      }
+      { std::lock_guard<std::mutex> l(sh.print_mu); for (int k = 0; k < cur->count; k++) std::cout << "Converting file: " << cur->names[k] << "\n"; }   // :744
+      bevgen_points in{p->x, p->y, p->z, p->inten, p->row, p->col, p->label};
+      bevgen_outputs out{p->o_label, p->o_owner, p->o_single, p->o_multi};
+      if (bevgen_process_host(ctx, cur->count, offs.data(), &in, &out) != 0) {
+        std::cerr << "bevgen_process_host: " << bevgen_last_error() << std::endl; sh.failed = true; give_pin(p); break;
+      }
+      cur->pending_encodes = cur->count;
+      for (int k = 0; k < cur->count; k++) {
+        sh.pool->submit([this, cur, k] {
+          encode_frame(sh, *cur, k);
+          sh.frames_done++;
+          if (--cur->pending_encodes == 0) give_pin(cur->pin);
+        });
+      }
+    }
+  }
+};
+
+int main(int argc, char** argv) {
+  if (argc < 3 || argv[1] == nullptr || argv[2] == nullptr) usage_and_exit(argv[0]);
+  Shared sh;
+  Options& opt = sh.opt;
+  opt.root = argv[1]; opt.sensor = argv[2];
+  for (int i = 3; i < argc; i++) {
+    std::string a = argv[i];
+    auto val = [&](const char* name) -> const char* { if (i + 1 >= argc) { std::cerr << name << " needs a value\n"; exit(1); } return argv[++i]; };
+    if (a == "--gpus") opt.gpus = atoi(val("--gpus"));
+    else if (a == "--batch") opt.batch = atoi(val("--batch"));
+    else if (a == "--threads") opt.threads = atoi(val("--threads"));
+    else if (a == "--png-level") opt.png_level = atoi(val("--png-level"));
+    else if (a == "--no-encode") opt.encode = false;
+    else if (a == "--no-pcd") opt.write_pcd = false;
+    else if (a == "--json-metrics") opt.json_metrics = val("--json-metrics");
+    else { std::cerr << "unknown option " << a << "\n"; exit(1); }
+  }
+  if (opt.gpus < 1) opt.gpus = 1;
+  if (opt.batch < 1) opt.batch = 1;
+  if (opt.threads <= 0) opt.threads = std::max(2u, std::thread::hardware_concurrency());
+  std::string root = opt.root;
+  if (root.back() != '/') root.append("/");                                   // :691-693
+  Dirs& d = sh.dirs;
+  d.pcd_in = root + "keyframe_point_cloud/"; d.non_ground = root + "non_ground_point_cloud/";
+  d.pose_file = root + "keyframe_pose.csv"; d.label_file = root + "keyframe_label.csv";
+  d.multi_bin = root + "output_multi_bev/binary/"; d.multi_img = root + "output_multi_bev/image/";
+  d.single_csv = root + "output_single_bev/csv/"; d.single_img = root + "output_single_bev/image/";
+
+  reset_dir(d.non_ground);                                                    // :704-705
+  sh.files = list_pcd(d.pcd_in);                                              // :708-709
+  reset_dir(root + "output_multi_bev/"); reset_dir(d.multi_bin); reset_dir(d.multi_img);   // initDirectories :39-71
+  reset_dir(d.single_csv); reset_dir(d.single_img);
+
+  if (bevgen_sensor_params(opt.sensor.c_str(), &sh.params) < 0) {             // :718-719
+    std::cerr << "Unknown sensor type: " << opt.sensor << "!" << std::endl;
+    std::cerr << "Unknown sensor type! " << std::endl;
+    return 1;   // the reference would go on with uninitialised SensorParams (undefined behaviour); we stop
+  }
+  sh.S = (size_t)sh.params.n_scan * sh.params.horizon_scan;
+  std::cout << "Using sensor_type " << opt.sensor << ", with params: N_SCAN: " << sh.params.n_scan << ", Horizon_SCAN: "
+            << sh.params.horizon_scan << ", GROUND_UPPER_SCAN: " << sh.params.ground_upper_scan << "\n";   // :720-722
+
+  ThreadPool pool(opt.threads);
+  sh.pool = &pool;
+  sh.n_batches = (int)((sh.files.size() + opt.batch - 1) / opt.batch);
+  const int n_workers = std::max(1, std::min(opt.gpus, std::max(1, sh.n_batches)));
+  std::vector<std::unique_ptr<GpuWorker>> workers;
+  for (int g = 0; g < n_workers; g++) workers.emplace_back(new GpuWorker(sh, g));
+  // contexts are also needed for the label stage even when there is no frame to process
+  for (auto& w : workers) if (!w->ensure_ctx((int)sh.S)) return 1;
+
+  auto t0 = Clock::now();
+  {
+    std::vector<std::thread> ths;
+    for (auto& w : workers) ths.emplace_back([&w] { w->run(); });
+    for (auto& t : ths) t.join();
+    pool.wait_idle();
+  }
+  double total_ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+  if (sh.failed) return 1;
+  // the reference averages its per-frame serial span (:749-759); here frames overlap, so this is wall time / frames
+  std::cout << "[TIME] Average preprocessing and BEV generation: " << (sh.files.empty() ? 0.0 : total_ms / sh.files.size()) << "\n";
+
+  // Step 2: labels (:761-765)
+  auto t1 = Clock::now();
+  std::vector<float> xyz = read_poses(d.pose_file);
+  const int K = (int)(xyz.size() / 3);
+  std::vector<int32_t> major(std::max(K, 1)), overlap(std::max(K, 1));
+  int32_t M = 0;
+  if (K > 0) {
+    if (bevgen_select_major(workers[0]->ctx, K, xyz.data(), major.data(), &M, overlap.data()) != 0) {
+      std::cerr << "bevgen_select_major: " << bevgen_last_error() << std::endl; return 1;
+    }
+    for (int i = 1; i < K; i++)
+      if (overlap[i] >= 0)                                                      // :553-555
+        std::cout << "Key Frame " << i << " overlaps with previous Major Frame " << overlap[i] << ", i.e. Key Frame " << major[overlap[i]] << ". \n";
+  }
+  std::cout << "One-hot label has length: " << M << std::endl;               // :580-581
+  std::vector<int32_t> nn((size_t)std::max(K, 1) * 2); std::vector<float> w((size_t)std::max(K, 1) * 2);
+  if (K > 0) {
+    // rows split per GPU, gathered in host memory
+    const int nw = (int)workers.size();
+    std::vector<std::thread> ths; std::atomic<bool> bad{false};
+    for (int g = 0; g < nw; g++) {
+      const int r0 = (int)((int64_t)K * g / nw), r1 = (int)((int64_t)K * (g + 1) / nw);
+      if (r0 == r1) continue;
+      ths.emplace_back([&, g, r0, r1] {
+        if (bevgen_labels(workers[g]->ctx, K, xyz.data(), M, major.data(), r0, r1, nullptr, nn.data() + 2 * (size_t)r0, w.data() + 2 * (size_t)r0) != 0) {
+          std::cerr << "bevgen_labels: " << bevgen_last_error() << std::endl; bad = true;
+        }
+      });
+    }
+    for (auto& t : ths) t.join();
+    if (bad) return 1;
+  }
+  {
+    // saveLabels (:645-661): every value through `ostream << float` followed by ',', rows end with '\n'
+    std::ofstream f(d.label_file);
+    if (!f.is_open()) { std::cerr << "failed to open keyframe label file: " << d.label_file << std::endl; exit(1); }
+    std::string zero_row; for (int j = 0; j < M; j++) zero_row += "0,";
+    for (int i = 0; i < K; i++) {
+      // a row has at most two non-zeros; emit runs of "0," around them (identical text to streaming M floats)
+      int a = nn[2 * i], b = nn[2 * i + 1]; float wa = w[2 * i], wb = w[2 * i + 1];
+      std::vector<std::pair<int, float>> nz;
+      if (b >= 0 && b == a) nz = {{a, wb}};                                      // M == 1 edge: w1 overwrote w0 (:629-630)
+      else { nz.push_back({a, wa}); if (b >= 0) nz.push_back({b, wb}); }
+      std::sort(nz.begin(), nz.end());
+      int col = 0; std::ostringstream row;
+      for (auto& e : nz) { row.write(zero_row.data(), 2 * (size_t)(e.first - col)); row << e.second << ","; col = e.first + 1; }
+      row.write(zero_row.data(), 2 * (size_t)(M - col));
+      f << row.str() << "\n";
+    }
+    std::cout << "saved labels from " << K << " key frames. " << std::endl;   // :659-660
+  }
+  double label_ms = std::chrono::duration<double, std::milli>(Clock::now() - t1).count();
+  if (!opt.json_metrics.empty()) {
+    std::ofstream j(opt.json_metrics);
+    j << "{\"frames\": " << sh.files.size() << ", \"gpus\": " << workers.size() << ", \"batch\": " << opt.batch << ", \"threads\": " << opt.threads
+      << ", \"encode\": " << (opt.encode ? "true" : "false") << ", \"write_pcd\": " << (opt.write_pcd ? "true" : "false")
+      << ", \"frames_wall_ms\": " << total_ms << ", \"frames_per_s\": " << (total_ms > 0 ? sh.files.size() / (total_ms * 1e-3) : 0.0)
+      << ", \"keyframes\": " << K << ", \"majors\": " << M << ", \"labels_wall_ms\": " << label_ms << "}\n";
+  }
+  for (auto& wk : workers) { if (wk->ctx) bevgen_destroy(wk->ctx); for (auto& p : wk->pins) p.release(); }
+  std::cout << "Done. " << std::endl;
+  return 0;
+}

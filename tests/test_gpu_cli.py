@@ -1,0 +1,137 @@
+"""End-to-end drop-in test of the `batch_multi_bev_gen` CLI on a synthetic keyframe folder: every output file of the
+reference's directory contract is compared with what the oracle says the reference computes."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import FIELDS, oracle_batch, cat_frames
+
+pytestmark = pytest.mark.gpu
+
+
+def make_folder(tmp, synth, pcd, sensor, n, ascii_idx=()):
+    root = os.path.join(tmp, "kf")
+    os.makedirs(os.path.join(root, "keyframe_point_cloud"))
+    frames = []
+    for i in range(n):
+        f = synth.make_frame(sensor, 300 + i)
+        frames.append(f)
+        p = os.path.join(root, "keyframe_point_cloud", "%06d.pcd" % i)
+        if i in ascii_idx:
+            pcd.write_ascii(p, f, fields=("label", "x", "y", "z", "col", "row", "intensity", "t"))   # shuffled field order
+        else:
+            pcd.write(p, f)
+    open(os.path.join(root, "keyframe_point_cloud", "notes.txt"), "w").write("ignored: suffix is not pcd")
+    xyz = synth.make_poses(n, seed=5, step=9.0)
+    open(os.path.join(root, "keyframe_pose.csv"), "w").write("\n".join(synth.pose_csv_lines(xyz)) + "\n")
+    # stale outputs must be wiped (rm -rf semantics, BatchMultiBevGen.cpp:49-70)
+    os.makedirs(os.path.join(root, "output_multi_bev", "binary"))
+    open(os.path.join(root, "output_multi_bev", "binary", "stale.bin"), "w").write("x")
+    return root, frames
+
+
+def parse_pose_xyz(root):
+    rows = [l.split(",") for l in open(os.path.join(root, "keyframe_pose.csv")).read().split()]
+    return np.array([[np.float32(float(r[1])), np.float32(float(r[2])), np.float32(float(r[3]))] for r in rows], np.float32)
+
+
+@pytest.mark.parametrize("sensor,n,extra", [("HDL_32E", 7, ["--batch", "3"]), ("OS1_64", 4, ["--gpus", "1", "--batch", "16", "--threads", "3"])])
+def test_cli_folder_contract(tmp_path, pkg, synth, O, sensor, n, extra):
+    import importlib
+    pcd = importlib.import_module("pcpt_b200.pcd")
+    cv2 = pytest.importorskip("cv2")
+    assert os.path.exists(pkg.CLI_PATH), "CLI not built"
+    root, frames = make_folder(str(tmp_path), synth, pcd, sensor, n, ascii_idx=(1,))
+    r = subprocess.run([pkg.CLI_PATH, root, sensor] + extra, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = r.stdout
+    sp = O.sensor(sensor)
+    assert "Using sensor_type %s, with params: N_SCAN: %d, Horizon_SCAN: %d, GROUND_UPPER_SCAN: %d" % (
+        sensor, sp.n_scan, sp.horizon_scan, sp.ground_upper_scan) in out
+    for i in range(n):
+        assert "Converting file: %06d\n" % i in out
+    assert "[TIME] Average preprocessing and BEV generation: " in out and out.rstrip().endswith("Done.")
+    assert not os.path.exists(os.path.join(root, "output_multi_bev", "binary", "stale.bin"))
+
+    ref = oracle_batch(O, sensor, cat_frames(frames))
+    S = sp.S
+    for i in range(n):
+        name = "%06d" % i
+        b = np.fromfile(os.path.join(root, "output_multi_bev", "binary", name + ".bin"), np.uint8)
+        assert b.size == 24 * 224 * 224 and np.array_equal(b.reshape(24, 224, 224), ref["multi"][i]), name
+        for l in range(24):
+            img = cv2.imread(os.path.join(root, "output_multi_bev", "image", name, "%02d.png" % l), cv2.IMREAD_UNCHANGED)
+            assert img is not None and img.dtype == np.uint8 and np.array_equal(img, ref["multi"][i][l]), (name, l)
+        img = cv2.imread(os.path.join(root, "output_single_bev", "image", name + ".png"), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(img, ref["single"][i])
+        txt = open(os.path.join(root, "output_single_bev", "csv", name + ".csv")).read()
+        want = "\n".join(", ".join("%3d" % v for v in row) for row in ref["single"][i]) + "\n"      # cv::Formatter::FMT_CSV
+        assert txt == want
+        got, hdr = pcd.read(os.path.join(root, "non_ground_point_cloud", name + ".pcd"))
+        assert hdr.encode() == pcd.header(S)
+        own = ref["owner"][i]; f = frames[i]
+        exp = np.zeros(S, pcd.DTYPE)
+        sel = own > 0; idx = own[sel].astype(np.int64) - 1
+        for k in ("x", "y", "z", "intensity", "row", "col", "t"):
+            exp[k][sel] = f[k][idx]
+        exp["label"] = ref["label"][i]
+        assert np.array_equal(pcd.records(got).tobytes(), exp.tobytes()), name
+
+    xyz = parse_pose_xyz(root)
+    mi, ov = O.select_major(xyz)
+    lab, _, _ = O.labels(xyz, mi)
+    rows = open(os.path.join(root, "keyframe_label.csv")).read().splitlines()
+    assert len(rows) == n
+    for i, row in enumerate(rows):
+        assert row.endswith(",")
+        vals = np.array([float(v) for v in row[:-1].split(",")], np.float64)
+        assert len(vals) == len(mi)
+        np.testing.assert_allclose(vals, lab[i], rtol=1e-5, atol=0)           # text has 6 significant digits; north_star: 1e-5 relative
+        assert row == "".join("%g," % v for v in lab[i])                      # and byte-identical to `ostream << float`
+    assert "One-hot label has length: %d" % len(mi) in out
+    assert "saved labels from %d key frames. " % n in out
+    for i in range(n):
+        if ov[i] >= 0:
+            assert "Key Frame %d overlaps with previous Major Frame %d, i.e. Key Frame %d. " % (i, ov[i], mi[ov[i]]) in out
+
+
+def test_cli_usage_and_errors(tmp_path, pkg):
+    r = subprocess.run([pkg.CLI_PATH], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("Usage: ") and "[keyframes_root_dir] [sensor_type]" in r.stdout
+    root = str(tmp_path / "empty"); os.makedirs(os.path.join(root, "keyframe_point_cloud"))
+    r = subprocess.run([pkg.CLI_PATH, root, "VLP16"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Unknown sensor type: VLP16!" in r.stderr
+    r = subprocess.run([pkg.CLI_PATH, root, "HDL_32E"], capture_output=True, text=True)      # no pose file: exit(1) like :389-390
+    assert r.returncode == 1 and "failed to load keyframe pose file" in r.stderr
+    assert os.path.isdir(os.path.join(root, "output_single_bev", "csv"))
+
+
+def test_cloud_manip_cli(tmp_path, pkg, O):
+    import importlib
+    pcd = importlib.import_module("pcpt_b200.pcd")
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(9)
+    n = 50_000
+    f = dict(x=rng.normal(0, 30, n).astype(np.float32), y=rng.normal(0, 30, n).astype(np.float32), z=rng.uniform(-2, 8, n).astype(np.float32),
+             intensity=rng.random(n).astype(np.float32), row=np.zeros(n, np.uint16), col=np.zeros(n, np.uint16),
+             t=np.arange(n, dtype=np.uint32), label=np.full(n, -2, np.int16))
+    src = str(tmp_path / "cloud.pcd"); pcd.write(src, f)
+    r = subprocess.run([pkg.CLOUD_MANIP_PATH, src, "3.5", "-1.25", "0.2", "37"], capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
+    assert r.returncode == 0, r.stderr
+    th = np.float32(np.float64(np.float32(37.0) / np.float32(180.0)) * np.pi)
+    c, s = np.float32(np.cos(th)), np.float32(np.sin(th))      # same libm on the same box
+    out, _ = pcd.read(str(tmp_path / "cloud.pcd_output.pcd"))
+    rt = np.array([c, -s, 0, 3.5, s, c, 0, -1.25, 0, 0, np.float32(np.float32(1) - c) + c, 0.2], np.float32)
+    tx, ty, tz = O.transform(rt, f["x"], f["y"], f["z"])
+    assert np.array_equal(out["x"], tx) and np.array_equal(out["y"], ty) and np.array_equal(out["z"], tz)
+    assert np.array_equal(out["t"], f["t"]) and np.array_equal(out["intensity"], f["intensity"])
+    for tag, (a, b, cc) in (("input", (f["x"], f["y"], f["z"])), ("output", (tx, ty, tz))):
+        m = O.save_as_mat(a, b, cc)
+        rows = open(str(tmp_path / ("cloud.pcd_%s.csv" % tag))).read().splitlines()
+        got = np.array([[float(v) for v in row.split(", ")] for row in rows])
+        assert got.shape == (201, 201)
+        np.testing.assert_allclose(got, m, rtol=6e-4)                                    # "%.4g"
+        png = cv2.imread(str(tmp_path / ("cloud.pcd_%s.csv.png" % tag)), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(png, np.clip(np.rint(m), 0, 255).astype(np.uint8))
