@@ -160,7 +160,7 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
     }
     memcpy(&sp.t_star, &lo, 4);
     double tt = tan((double)sp.t_star);
-    sp.q_lo = (float)(tt * (1.0 - 1e-5)); sp.q_hi = (float)(tt * (1.0 + 1e-5));
+    sp.q_lo2 = (float)(tt * tt * (1.0 - 2e-5)); sp.q_hi2 = (float)(tt * tt * (1.0 + 2e-5));
   }
   memcpy(c->xf.m, p->rt, sizeof c->xf.m); c->xf.on = p->has_transform ? 1 : 0;
 

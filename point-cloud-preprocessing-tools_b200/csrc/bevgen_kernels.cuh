@@ -35,7 +35,7 @@ struct SensorDev {
   int hr_pow2;
   // ground criterion constants (computed on the host at context creation, see bevgen_capi.cu)
   float t_star;         // largest float t with (float)((double)t*180.0/M_PI) <= 10.0f   (BatchMultiBevGen.cpp:173,179)
-  float q_lo, q_hi;     // tan(t_star)*(1 -/+ 1e-5): outside [q_lo,q_hi] the decision needs no atan2f
+  float q_lo2, q_hi2;   // (tan(t_star)*(1 -/+ 1e-5))^2: outside this band of dz^2/(dx^2+dy^2) no atan2f is needed
 };
 
 struct Xform { float m[12]; int on; };
@@ -140,15 +140,18 @@ __device__ __forceinline__ int cvtt_x86(double v) {
   return (v > -2147483649.0 && v < 2147483648.0) ? __double2int_rz(v) : INT32_MIN;
 }
 
-// getBelongingGrid, BatchMultiBevGen.h:73-99 -> sector id row*50+col.
+// getBelongingGrid, BatchMultiBevGen.h:73-99 -> sector id row*50+col, in float-only arithmetic:
+//  * normalized = float(double(p) + 75.0) equals the single-rounded float sum fl(p + 75.0f): the double sum is exact
+//    unless |p| < 2^-23, and then both roundings give exactly 75.0f (p is far below half a float ulp of 75).
+//  * floor(double(n) / 2.0) == floorf(n * 0.5f) (scaling by 1/2 is exact; a denormal that rounds to -0 clamps to 0 either way).
+//  * static_cast<int> is cvttsd2si: NaN and |v| >= 2^31 give INT_MIN, which the `< 0` clamp turns into 0.
+__device__ __forceinline__ int sector_axis(float p, float off, int n) {
+  const float f = floorf(__fmul_rn(__fadd_rn(p, off), 0.5f));
+  if (!(f >= 0.0f) || f >= 2147483648.0f) return 0;
+  return f >= (float)(n - 1) ? n - 1 : (int)f;
+}
 __device__ __forceinline__ unsigned sector_of(float px, float py) {
-  float nx = __double2float_rn((double)px + 75.0);   // float + double literal, stored to float (:78)
-  float ny = __double2float_rn((double)py + 50.0);
-  int sr = cvtt_x86(floor((double)nx * 0.5));        // /2.0 is exact, so is *0.5
-  int sc = cvtt_x86(floor((double)ny * 0.5));
-  sr = sr >= SECT_R ? SECT_R - 1 : sr; sr = sr < 0 ? 0 : sr;
-  sc = sc >= SECT_C ? SECT_C - 1 : sc; sc = sc < 0 ? 0 : sc;
-  return (unsigned)(sr * SECT_C + sc);
+  return (unsigned)(sector_axis(px, 75.0f, SECT_R) * SECT_C + sector_axis(py, 50.0f, SECT_C));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -214,13 +217,19 @@ __global__ void __launch_bounds__(256) k_order_fill(SensorDev sp, Xform xf, cons
 __device__ __forceinline__ bool is_neg1(const float4& p) { return (__float_as_uint(p.w) & W_NEG1) != 0; }
 
 __device__ __forceinline__ bool ground_decision(const SensorDev& sp, const float4& up, const float4& lo) {
-  float dx = __fsub_rn(up.x, lo.x), dy = __fsub_rn(up.y, lo.y), dz = __fsub_rn(up.z, lo.z);      // :169-171
-  float hyp = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));                        // :173 sqrtf
-  float q = __fdiv_rn(fabsf(dz), hyp);
-  if (q <= sp.q_lo) return true;     // far inside 10 degrees: |atan2f| < t_star without evaluating it
-  if (q >= sp.q_hi) return false;    // far outside
-  float t = atan2f_glibc(dz, hyp);   // borderline / NaN / 0-over-0: the exact libm value decides
-  return fabsf(t) <= sp.t_star;      // <=> fabsf((float)((double)t*180.0/M_PI)) <= 10.0f  (:173,:179)
+  const float dx = __fsub_rn(up.x, lo.x), dy = __fsub_rn(up.y, lo.y), dz = __fsub_rn(up.z, lo.z);      // :169-171
+  const float hh = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+  const float zz = __fmul_rn(dz, dz);
+  // Pre-filter on squares (no sqrt, no division): tan^2 thresholds carry a 2e-5 relative guard band, the three
+  // roundings involved are ~2e-7, and glibc's atan2f is accurate to < 1 ulp, so outside the band the sign of
+  // |atan2f(dz, sqrtf(hh))| - t_star is decided.  Only taken when nothing can overflow / underflow.
+  if (hh > 1e-30f && hh < 1e30f && zz < 1e30f) {
+    if (zz <= __fmul_rn(sp.q_lo2, hh)) return true;
+    if (zz >= __fmul_rn(sp.q_hi2, hh)) return false;
+  }
+  const float hyp = __fsqrt_rn(hh);                                                                  // :173 sqrtf
+  const float t = atan2f_glibc(dz, hyp);   // borderline / special values: the exact libm value decides
+  return fabsf(t) <= sp.t_star;            // <=> fabsf((float)((double)t*180.0/M_PI)) <= 10.0f  (:173,:179)
 }
 
 __global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4* __restrict__ rec,
@@ -242,9 +251,17 @@ __global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4*
       gkey[fb + (size_t)r * H + c] = (uint16_t)key;
       gz[fb + (size_t)r * H + c] = gm1 ? p.z : 0.0f;
     }
-    unsigned k2 = (act && gm1) ? key : 0x10000u;   // all non-ground lanes share one dummy group (never a leader)
-    unsigned peers = __match_any_sync(0xffffffffu, k2);
-    if (act && gm1 && lane == __ffs(peers) - 1) atomicAdd(&cnt[(size_t)f * NSECT + key], (uint32_t)__popc(peers));
+    // loop 2's count (:205) is order-free: one atomicAdd per run of equal sectors along the row (neighbouring
+    // columns of a ring fall into the same 2 m sector for long stretches)
+    const unsigned k2 = (act && gm1) ? key : NO_KEY;
+    const unsigned prev = __shfl_up_sync(0xffffffffu, k2, 1);
+    const bool head = lane == 0 || prev != k2;
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    if (head && k2 != NO_KEY) {
+      const unsigned above = heads & ~((2u << lane) - 1u);            // heads strictly above this lane
+      const int len = (above ? __ffs(above) - 1 : 32) - lane;
+      atomicAdd(&cnt[(size_t)f * NSECT + key], (uint32_t)len);
+    }
   };
 
   float4 lower = R[(size_t)(N - 1) * H + c];
@@ -304,19 +321,18 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
     if (base + 32 * U < sp.S) load(base + 32 * U, kn, zn);     // next group's loads fly during this group's chains
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const bool nz = (k[u] != NO_KEY) && (zz[u] != 0.0f);
-      unsigned m = __ballot_sync(0xffffffffu, nz);
-      if (m == 0) continue;
-      const unsigned peers = __match_any_sync(0xffffffffu, nz ? k[u] : 0x10000u);   // MATCH cost grows with #distinct values
-      const bool leader = nz && lane == __ffs(peers) - 1;
+      const bool valid = k[u] != NO_KEY;
+      if (__ballot_sync(0xffffffffu, valid) == 0) continue;
+      const unsigned peers = __match_any_sync(0xffffffffu, valid ? k[u] : NO_KEY);
+      const bool leader = valid && lane == __ffs(peers) - 1;
+      const unsigned mine = leader ? peers : 0u;       // lanes whose z this lane folds, in lane (= slot) order
       float acc = leader ? ssum[k[u]] : 0.0f;
-      // warp-uniform walk over the contributing lanes in slot order; lane j's z is broadcast and only the leader of
-      // j's sector group folds it in: acc = fl(acc + z)   (:198)
-      while (m) {
-        const int j = __ffs(m) - 1;
-        m &= m - 1;
+      // 32 independent broadcasts; the only serial dependence is the leader's FADD chain acc = fl(acc + z)  (:198).
+      // z is 0 for non-ground lanes and adding +-0 never changes a sum that is never -0, so no further masking.
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
         const float zj = __shfl_sync(0xffffffffu, zz[u], j);
-        if (leader && ((peers >> j) & 1u)) acc = __fadd_rn(acc, zj);
+        if (mine & (1u << j)) acc = __fadd_rn(acc, zj);
       }
       if (leader) ssum[k[u]] = acc;
       __syncwarp();
