@@ -61,7 +61,7 @@ struct bevgen_ctx {
   float* cnt_lut = 0;
   Scratch sc_dev;            // scratch of the device path
   int64_t* offs_d = 0; size_t offs_cap = 0;
-  bool lanes_ready = false; Lane lanes[2];
+  bool lanes_ready = false; Lane lanes[3];
   std::vector<Slot> slots;
   // profiling
   bool prof = false;
@@ -289,11 +289,15 @@ extern "C" int bevgen_sync(bevgen_ctx* c) {
 }
 
 // ---- host-buffer path: H2D (copy stream) | kernels (compute stream) | D2H (third stream), double-buffered ------
+// The host path is PCIe-bound, so its chunks are kept small enough that H2D of chunk k+1, the kernels of chunk k and
+// D2H of chunk k-1 overlap (the device path uses max_frames_per_batch-sized waves instead).
+static int host_chunk(const bevgen_ctx* c) { return std::min(c->max_frames, 48); }
+
 static int ensure_lanes(bevgen_ctx* c) {
   if (c->lanes_ready) return 0;
   for (auto& l : c->lanes) {
-    if (alloc_scratch(l.sc, c->max_frames, c->sp.S)) return -1;
-    if (alloc_io(l.in, l.out, c->max_frames, c->max_pts, c->sp.S)) return -1;
+    if (alloc_scratch(l.sc, host_chunk(c), c->sp.S)) return -1;
+    if (alloc_io(l.in, l.out, host_chunk(c), c->max_pts, c->sp.S)) return -1;
     CK(cudaEventCreateWithFlags(&l.ev_h2d, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&l.ev_comp, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&l.ev_d2h, cudaEventDisableTiming));
@@ -311,10 +315,11 @@ extern "C" int bevgen_process_host(bevgen_ctx* c, int nf, const int64_t* offsets
   if (upload_offsets(c, nf, offsets, c->s_comp, &max_n_all)) return -1;
   if (max_n_all > c->max_pts) return fail("bevgen_process_host: a frame exceeds max_points_per_frame");
   const size_t S = c->sp.S;
+  const int chunk = host_chunk(c);
   int k = 0;
-  for (int f0 = 0; f0 < nf; f0 += c->max_frames, k++) {
-    Lane& l = c->lanes[k & 1];
-    const int n = std::min(c->max_frames, nf - f0);
+  for (int f0 = 0; f0 < nf; f0 += chunk, k++) {
+    Lane& l = c->lanes[k % 3];
+    const int n = std::min(chunk, nf - f0);
     const int64_t base = offsets[f0];
     const size_t np = (size_t)(offsets[f0 + n] - base);
     int max_n = 0;
