@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -59,7 +60,9 @@ struct bevgen_ctx {
   int max_pts = 0, max_frames = 0;
   cudaStream_t s_copy = 0, s_comp = 0, s_d2h = 0;
   float* cnt_lut = 0;
-  Scratch sc_dev;            // scratch of the device path
+  Scratch sc_dev;            // scratch of the device path (waves on the compute stream)
+  Scratch sc_aux;            // second scratch set: odd waves run on s_aux so that consecutive waves overlap
+  cudaStream_t s_aux = 0; cudaEvent_t ev_fork = 0, ev_join = 0; int n_dev_streams = 2;
   int64_t* offs_d = 0; size_t offs_cap = 0;
   bool lanes_ready = false; Lane lanes[3];
   std::vector<Slot> slots;
@@ -174,6 +177,13 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
   CK(cudaGetLastError());
   c->launches++;
   if (alloc_scratch(c->sc_dev, max_frames, sp.S)) { delete c; return -1; }
+  if (const char* e = getenv("BEVGEN_STREAMS")) c->n_dev_streams = atoi(e) >= 2 ? 2 : 1;
+  if (c->n_dev_streams == 2) {
+    if (alloc_scratch(c->sc_aux, max_frames, sp.S)) { delete c; return -1; }
+    CK(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
   CK(cudaStreamSynchronize(c->s_comp));
   *out = c;
   return 0;
@@ -184,6 +194,7 @@ extern "C" void bevgen_destroy(bevgen_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_scratch(c->sc_dev);
+  if (c->s_aux) { free_scratch(c->sc_aux); cudaStreamDestroy(c->s_aux); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
   if (c->lanes_ready) for (auto& l : c->lanes) { free_scratch(l.sc); free_io(l.in, l.out); cudaEventDestroy(l.ev_h2d); cudaEventDestroy(l.ev_comp); cudaEventDestroy(l.ev_d2h); }
   for (auto& s : c->slots) { free_scratch(s.sc); free_io(s.in, s.out); cudaFreeHost(s.pin_in); cudaFreeHost(s.pin_out); cudaFree(s.offs_d); cudaStreamDestroy(s.st); cudaEventDestroy(s.done); }
   cudaFree(c->cnt_lut); cudaFree(c->offs_d);
@@ -210,7 +221,7 @@ static int run_wave(bevgen_ctx* c, cudaStream_t st, const Scratch& sc, int nf, c
   CK(cudaMemsetAsync(sc.cnt, 0, (size_t)nf * NSECT * sizeof(uint32_t), st));
   mark(1);
   if (max_n > 0) {
-    dim3 g((max_n + 255) / 256, nf);
+    dim3 g((max_n + 511) / 512, nf);
     k_order_claim<<<g, 256, 0, st>>>(sp, offs_d, row, col, out.owner);
   }
   mark(2);
@@ -270,14 +281,21 @@ extern "C" int bevgen_process_device(bevgen_ctx* c, int nf, const int64_t* offse
   const size_t S = c->sp.S;
   DevIn di; di.x = (float*)in->x; di.y = (float*)in->y; di.z = (float*)in->z; di.inten = (float*)in->intensity;
   di.row = (uint16_t*)in->row; di.col = (uint16_t*)in->col; di.label = (int16_t*)in->label;
-  for (int f0 = 0; f0 < nf; f0 += c->max_frames) {
+  // Waves alternate between the compute stream and an auxiliary stream (own scratch): the latency-bound sector sweep
+  // of one wave overlaps the bandwidth-bound ordering / binning kernels of the other.  Profiling serialises.
+  const bool two = c->n_dev_streams == 2 && !c->prof && nf > c->max_frames;
+  if (two) { CK(cudaEventRecord(c->ev_fork, c->s_comp)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0)); }
+  int w = 0;
+  for (int f0 = 0; f0 < nf; f0 += c->max_frames, w++) {
     const int n = std::min(c->max_frames, nf - f0);
     int max_n = 0;
     for (int f = f0; f < f0 + n; f++) max_n = std::max<int64_t>(max_n, offsets[f + 1] - offsets[f]);
     DevOut dout; dout.label = out->label + (size_t)f0 * S; dout.owner = out->owner + (size_t)f0 * S;
     dout.single = out->single_bev + (size_t)f0 * CELLS; dout.multi = out->multi_bev + (size_t)f0 * LAYERS * CELLS;
-    if (run_wave(c, c->s_comp, c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout, c->prof)) return -1;
+    const bool aux = two && (w & 1);
+    if (run_wave(c, aux ? c->s_aux : c->s_comp, aux ? c->sc_aux : c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout, c->prof)) return -1;
   }
+  if (two) { CK(cudaEventRecord(c->ev_join, c->s_aux)); CK(cudaStreamWaitEvent(c->s_comp, c->ev_join, 0)); }
   return 0;
 }
 

@@ -146,9 +146,10 @@ __device__ __forceinline__ int cvtt_x86(double v) {
 //  * floor(double(n) / 2.0) == floorf(n * 0.5f) (scaling by 1/2 is exact; a denormal that rounds to -0 clamps to 0 either way).
 //  * static_cast<int> is cvttsd2si: NaN and |v| >= 2^31 give INT_MIN, which the `< 0` clamp turns into 0.
 __device__ __forceinline__ int sector_axis(float p, float off, int n) {
-  const float f = floorf(__fmul_rn(__fadd_rn(p, off), 0.5f));
-  if (!(f >= 0.0f) || f >= 2147483648.0f) return 0;
-  return f >= (float)(n - 1) ? n - 1 : (int)f;
+  const float t = __fmul_rn(__fadd_rn(p, off), 0.5f);
+  int i = __float2int_rd(t);                 // floor; saturates, NaN -> 0
+  if (t >= 2147483648.0f) i = 0;             // cvttsd2si gives INT_MIN there, which the reference clamps to 0
+  return min(max(i, 0), n - 1);
 }
 __device__ __forceinline__ unsigned sector_of(float px, float py) {
   return (unsigned)(sector_axis(px, 75.0f, SECT_R) * SECT_C + sector_axis(py, 50.0f, SECT_C));
@@ -165,11 +166,13 @@ __global__ void __launch_bounds__(256) k_order_claim(SensorDev sp, const int64_t
   const int f = blockIdx.y;
   const int64_t o = offs[f];
   const int n = (int)(offs[f + 1] - o);
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= n) return;
-  const unsigned r = row[o + i], c = col[o + i];
-  if (r >= (unsigned)sp.N || c >= (unsigned)sp.H) return;           // :106-111
-  atomicMax(&owner[(size_t)f * sp.S + r * sp.H + c], (uint32_t)(i + 1));
+  const int i0 = blockIdx.x * 512 + threadIdx.x, i1 = i0 + 256;   // two points per thread: four loads in flight
+  unsigned r0 = 0xFFFF, c0 = 0xFFFF, r1 = 0xFFFF, c1 = 0xFFFF;
+  if (i0 < n) { r0 = row[o + i0]; c0 = col[o + i0]; }
+  if (i1 < n) { r1 = row[o + i1]; c1 = col[o + i1]; }
+  uint32_t* own = owner + (size_t)f * sp.S;
+  if (i0 < n && r0 < (unsigned)sp.N && c0 < (unsigned)sp.H) atomicMax(&own[r0 * sp.H + c0], (uint32_t)(i0 + 1));   // :106-113
+  if (i1 < n && r1 < (unsigned)sp.N && c1 < (unsigned)sp.H) atomicMax(&own[r1 * sp.H + c1], (uint32_t)(i1 + 1));
 }
 
 // K0b order_fill — pass 2: winners write their record, unowned slots get the value-initialised record (:98).
@@ -186,23 +189,26 @@ __global__ void __launch_bounds__(256) k_order_fill(SensorDev sp, Xform xf, cons
   const int n = (int)(offs[f + 1] - o);
   const int i = blockIdx.x * 256 + threadIdx.x;
   const size_t fb = (size_t)f * sp.S;
-  if (i < sp.S && owner[fb + i] == 0) rec[fb + i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i < n) {
-    const unsigned r = row[o + i], c = col[o + i];
-    if (r < (unsigned)sp.N && c < (unsigned)sp.H) {
-      const size_t slot = fb + r * sp.H + c;
-      if (owner[slot] == (uint32_t)(i + 1)) {
-        float px = x[o + i], py = y[o + i], pz = z[o + i];
-        if (xf.on) {
-          float ox = __fadd_rn(__fmul_rn(px, xf.m[0]), __fadd_rn(__fmul_rn(py, xf.m[1]), __fadd_rn(__fmul_rn(pz, xf.m[2]), xf.m[3])));
-          float oy = __fadd_rn(__fmul_rn(px, xf.m[4]), __fadd_rn(__fmul_rn(py, xf.m[5]), __fadd_rn(__fmul_rn(pz, xf.m[6]), xf.m[7])));
-          float oz = __fadd_rn(__fmul_rn(px, xf.m[8]), __fadd_rn(__fmul_rn(py, xf.m[9]), __fadd_rn(__fmul_rn(pz, xf.m[10]), xf.m[11])));
-          px = ox; py = oy; pz = oz;
-        }
-        unsigned w = (unsigned)(uint16_t)label[o + i] | W_OWNED | (inten[o + i] == -1.0f ? W_NEG1 : 0u);
-        rec[slot] = make_float4(px, py, pz, __uint_as_float(w));
-      }
+  // All loads that do not depend on the owner probe are issued up front (the kernel is bound by the latency of its
+  // dependent chain row/col -> owner[slot] -> record store, not by bandwidth); 99.5 % of the points are winners.
+  const bool pv = i < n;
+  unsigned r = 0xFFFF, c = 0xFFFF;
+  float px = 0.f, py = 0.f, pz = 0.f, pi = 0.f; int16_t lb = 0;
+  if (pv) { r = row[o + i]; c = col[o + i]; px = x[o + i]; py = y[o + i]; pz = z[o + i]; pi = inten[o + i]; lb = label[o + i]; }
+  const uint32_t own_s = i < sp.S ? owner[fb + i] : 1u;
+  const bool valid = pv && r < (unsigned)sp.N && c < (unsigned)sp.H;
+  const size_t slot = fb + (valid ? r * sp.H + c : 0u);
+  const uint32_t own_p = valid ? owner[slot] : 0u;
+  if (i < sp.S && own_s == 0) rec[fb + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid && own_p == (uint32_t)(i + 1)) {
+    if (xf.on) {
+      float ox = __fadd_rn(__fmul_rn(px, xf.m[0]), __fadd_rn(__fmul_rn(py, xf.m[1]), __fadd_rn(__fmul_rn(pz, xf.m[2]), xf.m[3])));
+      float oy = __fadd_rn(__fmul_rn(px, xf.m[4]), __fadd_rn(__fmul_rn(py, xf.m[5]), __fadd_rn(__fmul_rn(pz, xf.m[6]), xf.m[7])));
+      float oz = __fadd_rn(__fmul_rn(px, xf.m[8]), __fadd_rn(__fmul_rn(py, xf.m[9]), __fadd_rn(__fmul_rn(pz, xf.m[10]), xf.m[11])));
+      px = ox; py = oy; pz = oz;
     }
+    const unsigned w = (unsigned)(uint16_t)lb | W_OWNED | (pi == -1.0f ? W_NEG1 : 0u);
+    rec[slot] = make_float4(px, py, pz, __uint_as_float(w));
   }
 }
 
@@ -242,45 +248,48 @@ __global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4*
   const int lane = threadIdx.x & 31;
   const int H = sp.H, N = sp.N;
   const size_t fb = (size_t)f * sp.S;
-  const float4* R = rec + fb;
+  uint32_t* const cntf = cnt + (size_t)f * NSECT;
+  // everything is addressed relative to the current row and walked upwards by -H per iteration
+  const float4* pr = rec + fb + (size_t)(N - 1) * H + c;        // (row r, col c)
+  uint16_t* gk = gkey + fb + (size_t)(N - 1) * H + c;
+  float* gzp = gz + fb + (size_t)(N - 1) * H + c;
+  const int dplus = (c + 2 >= H ? c + 2 - H : c + 2) - c;       // (col+2) % H, relative to c           (:147)
+  const int dminus = -2;                                        // (col-2) % H stays negative in C++ for col < 2 (:152)
 
-  auto emit = [&](int r, const float4& p, bool gm1) {
+  auto emit = [&](const float4& p, bool gm1) {
     unsigned key = NO_KEY;
     if (gm1) key = sector_of(p.x, p.y);
-    if (act) {
-      gkey[fb + (size_t)r * H + c] = (uint16_t)key;
-      gz[fb + (size_t)r * H + c] = gm1 ? p.z : 0.0f;
-    }
+    if (act) { *gk = (uint16_t)key; *gzp = gm1 ? p.z : 0.0f; }
     // loop 2's count (:205) is order-free: one atomicAdd per run of equal sectors along the row (neighbouring
     // columns of a ring fall into the same 2 m sector for long stretches)
-    const unsigned k2 = (act && gm1) ? key : NO_KEY;
+    const unsigned k2 = act ? key : NO_KEY;
     const unsigned prev = __shfl_up_sync(0xffffffffu, k2, 1);
     const bool head = lane == 0 || prev != k2;
     const unsigned heads = __ballot_sync(0xffffffffu, head);
     if (head && k2 != NO_KEY) {
       const unsigned above = heads & ~((2u << lane) - 1u);            // heads strictly above this lane
-      const int len = (above ? __ffs(above) - 1 : 32) - lane;
-      atomicAdd(&cnt[(size_t)f * NSECT + key], (uint32_t)len);
+      atomicAdd(&cntf[key], (uint32_t)((above ? __ffs(above) - 1 : 32) - lane));
     }
   };
 
-  float4 lower = R[(size_t)(N - 1) * H + c];
-  float4 nxt = R[(size_t)(N - 2) * H + c];
+  float4 lower = pr[0];
+  float4 nxt = pr[-H];
   bool ground_prev = false;
   for (int r = N - 1; r > N - sp.G - 1; --r) {
     const float4 direct = nxt;
-    if (r - 2 >= 0) nxt = R[(size_t)(r - 2) * H + c];   // next iteration's upper: in flight during this row's math
+    if (r >= 2) nxt = pr[-2 * H];                                 // next iteration's upper: in flight during this row's math
     float4 up = direct;
-    if (is_neg1(up)) up = R[(size_t)(r - 1) * H + ((c + 2) % H)];                 // :146-149
-    if (is_neg1(up)) up = R[(size_t)((r - 1) * H + (c - 2))];                     // :151-154, C++ % keeps c-2 negative for c<2
-    if (is_neg1(up) && r >= 2) up = R[(size_t)(r - 2) * H + c];                   // :157-160
-    const bool invalid = is_neg1(lower) || is_neg1(up);                           // :162
+    if (is_neg1(up)) up = pr[-H + dplus];                         // :146-149
+    if (is_neg1(up)) up = pr[-H + dminus];                        // :151-154
+    if (is_neg1(up) && r >= 2) up = pr[-2 * H];                   // :157-160
+    const bool invalid = is_neg1(lower) || is_neg1(up);           // :162
     const bool ground = !invalid && ground_decision(sp, up, lower);
-    emit(r, lower, !invalid && (ground || ground_prev));
+    emit(lower, !invalid && (ground || ground_prev));
     ground_prev = ground;
     lower = direct;
+    pr -= H; gk -= H; gzp -= H;
   }
-  emit(N - sp.G - 1, lower, ground_prev);   // row above the band only receives gm[row-1] = 1 (:181)
+  emit(lower, ground_prev);   // row above the band only receives gm[row-1] = 1 (:181)
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -332,7 +341,7 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
 #pragma unroll
       for (int j = 0; j < 32; j++) {
         const float zj = __shfl_sync(0xffffffffu, zz[u], j);
-        if (mine & (1u << j)) acc = __fadd_rn(acc, zj);
+        acc = __fadd_rn(acc, (mine & (1u << j)) ? zj : 0.0f);    // the select is off the chain; + 0 is a no-op
       }
       if (leader) ssum[k[u]] = acc;
       __syncwarp();
