@@ -61,8 +61,9 @@ struct bevgen_ctx {
   cudaStream_t s_copy = 0, s_comp = 0, s_d2h = 0;
   float* cnt_lut = 0;
   Scratch sc_dev;            // scratch of the device path (waves on the compute stream)
-  Scratch sc_aux;            // second scratch set: odd waves run on s_aux so that consecutive waves overlap
-  cudaStream_t s_aux = 0; cudaEvent_t ev_fork = 0, ev_join = 0; int n_dev_streams = 2;
+  Scratch sc_aux;            // second scratch set: consecutive waves are software-pipelined (see bevgen_process_device)
+  cudaStream_t s_aux = 0;    // high-priority stream that only runs the sector sweep
+  cudaEvent_t ev_front[2] = {0, 0}, ev_sweep[2] = {0, 0}; int n_dev_streams = 2;
   int64_t* offs_d = 0; size_t offs_cap = 0;
   bool lanes_ready = false; Lane lanes[3];
   std::vector<Slot> slots;
@@ -180,9 +181,13 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
   if (const char* e = getenv("BEVGEN_STREAMS")) c->n_dev_streams = atoi(e) >= 2 ? 2 : 1;
   if (c->n_dev_streams == 2) {
     if (alloc_scratch(c->sc_aux, max_frames, sp.S)) { delete c; return -1; }
-    CK(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&c->s_aux, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 2; i++) {
+      CK(cudaEventCreateWithFlags(&c->ev_front[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->ev_sweep[i], cudaEventDisableTiming));
+    }
   }
   CK(cudaStreamSynchronize(c->s_comp));
   *out = c;
@@ -194,7 +199,7 @@ extern "C" void bevgen_destroy(bevgen_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_scratch(c->sc_dev);
-  if (c->s_aux) { free_scratch(c->sc_aux); cudaStreamDestroy(c->s_aux); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
+  if (c->s_aux) { free_scratch(c->sc_aux); cudaStreamDestroy(c->s_aux); for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_front[i]); cudaEventDestroy(c->ev_sweep[i]); } }
   if (c->lanes_ready) for (auto& l : c->lanes) { free_scratch(l.sc); free_io(l.in, l.out); cudaEventDestroy(l.ev_h2d); cudaEventDestroy(l.ev_comp); cudaEventDestroy(l.ev_d2h); }
   for (auto& s : c->slots) { free_scratch(s.sc); free_io(s.in, s.out); cudaFreeHost(s.pin_in); cudaFreeHost(s.pin_out); cudaFree(s.offs_d); cudaStreamDestroy(s.st); cudaEventDestroy(s.done); }
   cudaFree(c->cnt_lut); cudaFree(c->offs_d);
@@ -203,53 +208,75 @@ extern "C" void bevgen_destroy(bevgen_ctx* c) {
   delete c;
 }
 
-// ---- one wave of frames on a stream ---------------------------------------------------------------------------
+// ---- one wave of frames ----------------------------------------------------------------------------------------
 // offs_d: device offsets of the wave (nf+1 entries); `base` is subtracted so that `in` may be a staging buffer that
 // starts at the wave's first point.  max_n: largest frame of the wave (host-known).
-static int run_wave(bevgen_ctx* c, cudaStream_t st, const Scratch& sc, int nf, const int64_t* offs_d, int64_t base, int max_n,
-                    const DevIn& in, const DevOut& out, bool prof) {
+// The wave is three stages so that the device path can pipeline them across waves:
+//   front  = clear + order_claim + order_fill + ground_mark      (L2 / HBM bound)
+//   sweep  = sector_mean                                          (MIO / latency bound, few warps per SM)
+//   back   = finalize_bin_scatter                                 (HBM + shared-memory bound)
+struct WaveArgs { const Scratch* sc; int nf; const int64_t* offs_d; int64_t base; int max_n; DevIn in; DevOut out; };
+
+static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {
   const SensorDev& sp = c->sp;
   const size_t S = sp.S;
   auto mark = [&](int i) { if (prof) cudaEventRecord(c->pev[i], st); };
   // inputs are indexed with the caller's offsets: shift the pointers instead of the offsets
-  const float *x = in.x - base, *y = in.y - base, *z = in.z - base, *it = in.inten - base;
-  const uint16_t *row = in.row - base, *col = in.col - base;
-  const int16_t* lab = in.label - base;
-
+  const float *x = w.in.x - w.base, *y = w.in.y - w.base, *z = w.in.z - w.base, *it = w.in.inten - w.base;
+  const uint16_t *row = w.in.row - w.base, *col = w.in.col - w.base;
+  const int16_t* lab = w.in.label - w.base;
   mark(0);
-  CK(cudaMemsetAsync(out.owner, 0, (size_t)nf * S * sizeof(uint32_t), st));
-  CK(cudaMemsetAsync(sc.cnt, 0, (size_t)nf * NSECT * sizeof(uint32_t), st));
+  CK(cudaMemsetAsync(w.out.owner, 0, (size_t)w.nf * S * sizeof(uint32_t), st));
+  CK(cudaMemsetAsync(w.sc->cnt, 0, (size_t)w.nf * NSECT * sizeof(uint32_t), st));
   mark(1);
-  if (max_n > 0) {
-    dim3 g((max_n + 511) / 512, nf);
-    k_order_claim<<<g, 256, 0, st>>>(sp, offs_d, row, col, out.owner);
+  if (w.max_n > 0) {
+    dim3 g((w.max_n + 511) / 512, w.nf);
+    k_order_claim<<<g, 256, 0, st>>>(sp, w.offs_d, row, col, w.out.owner);
   }
   mark(2);
   {
-    dim3 g((std::max<int>(max_n, (int)S) + 255) / 256, nf);
-    k_order_fill<<<g, 256, 0, st>>>(sp, c->xf, offs_d, x, y, z, it, row, col, lab, out.owner, sc.rec);
+    dim3 g((std::max<int>(w.max_n, (int)S) + 255) / 256, w.nf);
+    k_order_fill<<<g, 256, 0, st>>>(sp, c->xf, w.offs_d, x, y, z, it, row, col, lab, w.out.owner, w.sc->rec);
   }
   mark(3);
   {
-    dim3 g((sp.H + 127) / 128, nf);
-    k_ground_mark<<<g, 128, 0, st>>>(sp, sc.rec, sc.gkey, sc.gz, sc.cnt);
+    dim3 g((sp.H + 127) / 128, w.nf);
+    k_ground_mark<<<g, 128, 0, st>>>(sp, w.sc->rec, w.sc->gkey, w.sc->gz, w.sc->cnt);
   }
   mark(4);
-  k_sector_mean<<<nf, 32, NSECT * sizeof(float), st>>>(sp, sc.gkey, sc.gz, sc.cnt, c->cnt_lut, sc.avg);
-  mark(5);
-  k_finalize_bin<<<nf, 1024, SMEM_BIN, st>>>(sp, sc.rec, sc.gkey, sc.avg, out.label, out.single, out.multi);
-  mark(6);
   CK(cudaGetLastError());
-  c->launches += (max_n > 0 ? 5 : 4);
+  c->launches += (w.max_n > 0 ? 3 : 2);
+  return 0;
+}
+static int wave_sweep(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {
+  k_sector_mean<<<w.nf, 32, NSECT * sizeof(float), st>>>(c->sp, w.sc->gkey, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->avg);
+  if (prof) cudaEventRecord(c->pev[5], st);
+  CK(cudaGetLastError());
+  c->launches += 1;
+  return 0;
+}
+static int wave_back(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {
+  k_finalize_bin<<<w.nf, 1024, SMEM_BIN, st>>>(c->sp, w.sc->rec, w.sc->gkey, w.sc->avg, w.out.label, w.out.single, w.out.multi);
+  if (prof) cudaEventRecord(c->pev[6], st);
+  CK(cudaGetLastError());
+  c->launches += 1;
   if (prof) {
     CK(cudaEventSynchronize(c->pev[6]));
     for (int i = 0; i < 6; i++) {
       float ms = 0; CK(cudaEventElapsedTime(&ms, c->pev[i], c->pev[i + 1]));
       c->stage_ms[i] += ms;
-      c->stage_launches[i] += (i == 0) ? 2 : ((i == 1 && max_n == 0) ? 0 : 1);
+      c->stage_launches[i] += (i == 0) ? 2 : ((i == 1 && w.max_n == 0) ? 0 : 1);
     }
   }
   return 0;
+}
+// all three stages back to back on one stream
+static int run_wave(bevgen_ctx* c, cudaStream_t st, const Scratch& sc, int nf, const int64_t* offs_d, int64_t base, int max_n,
+                    const DevIn& in, const DevOut& out, bool prof) {
+  WaveArgs w{&sc, nf, offs_d, base, max_n, in, out};
+  if (wave_front(c, st, w, prof)) return -1;
+  if (wave_sweep(c, st, w, prof)) return -1;
+  return wave_back(c, st, w, prof);
 }
 
 static int upload_offsets(bevgen_ctx* c, int nf, const int64_t* offsets, cudaStream_t st, int* max_n_out) {
@@ -281,21 +308,42 @@ extern "C" int bevgen_process_device(bevgen_ctx* c, int nf, const int64_t* offse
   const size_t S = c->sp.S;
   DevIn di; di.x = (float*)in->x; di.y = (float*)in->y; di.z = (float*)in->z; di.inten = (float*)in->intensity;
   di.row = (uint16_t*)in->row; di.col = (uint16_t*)in->col; di.label = (int16_t*)in->label;
-  // Waves alternate between the compute stream and an auxiliary stream (own scratch): the latency-bound sector sweep
-  // of one wave overlaps the bandwidth-bound ordering / binning kernels of the other.  Profiling serialises.
-  const bool two = c->n_dev_streams == 2 && !c->prof && nf > c->max_frames;
-  if (two) { CK(cudaEventRecord(c->ev_fork, c->s_comp)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0)); }
-  int w = 0;
-  for (int f0 = 0; f0 < nf; f0 += c->max_frames, w++) {
+  // Software pipeline across waves (two scratch sets).  Main stream: front(0) front(1) back(0) front(2) back(1) ...;
+  // the sweep of wave w runs on the high-priority stream between front(w) and back(w), so the MIO/latency-bound
+  // sweep overlaps the bandwidth-bound front of wave w+1 and back of wave w-1.  Profiling serialises everything.
+  const int nw = (nf + c->max_frames - 1) / c->max_frames;
+  const bool pipe = c->n_dev_streams == 2 && !c->prof && nw > 1;
+  auto wave_args = [&](int w) {
+    const int f0 = w * c->max_frames;
     const int n = std::min(c->max_frames, nf - f0);
     int max_n = 0;
     for (int f = f0; f < f0 + n; f++) max_n = std::max<int64_t>(max_n, offsets[f + 1] - offsets[f]);
     DevOut dout; dout.label = out->label + (size_t)f0 * S; dout.owner = out->owner + (size_t)f0 * S;
     dout.single = out->single_bev + (size_t)f0 * CELLS; dout.multi = out->multi_bev + (size_t)f0 * LAYERS * CELLS;
-    const bool aux = two && (w & 1);
-    if (run_wave(c, aux ? c->s_aux : c->s_comp, aux ? c->sc_aux : c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout, c->prof)) return -1;
+    return WaveArgs{(pipe && (w & 1)) ? &c->sc_aux : &c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout};
+  };
+  if (!pipe) {
+    for (int w = 0; w < nw; w++) {
+      WaveArgs a = wave_args(w);
+      if (wave_front(c, c->s_comp, a, c->prof) || wave_sweep(c, c->s_comp, a, c->prof) || wave_back(c, c->s_comp, a, c->prof)) return -1;
+    }
+    return 0;
   }
-  if (two) { CK(cudaEventRecord(c->ev_join, c->s_aux)); CK(cudaStreamWaitEvent(c->s_comp, c->ev_join, 0)); }
+  for (int w = 0; w <= nw; w++) {
+    if (w < nw) {
+      WaveArgs a = wave_args(w);
+      if (wave_front(c, c->s_comp, a, false)) return -1;
+      CK(cudaEventRecord(c->ev_front[w & 1], c->s_comp));
+      CK(cudaStreamWaitEvent(c->s_aux, c->ev_front[w & 1], 0));
+      if (wave_sweep(c, c->s_aux, a, false)) return -1;
+      CK(cudaEventRecord(c->ev_sweep[w & 1], c->s_aux));
+    }
+    if (w >= 1) {
+      WaveArgs a = wave_args(w - 1);
+      CK(cudaStreamWaitEvent(c->s_comp, c->ev_sweep[(w - 1) & 1], 0));
+      if (wave_back(c, c->s_comp, a, false)) return -1;
+    }
+  }
   return 0;
 }
 

@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4*
 __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t* __restrict__ gkey,
                                                      const float* __restrict__ gz, const uint32_t* __restrict__ cnt,
                                                      const float* __restrict__ cnt_lut, float* __restrict__ avg) {
-  extern __shared__ float ssum[];
+  extern __shared__ float ssum[];                 // [NSECT] running sums of this frame
+  __shared__ __align__(16) float zb[2][32];       // the current step's 32 heights (double-buffered)
   const int f = blockIdx.x, lane = threadIdx.x;
   for (int i = lane; i < NSECT; i += 32) ssum[i] = 0.0f;
   __syncwarp();
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
     }
   };
   int base = sp.band_row0 * sp.H;
+  int buf = 0;
   load(base, kn, zn);
   for (; base < sp.S; base += 32 * U) {
 #pragma unroll
@@ -331,19 +333,29 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const bool valid = k[u] != NO_KEY;
-      if (__ballot_sync(0xffffffffu, valid) == 0) continue;
+      const unsigned vm = __ballot_sync(0xffffffffu, valid);
+      if (vm == 0) continue;
       const unsigned peers = __match_any_sync(0xffffffffu, valid ? k[u] : NO_KEY);
       const bool leader = valid && lane == __ffs(peers) - 1;
       const unsigned mine = leader ? peers : 0u;       // lanes whose z this lane folds, in lane (= slot) order
+      // Stage the 32 heights once; every leader then reads them back as broadcast 128-bit words (all leaders read the
+      // same address => one shared-memory wavefront per read) instead of 32 warp shuffles through the same MIO pipe.
+      zb[buf][lane] = zz[u];                           // gz is 0 for non-ground slots; adding +-0 is a no-op
+      __syncwarp();
       float acc = leader ? ssum[k[u]] : 0.0f;
-      // 32 independent broadcasts; the only serial dependence is the leader's FADD chain acc = fl(acc + z)  (:198).
-      // z is 0 for non-ground lanes and adding +-0 never changes a sum that is never -0, so no further masking.
+      const float4* z4 = reinterpret_cast<const float4*>(zb[buf]);
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
-        const float zj = __shfl_sync(0xffffffffu, zz[u], j);
-        acc = __fadd_rn(acc, (mine & (1u << j)) ? zj : 0.0f);    // the select is off the chain; + 0 is a no-op
+      for (int q = 0; q < 8; q++) {
+        if (((vm >> (4 * q)) & 0xFu) == 0) continue;   // warp-uniform: no ground slot in this quad
+        const float4 v = z4[q];
+        // the only serial dependence is the leader's chain acc = fl(acc + z) in slot order (:198); selects are off it
+        acc = __fadd_rn(acc, (mine & (1u << (4 * q + 0))) ? v.x : 0.0f);
+        acc = __fadd_rn(acc, (mine & (1u << (4 * q + 1))) ? v.y : 0.0f);
+        acc = __fadd_rn(acc, (mine & (1u << (4 * q + 2))) ? v.z : 0.0f);
+        acc = __fadd_rn(acc, (mine & (1u << (4 * q + 3))) ? v.w : 0.0f);
       }
       if (leader) ssum[k[u]] = acc;
+      buf ^= 1;
       __syncwarp();
     }
   }
