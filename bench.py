@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sensor", default="HDL_64E")
-    ap.add_argument("--frames", type=int, default=2220, help="frames resident per GPU per step (device path)")
+    ap.add_argument("--frames", type=int, default=4440, help="frames resident per GPU per step (device path)")
     ap.add_argument("--e2e-frames", type=int, default=256, help="frames per step of the host-buffer (e2e) path")
     ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic frames generated, then tiled")
     ap.add_argument("--wave", type=int, default=int(os.environ.get("BEVGEN_WAVE", "2220")), help="frames per launch wave")

@@ -61,8 +61,8 @@ struct bevgen_ctx {
   cudaStream_t s_copy = 0, s_comp = 0, s_d2h = 0;
   float* cnt_lut = 0;
   Scratch sc_dev;            // scratch of the device path (waves on the compute stream)
-  Scratch sc_aux;            // second scratch set: consecutive waves are software-pipelined (see bevgen_process_device)
-  cudaStream_t s_aux = 0;    // high-priority stream that only runs the sector sweep
+  Scratch sc_aux;            // second scratch set for the waves that run on s_aux
+  cudaStream_t s_aux = 0;    // second compute stream for odd waves
   cudaEvent_t ev_front[2] = {0, 0}, ev_sweep[2] = {0, 0}; int n_dev_streams = 2;
   int64_t* offs_d = 0; size_t offs_cap = 0;
   bool lanes_ready = false; Lane lanes[3];
@@ -173,6 +173,9 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
   CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
   for (auto& e : c->pev) CK(cudaEventCreate(&e));
   CK(cudaFuncSetAttribute(k_finalize_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BIN));
+  // (measured: forcing the max-shared carveout on the ordering kernels makes k_order_fill 1.8x slower - it relies on L1)
+  CK(cudaFuncSetAttribute(k_sector_mean, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_finalize_bin, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaMalloc(&c->cnt_lut, ((size_t)sp.S + 1) * sizeof(float)));
   k_build_cnt_lut<<<1, 32, 0, c->s_comp>>>(sp.S, c->cnt_lut);
   CK(cudaGetLastError());
@@ -183,7 +186,8 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
     if (alloc_scratch(c->sc_aux, max_frames, sp.S)) { delete c; return -1; }
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CK(cudaStreamCreateWithPriority(&c->s_aux, cudaStreamNonBlocking, hi));
+    (void)lo; (void)hi;
+    CK(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
       CK(cudaEventCreateWithFlags(&c->ev_front[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&c->ev_sweep[i], cudaEventDisableTiming));
@@ -308,42 +312,24 @@ extern "C" int bevgen_process_device(bevgen_ctx* c, int nf, const int64_t* offse
   const size_t S = c->sp.S;
   DevIn di; di.x = (float*)in->x; di.y = (float*)in->y; di.z = (float*)in->z; di.inten = (float*)in->intensity;
   di.row = (uint16_t*)in->row; di.col = (uint16_t*)in->col; di.label = (int16_t*)in->label;
-  // Software pipeline across waves (two scratch sets).  Main stream: front(0) front(1) back(0) front(2) back(1) ...;
-  // the sweep of wave w runs on the high-priority stream between front(w) and back(w), so the MIO/latency-bound
-  // sweep overlaps the bandwidth-bound front of wave w+1 and back of wave w-1.  Profiling serialises everything.
+  // Consecutive waves alternate between the compute stream and an auxiliary stream (own scratch set), so kernels of
+  // two waves interleave on the SMs (e.g. the latency-bound sweep of one wave with the ordering kernels of the other).
+  // Measured alternatives (profiles/r1_notes.md): a front/sweep/back software pipeline with a high-priority sweep
+  // stream was slower - sweep and ordering kernels contend for the same L1/LSU data pipe.  Profiling serialises.
   const int nw = (nf + c->max_frames - 1) / c->max_frames;
-  const bool pipe = c->n_dev_streams == 2 && !c->prof && nw > 1;
-  auto wave_args = [&](int w) {
+  const bool two = c->n_dev_streams == 2 && !c->prof && nw > 1;
+  if (two) { CK(cudaEventRecord(c->ev_front[0], c->s_comp)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_front[0], 0)); }
+  for (int w = 0; w < nw; w++) {
     const int f0 = w * c->max_frames;
     const int n = std::min(c->max_frames, nf - f0);
     int max_n = 0;
     for (int f = f0; f < f0 + n; f++) max_n = std::max<int64_t>(max_n, offsets[f + 1] - offsets[f]);
     DevOut dout; dout.label = out->label + (size_t)f0 * S; dout.owner = out->owner + (size_t)f0 * S;
     dout.single = out->single_bev + (size_t)f0 * CELLS; dout.multi = out->multi_bev + (size_t)f0 * LAYERS * CELLS;
-    return WaveArgs{(pipe && (w & 1)) ? &c->sc_aux : &c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout};
-  };
-  if (!pipe) {
-    for (int w = 0; w < nw; w++) {
-      WaveArgs a = wave_args(w);
-      if (wave_front(c, c->s_comp, a, c->prof) || wave_sweep(c, c->s_comp, a, c->prof) || wave_back(c, c->s_comp, a, c->prof)) return -1;
-    }
-    return 0;
+    const bool aux = two && (w & 1);
+    if (run_wave(c, aux ? c->s_aux : c->s_comp, aux ? c->sc_aux : c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout, c->prof)) return -1;
   }
-  for (int w = 0; w <= nw; w++) {
-    if (w < nw) {
-      WaveArgs a = wave_args(w);
-      if (wave_front(c, c->s_comp, a, false)) return -1;
-      CK(cudaEventRecord(c->ev_front[w & 1], c->s_comp));
-      CK(cudaStreamWaitEvent(c->s_aux, c->ev_front[w & 1], 0));
-      if (wave_sweep(c, c->s_aux, a, false)) return -1;
-      CK(cudaEventRecord(c->ev_sweep[w & 1], c->s_aux));
-    }
-    if (w >= 1) {
-      WaveArgs a = wave_args(w - 1);
-      CK(cudaStreamWaitEvent(c->s_comp, c->ev_sweep[(w - 1) & 1], 0));
-      if (wave_back(c, c->s_comp, a, false)) return -1;
-    }
-  }
+  if (two) { CK(cudaEventRecord(c->ev_sweep[0], c->s_aux)); CK(cudaStreamWaitEvent(c->s_comp, c->ev_sweep[0], 0)); }
   return 0;
 }
 

@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4*
     const unsigned heads = __ballot_sync(0xffffffffu, head);
     if (head && k2 != NO_KEY) {
       const unsigned above = heads & ~((2u << lane) - 1u);            // heads strictly above this lane
-      atomicAdd(&cntf[key], (uint32_t)((above ? __ffs(above) - 1 : 32) - lane));
+      const int nxt = above ? __ffs(above) - 1 : 32;
+      atomicAdd(&cntf[key], (uint32_t)(nxt - lane));
     }
   };
 
@@ -335,8 +336,11 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
       const bool valid = k[u] != NO_KEY;
       const unsigned vm = __ballot_sync(0xffffffffu, valid);
       if (vm == 0) continue;
+      // Group the lanes by sector (exact, also for A B A patterns).  The group's lowest lane leads; that test is plain
+      // mask logic - bit-scan ops (FLO: ffs/clz/popc) run on the quarter-rate XU pipe and measurably stall this
+      // latency-bound single-warp kernel, so the sweep contains none.
       const unsigned peers = __match_any_sync(0xffffffffu, valid ? k[u] : NO_KEY);
-      const bool leader = valid && lane == __ffs(peers) - 1;
+      const bool leader = valid && (peers & ((1u << lane) - 1u)) == 0u;
       const unsigned mine = leader ? peers : 0u;       // lanes whose z this lane folds, in lane (= slot) order
       // Stage the 32 heights once; every leader then reads them back as broadcast 128-bit words (all leaders read the
       // same address => one shared-memory wavefront per read) instead of 32 warp shuffles through the same MIO pipe.
@@ -344,15 +348,16 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
       __syncwarp();
       float acc = leader ? ssum[k[u]] : 0.0f;
       const float4* z4 = reinterpret_cast<const float4*>(zb[buf]);
+      float4 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) v[q] = z4[q];        // 8 independent broadcast reads, issued back to back
+      // the only serial dependence is the leader's chain acc = fl(acc + z) in slot order (:198); selects are off it
 #pragma unroll
       for (int q = 0; q < 8; q++) {
-        if (((vm >> (4 * q)) & 0xFu) == 0) continue;   // warp-uniform: no ground slot in this quad
-        const float4 v = z4[q];
-        // the only serial dependence is the leader's chain acc = fl(acc + z) in slot order (:198); selects are off it
-        acc = __fadd_rn(acc, (mine & (1u << (4 * q + 0))) ? v.x : 0.0f);
-        acc = __fadd_rn(acc, (mine & (1u << (4 * q + 1))) ? v.y : 0.0f);
-        acc = __fadd_rn(acc, (mine & (1u << (4 * q + 2))) ? v.z : 0.0f);
-        acc = __fadd_rn(acc, (mine & (1u << (4 * q + 3))) ? v.w : 0.0f);
+        acc = __fadd_rn(acc, (mine & (1u << (4 * q + 0))) ? v[q].x : 0.0f);
+        acc = __fadd_rn(acc, (mine & (1u << (4 * q + 1))) ? v[q].y : 0.0f);
+        acc = __fadd_rn(acc, (mine & (1u << (4 * q + 2))) ? v[q].z : 0.0f);
+        acc = __fadd_rn(acc, (mine & (1u << (4 * q + 3))) ? v[q].w : 0.0f);
       }
       if (leader) ssum[k[u]] = acc;
       buf ^= 1;
