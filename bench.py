@@ -155,7 +155,8 @@ def main():
     batch = tile_batch(distinct, F)
     n_total = int(batch["offsets"][-1])
     din = {k: torch.from_numpy(batch[k]).to(dev) for k in FIELDS}
-    dout = dict(label=torch.empty((F, S), dtype=torch.int16, device=dev), owner=torch.empty((F, S), dtype=torch.int32, device=dev),
+    dout = dict(label=torch.empty((F, S), dtype=torch.int16, device=dev),
+                winner=torch.zeros(pkg.winner_words(n_total, F), dtype=torch.int32, device=dev),
                 single=torch.empty((F, 224 * 224), dtype=torch.uint8, device=dev),
                 multi=torch.empty((F, 24 * 224 * 224), dtype=torch.uint8, device=dev))
     pin, pout = {k: v.data_ptr() for k, v in din.items()}, {k: v.data_ptr() for k, v in dout.items()}
@@ -234,7 +235,7 @@ def main():
     for k in FIELDS:
         a = pkg.pinned_empty(hb[k].shape, hb[k].dtype); a[...] = hb[k]; hin[k] = a
     hin["offsets"] = hb["offsets"]
-    hout = g.alloc_outputs(Fe, pinned=True)
+    hout = g.alloc_outputs(Fe, pinned=True, n_total=int(hb["offsets"][-1]))
     h2d = int(sum(hin[k].nbytes for k in FIELDS)) + hb["offsets"].nbytes
     d2h = int(sum(v.nbytes for v in hout.values()))
     estep = lambda: g.process_host(hin, hout)

@@ -60,16 +60,23 @@ typedef struct bevgen_points {
 
 /* Per-frame outputs, frame-major. S = n_scan*horizon_scan.
  *   label      [F][S]           labels of the ordered cloud after markGroundPoints (0 = ground or empty slot)
- *   owner      [F][S]           1 + index (within the frame) of the input point that occupies the slot, 0 = empty;
- *                               with the original records this is the ordered cloud savePCDFileBinary writes (:756)
+ *   winner_bits                 one bit per INPUT point: set iff the point is the last writer of its (row, col) slot in
+ *                               getOrderedCloud's serial loop (:102-116), i.e. the record that ends up in the ordered
+ *                               cloud savePCDFileBinary writes (:756); slot = row*Horizon_SCAN + col is the caller's own
+ *                               data.  Frame f's bits start at 32-bit word (offsets[f] >> 5) + f; point i of the frame is
+ *                               bit (i & 31) of word (i >> 5) from there.  bevgen_winner_words(n_total, F) words in all;
+ *                               words between two frames are unspecified.
  *   single_bev [F][224][224]    computeAndSaveSingleBev matrix (:340-356)
  *   multi_bev  [F][24][224][224] computeAndSaveMultiBev layers = the .bin payload (:271-292, :307-314)          */
 typedef struct bevgen_outputs {
   int16_t *label;
-  uint32_t *owner;
+  uint32_t *winner_bits;
   uint8_t *single_bev;
   uint8_t *multi_bev;
 } bevgen_outputs;
+
+/* Number of 32-bit words of bevgen_outputs.winner_bits for F frames holding n_total points. */
+static inline size_t bevgen_winner_words(int64_t n_total, int n_frames) { return (size_t)(n_total >> 5) + (size_t)n_frames + 1; }
 
 /* parseSensorType + getSensorParams (src/Utility.cpp:72-124): substring match "HDL_32E" / "HDL_64E" / "OS1_64";
  * fills the BEV literals and an identity transform.  Returns the SensorType enum value (0,1,2) or -1 if unknown
@@ -104,8 +111,8 @@ BEVGEN_API int bevgen_sync(bevgen_ctx *ctx);
  * frame's event and copies the results out.  At most `max_frames_per_batch` frames may be in flight.     */
 BEVGEN_API int bevgen_submit(bevgen_ctx *ctx, int frame_id, int n_in, const float *x, const float *y, const float *z,
                   const float *intensity, const uint16_t *row, const uint16_t *col, const int16_t *label);
-BEVGEN_API int bevgen_collect(bevgen_ctx *ctx, int frame_id, int16_t *label_out, uint32_t *owner_out, uint8_t *single_bev,
-                   uint8_t *multi_bev);
+BEVGEN_API int bevgen_collect(bevgen_ctx *ctx, int frame_id, int16_t *label_out, uint32_t *winner_bits /* (n_in+31)/32 words */,
+                   uint8_t *single_bev, uint8_t *multi_bev);
 
 /* selectMajorFrames (BatchMultiBevGen.cpp:502-566).  xyz = K*3 host floats (Pose6f x,y,z, :441-444).
  * major_idx (host, capacity K) receives the M major-frame indices; *n_major = M.  overlap_nn (host, K, may be
@@ -126,8 +133,8 @@ BEVGEN_API int bevgen_cloud_manip(bevgen_ctx *ctx, int64_t n, const float *rt, c
 
 /* ---- introspection for bench / tests (no reference counterpart) ---------------------------------------------- */
 #define BEVGEN_N_STAGES 8
-/* Stage order: 0 clear, 1 order_claim, 2 order_fill, 3 ground_mark, 4 sector_mean, 5 finalize_bin_scatter,
- * 6..7 reserved.  When profiling is enabled, process_device brackets every stage with CUDA events on the compute
+/* Stage order: 0 clear, 1 order (claim), 2 order_fill (large range images only), 3 ground_mark, 4 sector_mean,
+ * 5 finalize_bin_scatter, 6..7 reserved.  When profiling is enabled, process_device brackets every stage with CUDA events on the compute
  * stream; stage_ms returns the accumulated milliseconds and launch counts since the last reset. */
 BEVGEN_API int bevgen_set_profiling(bevgen_ctx *ctx, int enabled);
 BEVGEN_API int bevgen_stage_ms(bevgen_ctx *ctx, float *ms /*[BEVGEN_N_STAGES]*/, int64_t *launches /*[BEVGEN_N_STAGES]*/);

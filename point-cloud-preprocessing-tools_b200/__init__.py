@@ -37,7 +37,35 @@ class Points(C.Structure):
 
 
 class Outputs(C.Structure):
-    _fields_ = [("label", C.c_void_p), ("owner", C.c_void_p), ("single_bev", C.c_void_p), ("multi_bev", C.c_void_p)]
+    _fields_ = [("label", C.c_void_p), ("winner_bits", C.c_void_p), ("single_bev", C.c_void_p), ("multi_bev", C.c_void_p)]
+
+
+def winner_words(n_total, n_frames):
+    """bevgen_winner_words (include/bevgen.h)."""
+    return (int(n_total) >> 5) + int(n_frames) + 1
+
+
+def winner_mask(winner, offsets, f):
+    """bool[n_f]: which input points of frame f survive getOrderedCloud (unpacks bevgen_outputs.winner_bits)."""
+    o, e = int(offsets[f]), int(offsets[f + 1])
+    n = e - o
+    w0 = (o >> 5) + f
+    words = np.asarray(winner[w0:w0 + (n + 31) // 32], np.uint32)
+    return np.unpackbits(words.view(np.uint8), bitorder="little")[:n].astype(bool)
+
+
+def owner_from_winner(winner, offsets, row, col, H, S):
+    """[F][S] uint32, 1 + index of the input point that occupies the slot (0 = empty): the ordered cloud of
+    getOrderedCloud (BatchMultiBevGen.cpp:94-117) expressed as a gather table, rebuilt on the host from the winner bits
+    and the caller's own row/col — what a host does to write non_ground_point_cloud/*.pcd (:756)."""
+    F = len(offsets) - 1
+    own = np.zeros((F, S), np.uint32)
+    for f in range(F):
+        o, e = int(offsets[f]), int(offsets[f + 1])
+        idx = np.nonzero(winner_mask(winner, offsets, f))[0]
+        slot = row[o:e][idx].astype(np.int64) * H + col[o:e][idx].astype(np.int64)
+        own[f, slot] = (idx + 1).astype(np.uint32)
+    return own
 
 
 EXPORTS = ["bevgen_sensor_params", "bevgen_create", "bevgen_destroy", "bevgen_last_error", "bevgen_host_alloc",
@@ -156,27 +184,33 @@ class BevGen:
             pass
 
     # ---- hot loop -------------------------------------------------------------------------------------------
-    def alloc_outputs(self, F, pinned=False):
+    def alloc_outputs(self, F, pinned=False, n_total=None):
         mk = pinned_empty if pinned else np.empty
-        return dict(label=mk((F, self.S), np.int16), owner=mk((F, self.S), np.uint32),
-                    single=mk((F, GRID, GRID), np.uint8), multi=mk((F, LAYERS, GRID, GRID), np.uint8))
+        n_total = F * self.max_pts if n_total is None else n_total
+        out = dict(label=mk((F, self.S), np.int16), winner=mk((winner_words(n_total, F),), np.uint32),
+                   single=mk((F, GRID, GRID), np.uint8), multi=mk((F, LAYERS, GRID, GRID), np.uint8))
+        out["winner"][...] = 0      # the library writes every word of a frame's range and zeroes the gaps; the tail word is spare
+        return out
 
     def process_host(self, batch, out=None):
         """batch: dict x,y,z,intensity,row,col,label (+offsets int64[F+1]) of HOST numpy arrays."""
         offs = np.ascontiguousarray(batch["offsets"], np.int64)
         F = len(offs) - 1
-        out = out or self.alloc_outputs(F)
+        user_out = out is not None
+        out = out or self.alloc_outputs(F, n_total=int(offs[-1]))
         arrs = [_as(batch[k], t) for k, t in _FIELDS]      # keep converted temporaries alive across the call
         pts = Points(*[_ptr(a) for a in arrs])
-        o = Outputs(_ptr(out["label"]), _ptr(out["owner"]), _ptr(out["single"]), _ptr(out["multi"]))
+        o = Outputs(_ptr(out["label"]), _ptr(out["winner"]), _ptr(out["single"]), _ptr(out["multi"]))
         _ck(lib().bevgen_process_host(self._ctx, C.c_int(F), _ptr(offs), C.byref(pts), C.byref(o)))
+        if not user_out:   # convenience for tests: the ordered cloud as a gather table (host-side unpack of the winner bits)
+            out["owner"] = owner_from_winner(out["winner"], offs, arrs[4], arrs[5], self.params.horizon_scan, self.S)
         return out
 
     def process_device(self, F, offsets, dev_in, dev_out):
         """dev_in / dev_out: dicts of integer DEVICE pointers (same keys as the host form); async on the compute stream."""
         offs = np.ascontiguousarray(offsets, np.int64)
         pts = Points(*[C.c_void_p(int(dev_in[k])) for k, _ in _FIELDS])
-        o = Outputs(C.c_void_p(int(dev_out["label"])), C.c_void_p(int(dev_out["owner"])), C.c_void_p(int(dev_out["single"])),
+        o = Outputs(C.c_void_p(int(dev_out["label"])), C.c_void_p(int(dev_out["winner"])), C.c_void_p(int(dev_out["single"])),
                     C.c_void_p(int(dev_out["multi"])))
         _ck(lib().bevgen_process_device(self._ctx, C.c_int(F), _ptr(offs), C.byref(pts), C.byref(o)))
 
@@ -188,11 +222,17 @@ class BevGen:
         a = [_as(f[k], t) for k, t in _FIELDS]
         _ck(lib().bevgen_submit(self._ctx, C.c_int(frame_id), C.c_int(n), *[_ptr(v) for v in a]))
 
-    def collect(self, frame_id):
+    def collect(self, frame_id, frame=None):
+        """frame: the submitted frame (for row/col) - then the result also carries the 'owner' gather table."""
         out = self.alloc_outputs(1)
-        _ck(lib().bevgen_collect(self._ctx, C.c_int(frame_id), _ptr(out["label"]), _ptr(out["owner"]), _ptr(out["single"]),
+        _ck(lib().bevgen_collect(self._ctx, C.c_int(frame_id), _ptr(out["label"]), _ptr(out["winner"]), _ptr(out["single"]),
                                  _ptr(out["multi"])))
-        return {k: v[0] for k, v in out.items()}
+        res = {k: (v if k == "winner" else v[0]) for k, v in out.items()}
+        if frame is not None:
+            n = len(frame["row"])
+            res["owner"] = owner_from_winner(out["winner"], np.array([0, n]), _as(frame["row"], np.uint16), _as(frame["col"], np.uint16),
+                                             self.params.horizon_scan, self.S)[0]
+        return res
 
     # ---- labels ---------------------------------------------------------------------------------------------
     def select_major(self, xyz):

@@ -31,10 +31,13 @@ static int fail(const std::string& m) { g_err = m; return -1; }
 namespace {
 
 struct DevIn { float *x = 0, *y = 0, *z = 0, *inten = 0; uint16_t *row = 0, *col = 0; int16_t* label = 0; };
-struct DevOut { int16_t* label = 0; uint32_t* owner = 0; uint8_t* single = 0; uint8_t* multi = 0; };
+struct DevOut { int16_t* label = 0; uint32_t* wbits = 0; uint8_t* single = 0; uint8_t* multi = 0; };
+static size_t wwords(size_t n_total, size_t frames) { return (n_total >> 5) + frames + 1; }
 
 struct Scratch {            // device scratch for one wave of up to `frames` frames
   float4* rec = 0; uint16_t* gkey = 0; float* gz = 0; uint32_t* cnt = 0; float* avg = 0;
+  uint4* gsum = 0; uint32_t* slow = 0;   // per (row, 32-column group) summaries; per-frame "use the sweep kernel" flag
+  uint32_t* owner = 0;                   // [frames][S] claim table, only for range images too large for k_order's shared memory
 };
 
 struct Lane {               // host-path double buffer: device staging of inputs/outputs + scratch
@@ -47,7 +50,7 @@ struct Slot {               // submit/collect ring entry: one frame, own stream,
   Scratch sc; DevIn in; DevOut out;
   char* pin_in = 0; char* pin_out = 0; int64_t* offs_d = 0;
   cudaStream_t st = 0; cudaEvent_t done = 0;
-  int frame_id = -1; bool busy = false;
+  int frame_id = -1; bool busy = false; int n_in = 0;
 };
 
 }  // namespace
@@ -60,6 +63,7 @@ struct bevgen_ctx {
   int max_pts = 0, max_frames = 0;
   cudaStream_t s_copy = 0, s_comp = 0, s_d2h = 0;
   float* cnt_lut = 0;
+  int seg_cap = SEG_CAP;     // BEVGEN_SEG_CAP (tests): frames with more segments take the sweep kernel
   Scratch sc_dev;            // scratch of the device path (waves on the compute stream)
   Scratch sc_aux;            // second scratch set for the waves that run on s_aux
   cudaStream_t s_aux = 0;    // second compute stream for odd waves
@@ -75,7 +79,7 @@ struct bevgen_ctx {
   int64_t launches = 0;
 };
 
-static const char* kStageNames[BEVGEN_N_STAGES] = {"clear", "order_claim", "order_fill", "ground_mark",
+static const char* kStageNames[BEVGEN_N_STAGES] = {"clear", "order", "order_fill", "ground_mark",
                                                    "sector_mean", "finalize_bin_scatter", "reserved6", "reserved7"};
 
 // ---- params ---------------------------------------------------------------------------------------------------
@@ -104,7 +108,13 @@ extern "C" void* bevgen_host_alloc(size_t bytes) {
 extern "C" void bevgen_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ---- allocation helpers ---------------------------------------------------------------------------------------
-static int alloc_scratch(Scratch& s, size_t frames, size_t S) {
+static size_t gsum_per_frame(const SensorDev& sp) { return (size_t)(sp.G + 1) * ((sp.H + 31) / 32); }
+static bool fused_order(const SensorDev& sp) { return ord_smem_bytes(sp.S) <= 200 * 1024; }
+static int alloc_scratch(Scratch& s, size_t frames, const SensorDev& sp) {
+  const size_t S = sp.S;
+  if (!fused_order(sp)) CK(cudaMalloc(&s.owner, frames * S * sizeof(uint32_t)));
+  CK(cudaMalloc(&s.gsum, frames * gsum_per_frame(sp) * sizeof(uint4)));
+  CK(cudaMalloc(&s.slow, frames * sizeof(uint32_t)));
   CK(cudaMalloc(&s.rec, frames * S * sizeof(float4)));
   CK(cudaMalloc(&s.gkey, frames * S * sizeof(uint16_t)));
   CK(cudaMalloc(&s.gz, frames * S * sizeof(float)));
@@ -112,18 +122,21 @@ static int alloc_scratch(Scratch& s, size_t frames, size_t S) {
   CK(cudaMalloc(&s.avg, frames * NSECT * sizeof(float)));
   return 0;
 }
-static void free_scratch(Scratch& s) { cudaFree(s.rec); cudaFree(s.gkey); cudaFree(s.gz); cudaFree(s.cnt); cudaFree(s.avg); s = Scratch(); }
+static void free_scratch(Scratch& s) {
+  cudaFree(s.rec); cudaFree(s.gkey); cudaFree(s.gz); cudaFree(s.cnt); cudaFree(s.avg); cudaFree(s.gsum); cudaFree(s.slow); cudaFree(s.owner);
+  s = Scratch();
+}
 static int alloc_io(DevIn& in, DevOut& out, size_t frames, size_t pts, size_t S) {
   const size_t n = frames * pts;
   CK(cudaMalloc(&in.x, n * 4)); CK(cudaMalloc(&in.y, n * 4)); CK(cudaMalloc(&in.z, n * 4)); CK(cudaMalloc(&in.inten, n * 4));
   CK(cudaMalloc(&in.row, n * 2)); CK(cudaMalloc(&in.col, n * 2)); CK(cudaMalloc(&in.label, n * 2));
-  CK(cudaMalloc(&out.label, frames * S * 2)); CK(cudaMalloc(&out.owner, frames * S * 4));
+  CK(cudaMalloc(&out.label, frames * S * 2)); CK(cudaMalloc(&out.wbits, (wwords(n, frames) + 2) * 4));
   CK(cudaMalloc(&out.single, frames * CELLS)); CK(cudaMalloc(&out.multi, frames * (size_t)LAYERS * CELLS));
   return 0;
 }
 static void free_io(DevIn& in, DevOut& out) {
   cudaFree(in.x); cudaFree(in.y); cudaFree(in.z); cudaFree(in.inten); cudaFree(in.row); cudaFree(in.col); cudaFree(in.label);
-  cudaFree(out.label); cudaFree(out.owner); cudaFree(out.single); cudaFree(out.multi);
+  cudaFree(out.label); cudaFree(out.wbits); cudaFree(out.single); cudaFree(out.multi);
   in = DevIn(); out = DevOut();
 }
 
@@ -173,6 +186,10 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
   CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
   for (auto& e : c->pev) CK(cudaEventCreate(&e));
   CK(cudaFuncSetAttribute(k_finalize_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BIN));
+  CK(cudaFuncSetAttribute(k_sector_mean_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SEG));
+  CK(cudaFuncSetAttribute(k_order, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // function-wide: the largest any context may ask for
+  CK(cudaFuncSetAttribute(k_sector_mean_seg, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (const char* e = getenv("BEVGEN_SEG_CAP")) c->seg_cap = std::max(0, std::min(SEG_CAP, atoi(e)));
   // (measured: forcing the max-shared carveout on the ordering kernels makes k_order_fill 1.8x slower - it relies on L1)
   CK(cudaFuncSetAttribute(k_sector_mean, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_finalize_bin, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -180,10 +197,10 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
   k_build_cnt_lut<<<1, 32, 0, c->s_comp>>>(sp.S, c->cnt_lut);
   CK(cudaGetLastError());
   c->launches++;
-  if (alloc_scratch(c->sc_dev, max_frames, sp.S)) { delete c; return -1; }
+  if (alloc_scratch(c->sc_dev, max_frames, sp)) { delete c; return -1; }
   if (const char* e = getenv("BEVGEN_STREAMS")) c->n_dev_streams = atoi(e) >= 2 ? 2 : 1;
   if (c->n_dev_streams == 2) {
-    if (alloc_scratch(c->sc_aux, max_frames, sp.S)) { delete c; return -1; }
+    if (alloc_scratch(c->sc_aux, max_frames, sp)) { delete c; return -1; }
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     (void)lo; (void)hi;
@@ -219,7 +236,7 @@ extern "C" void bevgen_destroy(bevgen_ctx* c) {
 //   front  = clear + order_claim + order_fill + ground_mark      (L2 / HBM bound)
 //   sweep  = sector_mean                                          (MIO / latency bound, few warps per SM)
 //   back   = finalize_bin_scatter                                 (HBM + shared-memory bound)
-struct WaveArgs { const Scratch* sc; int nf; const int64_t* offs_d; int64_t base; int max_n; DevIn in; DevOut out; };
+struct WaveArgs { const Scratch* sc; int nf; const int64_t* offs_d; int64_t base; int max_n; DevIn in; DevOut out; int frame0; };
 
 static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {
   const SensorDev& sp = c->sp;
@@ -230,33 +247,45 @@ static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
   const uint16_t *row = w.in.row - w.base, *col = w.in.col - w.base;
   const int16_t* lab = w.in.label - w.base;
   mark(0);
-  CK(cudaMemsetAsync(w.out.owner, 0, (size_t)w.nf * S * sizeof(uint32_t), st));
   CK(cudaMemsetAsync(w.sc->cnt, 0, (size_t)w.nf * NSECT * sizeof(uint32_t), st));
+  if (!fused_order(sp)) CK(cudaMemsetAsync(w.sc->owner, 0, (size_t)w.nf * S * sizeof(uint32_t), st));
   mark(1);
-  if (w.max_n > 0) {
-    dim3 g((w.max_n + 511) / 512, w.nf);
-    k_order_claim<<<g, 256, 0, st>>>(sp, w.offs_d, row, col, w.out.owner);
-  }
-  mark(2);
-  {
+  if (fused_order(sp)) {
+    k_order<<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, c->xf, w.offs_d, w.frame0, x, y, z, it, row, col, lab, w.sc->rec, w.out.wbits);
+    mark(2);
+    c->launches += 1;
+  } else {   // range image too large for shared memory: claim table in global memory (two kernels + the winner bits)
+    if (w.max_n > 0) {
+      dim3 g((w.max_n + 511) / 512, w.nf);
+      k_order_claim<<<g, 256, 0, st>>>(sp, w.offs_d, row, col, w.sc->owner);
+    }
+    mark(2);
     dim3 g((std::max<int>(w.max_n, (int)S) + 255) / 256, w.nf);
-    k_order_fill<<<g, 256, 0, st>>>(sp, c->xf, w.offs_d, x, y, z, it, row, col, lab, w.out.owner, w.sc->rec);
+    k_order_fill<<<g, 256, 0, st>>>(sp, c->xf, w.offs_d, x, y, z, it, row, col, lab, w.sc->owner, w.sc->rec);
+    if (w.max_n > 0) {
+      dim3 g2((w.max_n + 255) / 256, w.nf);
+      k_winner_bits<<<g2, 256, 0, st>>>(sp, w.offs_d, w.frame0, row, col, w.sc->owner, w.out.wbits);
+    }
+    c->launches += (w.max_n > 0 ? 3 : 1);
   }
   mark(3);
   {
     dim3 g((sp.H + 127) / 128, w.nf);
-    k_ground_mark<<<g, 128, 0, st>>>(sp, w.sc->rec, w.sc->gkey, w.sc->gz, w.sc->cnt);
+    k_ground_mark<<<g, 128, 0, st>>>(sp, w.sc->rec, w.sc->gkey, w.sc->gz, w.sc->cnt, w.sc->gsum);
   }
   mark(4);
   CK(cudaGetLastError());
-  c->launches += (w.max_n > 0 ? 3 : 2);
+  c->launches += 1;
   return 0;
 }
 static int wave_sweep(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {
-  k_sector_mean<<<w.nf, 32, NSECT * sizeof(float), st>>>(c->sp, w.sc->gkey, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->avg);
+  // segment form first; frames it cannot hold (> seg_cap segments) raise slow[f] and are swept by k_sector_mean
+  k_sector_mean_seg<<<w.nf, SEGT, SMEM_SEG, st>>>(c->sp, c->seg_cap, w.sc->gsum, w.sc->gkey, w.sc->gz, w.sc->cnt, c->cnt_lut,
+                                                  w.sc->avg, w.sc->slow);
+  k_sector_mean<<<w.nf, 32, NSECT * sizeof(float), st>>>(c->sp, w.sc->gkey, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->avg, w.sc->slow);
   if (prof) cudaEventRecord(c->pev[5], st);
   CK(cudaGetLastError());
-  c->launches += 1;
+  c->launches += 2;
   return 0;
 }
 static int wave_back(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {
@@ -269,15 +298,15 @@ static int wave_back(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pro
     for (int i = 0; i < 6; i++) {
       float ms = 0; CK(cudaEventElapsedTime(&ms, c->pev[i], c->pev[i + 1]));
       c->stage_ms[i] += ms;
-      c->stage_launches[i] += (i == 0) ? 2 : ((i == 1 && w.max_n == 0) ? 0 : 1);
+      c->stage_launches[i] += (i == 2 && fused_order(c->sp)) ? 0 : 1;
     }
   }
   return 0;
 }
 // all three stages back to back on one stream
 static int run_wave(bevgen_ctx* c, cudaStream_t st, const Scratch& sc, int nf, const int64_t* offs_d, int64_t base, int max_n,
-                    const DevIn& in, const DevOut& out, bool prof) {
-  WaveArgs w{&sc, nf, offs_d, base, max_n, in, out};
+                    const DevIn& in, const DevOut& out, bool prof, int frame0) {
+  WaveArgs w{&sc, nf, offs_d, base, max_n, in, out, frame0};
   if (wave_front(c, st, w, prof)) return -1;
   if (wave_sweep(c, st, w, prof)) return -1;
   return wave_back(c, st, w, prof);
@@ -324,10 +353,10 @@ extern "C" int bevgen_process_device(bevgen_ctx* c, int nf, const int64_t* offse
     const int n = std::min(c->max_frames, nf - f0);
     int max_n = 0;
     for (int f = f0; f < f0 + n; f++) max_n = std::max<int64_t>(max_n, offsets[f + 1] - offsets[f]);
-    DevOut dout; dout.label = out->label + (size_t)f0 * S; dout.owner = out->owner + (size_t)f0 * S;
+    DevOut dout; dout.label = out->label + (size_t)f0 * S; dout.wbits = out->winner_bits;   // words are indexed by absolute offsets
     dout.single = out->single_bev + (size_t)f0 * CELLS; dout.multi = out->multi_bev + (size_t)f0 * LAYERS * CELLS;
     const bool aux = two && (w & 1);
-    if (run_wave(c, aux ? c->s_aux : c->s_comp, aux ? c->sc_aux : c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout, c->prof)) return -1;
+    if (run_wave(c, aux ? c->s_aux : c->s_comp, aux ? c->sc_aux : c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout, c->prof, f0)) return -1;
   }
   if (two) { CK(cudaEventRecord(c->ev_sweep[0], c->s_aux)); CK(cudaStreamWaitEvent(c->s_comp, c->ev_sweep[0], 0)); }
   return 0;
@@ -348,7 +377,7 @@ static int host_chunk(const bevgen_ctx* c) { return std::min(c->max_frames, 48);
 static int ensure_lanes(bevgen_ctx* c) {
   if (c->lanes_ready) return 0;
   for (auto& l : c->lanes) {
-    if (alloc_scratch(l.sc, host_chunk(c), c->sp.S)) return -1;
+    if (alloc_scratch(l.sc, host_chunk(c), c->sp)) return -1;
     if (alloc_io(l.in, l.out, host_chunk(c), c->max_pts, c->sp.S)) return -1;
     CK(cudaEventCreateWithFlags(&l.ev_h2d, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&l.ev_comp, cudaEventDisableTiming));
@@ -388,11 +417,14 @@ extern "C" int bevgen_process_host(bevgen_ctx* c, int nf, const int64_t* offsets
     CK(cudaEventRecord(l.ev_h2d, c->s_copy));
     CK(cudaStreamWaitEvent(c->s_comp, l.ev_h2d, 0));
     if (l.used) CK(cudaStreamWaitEvent(c->s_comp, l.ev_d2h, 0));   // outputs of the previous wave have left
-    if (run_wave(c, c->s_comp, l.sc, n, c->offs_d + f0, base, max_n, l.in, l.out, false)) return -1;
+    // winner words of this chunk: [w0, w1) of the caller's array; the kernel indexes with absolute offsets / frame ids
+    const size_t w0 = (size_t)(base >> 5) + (size_t)f0, w1 = (size_t)(offsets[f0 + n] >> 5) + (size_t)(f0 + n);
+    DevOut lo = l.out; lo.wbits = l.out.wbits - w0;
+    if (run_wave(c, c->s_comp, l.sc, n, c->offs_d + f0, base, max_n, l.in, lo, false, f0)) return -1;
     CK(cudaEventRecord(l.ev_comp, c->s_comp));
     CK(cudaStreamWaitEvent(c->s_d2h, l.ev_comp, 0));
     CK(cudaMemcpyAsync(out->label + (size_t)f0 * S, l.out.label, (size_t)n * S * 2, cudaMemcpyDeviceToHost, c->s_d2h));
-    CK(cudaMemcpyAsync(out->owner + (size_t)f0 * S, l.out.owner, (size_t)n * S * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    CK(cudaMemcpyAsync(out->winner_bits + w0, l.out.wbits, (w1 - w0) * 4, cudaMemcpyDeviceToHost, c->s_d2h));
     CK(cudaMemcpyAsync(out->single_bev + (size_t)f0 * CELLS, l.out.single, (size_t)n * CELLS, cudaMemcpyDeviceToHost, c->s_d2h));
     CK(cudaMemcpyAsync(out->multi_bev + (size_t)f0 * LAYERS * CELLS, l.out.multi, (size_t)n * LAYERS * CELLS, cudaMemcpyDeviceToHost, c->s_d2h));
     CK(cudaEventRecord(l.ev_d2h, c->s_d2h));
@@ -412,10 +444,10 @@ static int ensure_slots(bevgen_ctx* c) {
   c->slots.resize(ns);
   const size_t S = c->sp.S;
   for (auto& s : c->slots) {
-    if (alloc_scratch(s.sc, 1, S)) return -1;
+    if (alloc_scratch(s.sc, 1, c->sp)) return -1;
     if (alloc_io(s.in, s.out, 1, c->max_pts, S)) return -1;
     CK(cudaHostAlloc((void**)&s.pin_in, in_bytes(c->max_pts) + 16, cudaHostAllocPortable));
-    CK(cudaHostAlloc((void**)&s.pin_out, S * 6 + CELLS + (size_t)LAYERS * CELLS, cudaHostAllocPortable));
+    CK(cudaHostAlloc((void**)&s.pin_out, ((size_t)c->max_pts / 32 + 4) * 4 + S * 2 + CELLS + (size_t)LAYERS * CELLS, cudaHostAllocPortable));
     CK(cudaMalloc(&s.offs_d, 2 * sizeof(int64_t)));
     CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -450,18 +482,19 @@ extern "C" int bevgen_submit(bevgen_ctx* c, int frame_id, int n_in, const float*
   CK(cudaMemcpyAsync(s->in.row, pr, n * 2, cudaMemcpyHostToDevice, s->st));
   CK(cudaMemcpyAsync(s->in.col, pc, n * 2, cudaMemcpyHostToDevice, s->st));
   CK(cudaMemcpyAsync(s->in.label, pl, n * 2, cudaMemcpyHostToDevice, s->st));
-  if (run_wave(c, s->st, s->sc, 1, s->offs_d, 0, n_in, s->in, s->out, false)) return -1;
+  if (run_wave(c, s->st, s->sc, 1, s->offs_d, 0, n_in, s->in, s->out, false, 0)) return -1;
   char* q = s->pin_out;
-  CK(cudaMemcpyAsync(q, s->out.owner, S * 4, cudaMemcpyDeviceToHost, s->st)); q += S * 4;
+  const size_t ww = ((size_t)c->max_pts / 32 + 4) * 4;
+  CK(cudaMemcpyAsync(q, s->out.wbits, ((n + 31) / 32) * 4, cudaMemcpyDeviceToHost, s->st)); q += ww;
   CK(cudaMemcpyAsync(q, s->out.label, S * 2, cudaMemcpyDeviceToHost, s->st)); q += S * 2;
   CK(cudaMemcpyAsync(q, s->out.single, CELLS, cudaMemcpyDeviceToHost, s->st)); q += CELLS;
   CK(cudaMemcpyAsync(q, s->out.multi, (size_t)LAYERS * CELLS, cudaMemcpyDeviceToHost, s->st));
   CK(cudaEventRecord(s->done, s->st));
-  s->busy = true; s->frame_id = frame_id;
+  s->busy = true; s->frame_id = frame_id; s->n_in = n_in;
   return 0;
 }
 
-extern "C" int bevgen_collect(bevgen_ctx* c, int frame_id, int16_t* label_out, uint32_t* owner_out, uint8_t* single_bev, uint8_t* multi_bev) {
+extern "C" int bevgen_collect(bevgen_ctx* c, int frame_id, int16_t* label_out, uint32_t* winner_bits, uint8_t* single_bev, uint8_t* multi_bev) {
   if (!c) return fail("bevgen_collect: null ctx");
   CK(cudaSetDevice(c->device));
   for (auto& s : c->slots) {
@@ -469,7 +502,8 @@ extern "C" int bevgen_collect(bevgen_ctx* c, int frame_id, int16_t* label_out, u
     CK(cudaEventSynchronize(s.done));
     const size_t S = c->sp.S;
     const char* q = s.pin_out;
-    if (owner_out) memcpy(owner_out, q, S * 4); q += S * 4;
+    if (winner_bits) memcpy(winner_bits, q, (((size_t)s.n_in + 31) / 32) * 4);
+    q += ((size_t)c->max_pts / 32 + 4) * 4;
     if (label_out) memcpy(label_out, q, S * 2); q += S * 2;
     if (single_bev) memcpy(single_bev, q, CELLS); q += CELLS;
     if (multi_bev) memcpy(multi_bev, q, (size_t)LAYERS * CELLS);

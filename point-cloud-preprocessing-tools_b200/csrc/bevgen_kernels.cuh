@@ -212,6 +212,183 @@ __global__ void __launch_bounds__(256) k_order_fill(SensorDev sp, Xform xf, cons
   }
 }
 
+// Winner bits for the global-memory claim path: point i survives iff owner[slot(i)] == i + 1.
+// grid (ceil(max_n/256), F), block 256.
+__global__ void __launch_bounds__(256) k_winner_bits(SensorDev sp, const int64_t* __restrict__ offs, int frame0,
+                                                      const uint16_t* __restrict__ row, const uint16_t* __restrict__ col,
+                                                      const uint32_t* __restrict__ owner, uint32_t* __restrict__ winner_bits) {
+  const int f = blockIdx.y;
+  const int64_t o = offs[f];
+  const int n = (int)(offs[f + 1] - o);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i == 0)
+    for (int64_t w = (n + 31) >> 5; w < ((o + n) >> 5) + 1 - (o >> 5); w++) winner_bits[(o >> 5) + (frame0 + f) + w] = 0u;
+  if (i - (int)(threadIdx.x & 31) >= n) return;
+  bool win = false;
+  if (i < n) {
+    const unsigned r = row[o + i], c = col[o + i];
+    if (r < (unsigned)sp.N && c < (unsigned)sp.H) win = owner[(size_t)f * sp.S + r * sp.H + c] == (uint32_t)(i + 1);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, win);
+  if ((threadIdx.x & 31) == 0) winner_bits[(o >> 5) + (frame0 + f) + (i >> 5)] = m;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K0 order (fused) — getOrderedCloud (BatchMultiBevGen.cpp:94-117) in ONE pass structure, one CTA per frame, with
+// the slot bookkeeping in shared memory instead of an S-entry table in L2:
+//   occ  : 1 bit per slot, set by every valid point (atomicOr); a point that finds its bit already set marks the
+//   cont : "contended" bit of the slot (two or more input points map to it; 0.5 % of the slots on sensor data).
+// A point whose slot is not contended is the slot's only writer => it wins without any further communication and
+// scatters its record straight away.  Contended slots get a dense id (prefix popcount over `cont`), the serial
+// loop's last-writer-wins is max(input index) per id (shared-memory atomicMax), resolved in a second small pass.
+// Outputs: rec (ordered cloud, unowned slots zero = PointCloud::resize value-init, :98) and one WINNER bit per
+// input point (the host rebuilds the ordered cloud for savePCDFileBinary from it, :756).
+// Per point this costs one scattered 16-byte store to L2 and shared-memory atomics; the previous two-kernel form
+// (k_order_claim / k_order_fill, kept for range images too large for shared memory) paid an L2 atomic, an L2 probe
+// and the store.
+// grid F, block ORD_T, dynamic smem ord_smem_bytes(S).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ORD_T = 512;
+constexpr int ORD_CCAP = 4096;   // contended slots resolved per round
+constexpr int ORD_LCAP = 4096;   // contended points remembered between the passes (else the frame is re-scanned)
+__host__ __device__ inline size_t ord_smem_bytes(int S) {
+  const size_t W = ((size_t)S + 31) / 32;
+  return W * 4 * 3 + ORD_CCAP * 4 + ORD_LCAP * 4 + 64;
+}
+
+__global__ void __launch_bounds__(ORD_T) k_order(SensorDev sp, Xform xf, const int64_t* __restrict__ offs, int frame0,
+                                                  const float* __restrict__ x, const float* __restrict__ y,
+                                                  const float* __restrict__ z, const float* __restrict__ inten,
+                                                  const uint16_t* __restrict__ row, const uint16_t* __restrict__ col,
+                                                  const int16_t* __restrict__ label, float4* __restrict__ rec,
+                                                  uint32_t* __restrict__ winner_bits) {
+  extern __shared__ __align__(16) unsigned char ord_smem[];
+  const int W = (sp.S + 31) >> 5;
+  uint32_t* occ = reinterpret_cast<uint32_t*>(ord_smem);           // [W]
+  uint32_t* cont = occ + W;                                        // [W]
+  uint32_t* cmax = cont + W;                                       // [ORD_CCAP] 1 + largest input index per contended slot
+  uint32_t* clist = cmax + ORD_CCAP;                               // [ORD_LCAP] contended input points
+  uint32_t* misc = clist + ORD_LCAP;                               // [16] counters / scan carries
+  uint32_t* cpre = misc + 16;                                      // [W] contended slots before word w
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t o = offs[f];
+  const int n = (int)(offs[f + 1] - o);
+  const size_t fb = (size_t)f * sp.S;
+  const uint16_t* R = row + o; const uint16_t* C = col + o;
+  uint32_t* wb = winner_bits + (o >> 5) + (frame0 + f);            // this frame's winner words (see bevgen.h)
+  const unsigned N = (unsigned)sp.N, H = (unsigned)sp.H;
+
+  for (int i = tid; i < W; i += ORD_T) { occ[i] = 0u; cont[i] = 0u; }
+  if (tid < 16) misc[tid] = 0u;
+  if (tid == 0)   // words between this frame's bits and the next frame's first word are defined as zero
+    for (int64_t w = (n + 31) >> 5; w < ((o + n) >> 5) + 1 - (o >> 5); w++) wb[w] = 0u;
+  __syncthreads();
+  // ---- scan 1: occupancy + contention bits ----
+  for (int i0 = tid; i0 < n; i0 += 4 * ORD_T) {
+    unsigned r[4], c[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int i = i0 + u * ORD_T; r[u] = 0xFFFFu; c[u] = 0xFFFFu; if (i < n) { r[u] = R[i]; c[u] = C[i]; } }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * ORD_T;
+      if (i < n && r[u] < N && c[u] < H) {                         // :106-109
+        const unsigned slot = r[u] * H + c[u], bit = 1u << (slot & 31);
+        if (atomicOr(&occ[slot >> 5], bit) & bit) atomicOr(&cont[slot >> 5], bit);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- unowned slots keep the value-initialised record (:98); dense ids of the contended slots ----
+  for (int sl = tid; sl < sp.S; sl += ORD_T)
+    if (!((occ[sl >> 5] >> (sl & 31)) & 1u)) rec[fb + sl] = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    const int wpt = (W + ORD_T - 1) / ORD_T;                        // consecutive words per thread
+    const int w0 = min(tid * wpt, W), w1 = min(w0 + wpt, W);
+    unsigned loc = 0;
+    for (int w = w0; w < w1; w++) loc += __popc(cont[w]);
+    unsigned incl = loc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    uint32_t* wsum = occ;                                           // occ is dead from here on; reuse its first words
+    __syncthreads();
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    unsigned wbase = 0, total = 0;
+    for (int w = 0; w < ORD_T / 32; w++) { const unsigned t = wsum[w]; if (w < wid) wbase += t; total += t; }
+    unsigned run = wbase + incl - loc;
+    for (int w = w0; w < w1; w++) { cpre[w] = run; run += __popc(cont[w]); }
+    if (tid == 0) misc[1] = total;
+  }
+  __syncthreads();
+  const unsigned ncont = misc[1];
+  // ---- scan 2: winners of uncontended slots scatter their record; contended points are listed ----
+  for (int i0 = tid; i0 < ((n + 31) & ~31); i0 += 2 * ORD_T) {
+    unsigned r[2], c[2]; float px[2], py[2], pz[2], pi[2]; int16_t lb[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int i = i0 + u * ORD_T;
+      r[u] = 0xFFFFu; c[u] = 0xFFFFu; px[u] = py[u] = pz[u] = pi[u] = 0.f; lb[u] = 0;
+      if (i < n) { r[u] = R[i]; c[u] = C[i]; px[u] = x[o + i]; py[u] = y[o + i]; pz[u] = z[o + i]; pi[u] = inten[o + i]; lb[u] = label[o + i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int i = i0 + u * ORD_T;
+      if (i - lane >= n) continue;                                  // whole warp past the end (uniform)
+      const bool valid = i < n && r[u] < N && c[u] < H;
+      const unsigned slot = valid ? r[u] * H + c[u] : 0u, bit = 1u << (slot & 31);
+      const bool contended = valid && (cont[slot >> 5] & bit);
+      const bool win = valid && !contended;
+      if (win) {
+        float ox = px[u], oy = py[u], oz = pz[u];
+        if (xf.on) {   // pcl::transformPointCloud, PCL >= 1.9 SSE order (CloudManip.cpp:128)
+          ox = __fadd_rn(__fmul_rn(px[u], xf.m[0]), __fadd_rn(__fmul_rn(py[u], xf.m[1]), __fadd_rn(__fmul_rn(pz[u], xf.m[2]), xf.m[3])));
+          oy = __fadd_rn(__fmul_rn(px[u], xf.m[4]), __fadd_rn(__fmul_rn(py[u], xf.m[5]), __fadd_rn(__fmul_rn(pz[u], xf.m[6]), xf.m[7])));
+          oz = __fadd_rn(__fmul_rn(px[u], xf.m[8]), __fadd_rn(__fmul_rn(py[u], xf.m[9]), __fadd_rn(__fmul_rn(pz[u], xf.m[10]), xf.m[11])));
+        }
+        const unsigned w = (unsigned)(uint16_t)lb[u] | W_OWNED | (pi[u] == -1.0f ? W_NEG1 : 0u);
+        rec[fb + slot] = make_float4(ox, oy, oz, __uint_as_float(w));
+      }
+      if (contended) { const unsigned j = atomicAdd(&misc[0], 1u); if (j < ORD_LCAP) clist[j] = (uint32_t)i; }
+      const unsigned wm = __ballot_sync(0xffffffffu, win);
+      if (lane == 0) wb[i >> 5] = wm;
+    }
+  }
+  __syncthreads();
+  // ---- contended slots: last writer = largest input index (:102-116 is a serial loop), ORD_CCAP ids per round ----
+  const unsigned nlist = misc[0];
+  const bool listed = nlist <= ORD_LCAP;
+  const unsigned npts = listed ? nlist : (unsigned)n;
+  for (unsigned base = 0; base < ncont; base += ORD_CCAP) {
+    for (int j = tid; j < ORD_CCAP; j += ORD_T) cmax[j] = 0u;
+    __syncthreads();
+    for (int pass = 0; pass < 2; pass++) {
+      for (unsigned j = tid; j < npts; j += ORD_T) {
+        const unsigned i = listed ? clist[j] : j;
+        const unsigned rr = R[i], cc = C[i];
+        if (!(rr < N && cc < H)) continue;
+        const unsigned slot = rr * H + cc, bit = 1u << (slot & 31), cw = cont[slot >> 5];
+        if (!(cw & bit)) continue;
+        const unsigned id = cpre[slot >> 5] + __popc(cw & (bit - 1u)) - base;              // wraps to >= ORD_CCAP below the window
+        if (id >= ORD_CCAP) continue;
+        if (pass == 0) atomicMax(&cmax[id], i + 1u);
+        else if (cmax[id] == i + 1u) {
+          float px = x[o + i], py = y[o + i], pz = z[o + i];
+          if (xf.on) {
+            const float ox = __fadd_rn(__fmul_rn(px, xf.m[0]), __fadd_rn(__fmul_rn(py, xf.m[1]), __fadd_rn(__fmul_rn(pz, xf.m[2]), xf.m[3])));
+            const float oy = __fadd_rn(__fmul_rn(px, xf.m[4]), __fadd_rn(__fmul_rn(py, xf.m[5]), __fadd_rn(__fmul_rn(pz, xf.m[6]), xf.m[7])));
+            const float oz = __fadd_rn(__fmul_rn(px, xf.m[8]), __fadd_rn(__fmul_rn(py, xf.m[9]), __fadd_rn(__fmul_rn(pz, xf.m[10]), xf.m[11])));
+            px = ox; py = oy; pz = oz;
+          }
+          const unsigned w = (unsigned)(uint16_t)label[o + i] | W_OWNED | (inten[o + i] == -1.0f ? W_NEG1 : 0u);
+          rec[fb + slot] = make_float4(px, py, pz, __uint_as_float(w));
+          atomicOr(&wb[i >> 5], 1u << (i & 31));
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // K1 ground_mark — markGroundPoints loop 1 (BatchMultiBevGen.cpp:139-184).  One thread per range-image column,
 // walking rows N-1 .. N-G like the reference; consecutive lanes = consecutive columns, so every record load is a
@@ -240,7 +417,7 @@ __device__ __forceinline__ bool ground_decision(const SensorDev& sp, const float
 
 __global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4* __restrict__ rec,
                                                       uint16_t* __restrict__ gkey, float* __restrict__ gz,
-                                                      uint32_t* __restrict__ cnt) {
+                                                      uint32_t* __restrict__ cnt, uint4* __restrict__ gsum) {
   const int f = blockIdx.y;
   const int c0 = blockIdx.x * 128 + threadIdx.x;
   const bool act = c0 < sp.H;
@@ -256,6 +433,11 @@ __global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4*
   const int dplus = (c + 2 >= H ? c + 2 - H : c + 2) - c;       // (col+2) % H, relative to c           (:147)
   const int dminus = -2;                                        // (col-2) % H stays negative in C++ for col < 2 (:152)
 
+  // per (row, 32-column group) summary for the segment form of loop 2 (k_sector_mean_seg)
+  const int NG = (H + 31) >> 5;
+  uint4* gs = gsum + ((size_t)f * (sp.G + 1) + sp.G) * NG + (c0 >> 5);     // row N-1 first, walked upwards by -NG
+  const unsigned lt = (1u << lane) - 1u;
+
   auto emit = [&](const float4& p, bool gm1) {
     unsigned key = NO_KEY;
     if (gm1) key = sector_of(p.x, p.y);
@@ -270,6 +452,20 @@ __global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4*
       const unsigned above = heads & ~((2u << lane) - 1u);            // heads strictly above this lane
       const int nxt = above ? __ffs(above) - 1 : 32;
       atomicAdd(&cntf[key], (uint32_t)(nxt - lane));
+    }
+    // Loop 2's float sums (:198) only change when a non-zero height is added, so the "participating" slots are the
+    // ground slots with z != 0 (NaN participates).  pm = participating lanes, hm = lanes whose sector differs from the
+    // previous participating lane of this group, fk / lk = sector of the first / last participating lane.
+    const bool part = k2 != NO_KEY && p.z != 0.0f;
+    const unsigned pm = __ballot_sync(0xffffffffu, part);
+    const unsigned below = pm & lt;
+    const unsigned pk = __shfl_sync(0xffffffffu, k2, (31 - __clz(below)) & 31);
+    const unsigned hm = __ballot_sync(0xffffffffu, part && below != 0u && pk != k2);
+    if (c0 - lane < H) {                                         // the group exists (warp-uniform)
+      if (lane == 0) { gs->x = pm; gs->y = hm; }
+      uint16_t* fl = reinterpret_cast<uint16_t*>(&gs->z);
+      if (part && below == 0u) fl[0] = (uint16_t)k2;
+      if (part && (pm >> lane) == 1u) fl[1] = (uint16_t)k2;
     }
   };
 
@@ -288,7 +484,7 @@ __global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4*
     emit(lower, !invalid && (ground || ground_prev));
     ground_prev = ground;
     lower = direct;
-    pr -= H; gk -= H; gzp -= H;
+    pr -= H; gk -= H; gzp -= H; gs -= NG;
   }
   emit(lower, ground_prev);   // row above the band only receives gm[row-1] = 1 (:181)
 }
@@ -304,8 +500,10 @@ __global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4*
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t* __restrict__ gkey,
                                                      const float* __restrict__ gz, const uint32_t* __restrict__ cnt,
-                                                     const float* __restrict__ cnt_lut, float* __restrict__ avg) {
+                                                     const float* __restrict__ cnt_lut, float* __restrict__ avg,
+                                                     const uint32_t* __restrict__ slow_flag) {
   extern __shared__ float ssum[];                 // [NSECT] running sums of this frame
+  if (slow_flag && !slow_flag[blockIdx.x]) return; // the segment form (k_sector_mean_seg) already did this frame
   __shared__ __align__(16) float zb[2][32];       // the current step's 32 heights (double-buffered)
   const int f = blockIdx.x, lane = threadIdx.x;
   for (int i = lane; i < NSECT; i += 32) ssum[i] = 0.0f;
@@ -366,6 +564,207 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
   }
   for (int i = lane; i < NSECT; i += 32)
     avg[(size_t)f * NSECT + i] = __fdiv_rn(ssum[i], cnt_lut[cnt[(size_t)f * NSECT + i]]);   // :210 IEEE divide
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2' sector_mean, segment form — the same order-exact sums as k_sector_mean, parallel across sectors instead of
+// along the slot order.  A sector's chain  sum = fl(sum + z)  (:198) only has to see ITS ground slots in row-major
+// order; chains of different sectors are independent.  k_ground_mark leaves one summary per (row, 32-column group);
+// from those this kernel cuts the band into segments = maximal stretches whose participating slots (ground, z != 0)
+// all lie in one sector.  gz is 0 on every other slot, and adding +-0 never changes a sum that starts at +0, so a
+// segment is folded by simply adding gz[start..end].  Segments are bucketed per sector in slot order (ordered list
+// + one warp assigning ranks with match_any), then one thread per sector folds its segments sequentially.
+// HDL_64E synthetic frames: ~2.7 k segments, ~350 active sectors, longest chain ~3 k additions.
+// Frames with more than `cap` segments raise slow_flag[f] and are handled by k_sector_mean (the sweep form).
+// grid F, block SEGT.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SEG_CAP = 4096;
+constexpr int SEGT = 512;
+constexpr int SMEM_SEG = SEG_CAP * 8 + NSECT * 8 + SEGT * 8 + 256 + SEG_CAP * 4 + (NSECT + 2) * 2 + 16 + (SEGT / 32) * 256 * 4;   // 106,944 B
+
+__global__ void __launch_bounds__(SEGT) k_sector_mean_seg(SensorDev sp, int cap, const uint4* __restrict__ gsum,
+                                                           const uint16_t* __restrict__ gkey, const float* __restrict__ gz,
+                                                           const uint32_t* __restrict__ cnt, const float* __restrict__ cnt_lut,
+                                                           float* __restrict__ avg, uint32_t* __restrict__ slow_flag) {
+  extern __shared__ __align__(16) unsigned char seg_smem[];
+  uint32_t* s_start = reinterpret_cast<uint32_t*>(seg_smem);   // [SEG_CAP] first slot of the segment
+  uint32_t* s_end = s_start + SEG_CAP;                          // [SEG_CAP] last participating slot
+  uint32_t* s_kcnt = s_end + SEG_CAP;                           // [NSECT] segments per sector
+  uint32_t* s_kbase = s_kcnt + NSECT;                           // [NSECT] bucket base, later bucket end
+  uint32_t* s_lk = s_kbase + NSECT;                             // [SEGT] sector of the last participating slot of the thread's groups
+  int* s_lp = reinterpret_cast<int*>(s_lk + SEGT);              // [SEGT] its slot (relative to the frame), -1 if none
+  uint32_t* s_scan = reinterpret_cast<uint32_t*>(s_lp + SEGT);  // [32]
+  uint32_t* s_warp = s_scan + 32;                               // [32]
+  uint16_t* s_key = reinterpret_cast<uint16_t*>(s_warp + 32);   // [SEG_CAP] sector of the segment
+  uint16_t* s_order = s_key + SEG_CAP;                          // [SEG_CAP] segment ids bucketed by sector, slot order kept
+  uint16_t* s_act = s_order + SEG_CAP;                          // [NSECT + 2] sectors that own at least one segment
+  uint32_t* s_nact = reinterpret_cast<uint32_t*>(s_act + NSECT + 2);
+  float* s_zb = reinterpret_cast<float*>(s_nact + 4);           // [SEGT/32][8][32] per-warp staging of 8 chunks of heights
+
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int H = sp.H, NG = (H + 31) >> 5;
+  const int n_groups = (sp.G + 1) * NG;
+  const int gpt = (n_groups + SEGT - 1) / SEGT;                 // consecutive groups per thread
+  const uint4* GS = gsum + (size_t)f * n_groups;
+  const size_t fb = (size_t)f * sp.S;
+  const uint16_t* K = gkey + fb;
+  const float* Z = gz + fb;
+  const int g0 = min(tid * gpt, n_groups), g1 = min(g0 + gpt, n_groups);
+  auto slot_of = [&](int g, int l) { const int rb = g / NG, cg = g - rb * NG; return (sp.band_row0 + rb) * H + cg * 32 + l; };
+
+  for (int i = tid; i < NSECT; i += SEGT) s_kcnt[i] = 0;
+  if (tid == 0) *s_nact = 0;
+  // ---- pass 1: last participating slot / sector of this thread's groups ----
+  {
+    unsigned lk = NO_KEY; int lp = -1;
+    for (int g = g0; g < g1; g++) {
+      const uint4 v = GS[g];
+      if (v.x) { lk = v.z >> 16; lp = slot_of(g, 31 - __clz(v.x)); }
+    }
+    s_lk[tid] = lk; s_lp[tid] = lp;
+  }
+  __syncthreads();
+  // carry-in: last participating slot before this thread's first group
+  unsigned ck = NO_KEY; int cp = -1;
+  for (int t = tid - 1; t >= 0; t--) if (s_lp[t] >= 0) { ck = s_lk[t]; cp = s_lp[t]; break; }
+  // ---- pass 2: count heads ----
+  unsigned nh = 0;
+  {
+    unsigned k = ck;
+    for (int g = g0; g < g1; g++) {
+      const uint4 v = GS[g];
+      if (!v.x) continue;
+      nh += __popc(v.y) + ((v.z & 0xFFFFu) != k ? 1u : 0u);
+      k = v.z >> 16;
+    }
+  }
+  // block exclusive scan of nh
+  unsigned incl = nh;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  unsigned wbase = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < SEGT / 32; w++) { const unsigned c = s_warp[w]; if (w < wid) wbase += c; total += c; }
+  const int nseg = (int)total;
+  if (nseg > cap) { if (tid == 0) slow_flag[f] = 1u; return; }    // uniform: the sweep kernel takes this frame
+  if (tid == 0) slow_flag[f] = 0u;
+  // ---- pass 3: emit segments in slot order ----
+  {
+    unsigned e = wbase + incl - nh;
+    unsigned k = ck; int lastp = cp;
+    for (int g = g0; g < g1; g++) {
+      const uint4 v = GS[g];
+      const unsigned pm = v.x;
+      if (!pm) continue;
+      unsigned hm = v.y;
+      if ((v.z & 0xFFFFu) != k) hm |= pm & (0u - pm);             // the first participating lane opens a segment
+      const int base = slot_of(g, 0);
+      while (hm) {
+        const int l = __ffs(hm) - 1; hm &= hm - 1;
+        const unsigned below = pm & ((1u << l) - 1u);
+        const int prev_end = below ? base + 31 - __clz(below) : lastp;
+        s_start[e] = (uint32_t)(base + l);
+        s_key[e] = K[base + l];
+        if (e > 0) s_end[e - 1] = (uint32_t)prev_end;
+        e++;
+      }
+      k = v.z >> 16; lastp = base + 31 - __clz(pm);
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && nseg > 0) {
+    int lp = -1;
+    for (int t = SEGT - 1; t >= 0; t--) if (s_lp[t] >= 0) { lp = s_lp[t]; break; }
+    s_end[nseg - 1] = (uint32_t)lp;
+  }
+  // ---- segments per sector, exclusive scan over sectors ----
+  for (int e = tid; e < nseg; e += SEGT) atomicAdd(&s_kcnt[s_key[e]], 1u);
+  __syncthreads();
+  {
+    constexpr int KPT = (NSECT + SEGT - 1) / SEGT;              // 8 sectors per thread
+    unsigned loc = 0;
+#pragma unroll
+    for (int j = 0; j < KPT; j++) { const int k = tid * KPT + j; if (k < NSECT) loc += s_kcnt[k]; }
+    unsigned inc2 = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += y; }
+    if (lane == 31) s_scan[wid] = inc2;
+    __syncthreads();
+    unsigned wb = 0;
+#pragma unroll
+    for (int w = 0; w < SEGT / 32; w++) if (w < wid) wb += s_scan[w];
+    unsigned run = wb + inc2 - loc;
+#pragma unroll
+    for (int j = 0; j < KPT; j++) { const int k = tid * KPT + j; if (k < NSECT) { s_kbase[k] = run; run += s_kcnt[k]; } }
+  }
+  __syncthreads();
+  // ---- one warp walks the ordered segment list and hands out positions: s_kbase[k] ends as the END of bucket k ----
+  if (wid == 0) {
+    for (int b = 0; b < nseg; b += 32) {
+      const int e = b + lane;
+      const bool valid = e < nseg;
+      const unsigned k = valid ? (unsigned)s_key[e] : NO_KEY;
+      const unsigned peers = __match_any_sync(0xffffffffu, k);
+      const unsigned pos = valid ? s_kbase[k] + __popc(peers & ((1u << lane) - 1u)) : 0u;
+      __syncwarp();
+      if (valid && (peers >> lane) == 1u) s_kbase[k] = pos + 1u;  // the group's highest lane publishes the new fill level
+      if (valid) s_order[pos] = (uint16_t)e;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // ---- one WARP per active sector folds its segments in slot order (:198), then the IEEE divide (:210) ----
+  // The warp loads 32 consecutive heights with one coalesced access (the next chunk is in flight while the current one
+  // is folded), stages them in shared memory and every lane runs the same serial chain over broadcast 128-bit reads;
+  // chunks are padded with +0, which never changes the sum.
+  for (int k = tid; k < NSECT; k += SEGT) {
+    if (s_kcnt[k]) s_act[atomicAdd(s_nact, 1u)] = (uint16_t)k;
+    else avg[(size_t)f * NSECT + k] = 0.0f;                     // 0 / num, num > 0
+  }
+  __syncthreads();
+  const unsigned n_act = *s_nact;
+  constexpr int CH = 8;                                           // chunks (of 32 heights) loaded per round: 8 loads in flight per warp
+  float* zb = s_zb + wid * (CH * 32);
+  for (unsigned a = wid; a < n_act; a += SEGT / 32) {
+    const unsigned k = s_act[a];
+    const unsigned n = s_kcnt[k];
+    const unsigned b0 = s_kbase[k] - n;
+    float acc = 0.0f;
+    unsigned s = 0;                                               // cursor: segment s of this sector, `off` heights consumed
+    unsigned e = s_order[b0];
+    unsigned st = s_start[e]; int rem = (int)(s_end[e] - st) + 1;
+    while (s < n) {
+      unsigned cst[CH]; int ccur[CH];
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        cst[c] = st; ccur[c] = s < n ? min(rem, 32) : 0;
+        st += 32; rem -= 32;
+        if (rem <= 0 && s < n) {
+          s++;
+          if (s < n) { e = s_order[b0 + s]; st = s_start[e]; rem = (int)(s_end[e] - st) + 1; }
+        }
+      }
+      float v[CH];
+#pragma unroll
+      for (int c = 0; c < CH; c++) v[c] = lane < ccur[c] ? Z[cst[c] + lane] : 0.0f;
+#pragma unroll
+      for (int c = 0; c < CH; c++) zb[c * 32 + lane] = v[c];
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const float4* z4 = reinterpret_cast<const float4*>(zb + c * 32);
+        const int nq = (ccur[c] + 3) >> 2;
+        for (int q = 0; q < nq; q++) {
+          const float4 t = z4[q];
+          acc = __fadd_rn(acc, t.x); acc = __fadd_rn(acc, t.y); acc = __fadd_rn(acc, t.z); acc = __fadd_rn(acc, t.w);
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) avg[(size_t)f * NSECT + k] = __fdiv_rn(acc, cnt_lut[cnt[(size_t)f * NSECT + k]]);
+  }
 }
 
 // num_ground_grid_points replay (:135, :205): lut[n] = fl(...fl(fl(0.01f + 1) + 1)... + 1), n additions.

@@ -142,25 +142,26 @@ static std::vector<float> read_poses(const std::string& file) {
 struct PinnedSet {     // pinned staging of one batch: SoA inputs + outputs
   size_t cap_pts = 0; int cap_frames = 0; size_t S = 0;
   float *x = 0, *y = 0, *z = 0, *inten = 0; uint16_t *row = 0, *col = 0; int16_t* label = 0;
-  int16_t* o_label = 0; uint32_t* o_owner = 0; uint8_t *o_single = 0, *o_multi = 0;
+  int16_t* o_label = 0; uint32_t* o_winner = 0; uint8_t *o_single = 0, *o_multi = 0;
   bool alloc(size_t pts, int frames, size_t S_) {
     release(); cap_pts = pts; cap_frames = frames; S = S_;
     auto A = [](size_t n) { return bevgen_host_alloc(n); };
     x = (float*)A(pts * 4); y = (float*)A(pts * 4); z = (float*)A(pts * 4); inten = (float*)A(pts * 4);
     row = (uint16_t*)A(pts * 2); col = (uint16_t*)A(pts * 2); label = (int16_t*)A(pts * 2);
-    o_label = (int16_t*)A((size_t)frames * S * 2); o_owner = (uint32_t*)A((size_t)frames * S * 4);
+    o_label = (int16_t*)A((size_t)frames * S * 2); o_winner = (uint32_t*)A(bevgen_winner_words((int64_t)pts, frames) * 4);
     o_single = (uint8_t*)A((size_t)frames * BEVGEN_GRID_SIZE * BEVGEN_GRID_SIZE);
     o_multi = (uint8_t*)A((size_t)frames * BEVGEN_NUM_LAYERS * BEVGEN_GRID_SIZE * BEVGEN_GRID_SIZE);
-    return x && y && z && inten && row && col && label && o_label && o_owner && o_single && o_multi;
+    return x && y && z && inten && row && col && label && o_label && o_winner && o_single && o_multi;
   }
   void release() {
-    for (void* p : {(void*)x, (void*)y, (void*)z, (void*)inten, (void*)row, (void*)col, (void*)label, (void*)o_label, (void*)o_owner, (void*)o_single, (void*)o_multi}) bevgen_host_free(p);
-    x = y = z = inten = 0; row = col = 0; label = 0; o_label = 0; o_owner = 0; o_single = o_multi = 0;
+    for (void* p : {(void*)x, (void*)y, (void*)z, (void*)inten, (void*)row, (void*)col, (void*)label, (void*)o_label, (void*)o_winner, (void*)o_single, (void*)o_multi}) bevgen_host_free(p);
+    x = y = z = inten = 0; row = col = 0; label = 0; o_label = 0; o_winner = 0; o_single = o_multi = 0;
   }
 };
 
 struct Batch {
   int first = 0, count = 0;
+  std::vector<int64_t> offs;       // point offsets of the batch's frames (winner words are addressed through them)
   std::vector<pcdio::Cloud> clouds;
   std::vector<std::string> names;
   std::vector<std::future<void>> loads;
@@ -202,16 +203,19 @@ static void encode_frame(Shared& sh, const Batch& b, int k) {
   }
   if (sh.opt.write_pcd) {
     // savePCDFileBinary(non_ground/<name>.pcd, cloud_ordered) (:755-756): S slots; slot record = winning input record
-    // with its label replaced by the post-ground label, empty slots all-zero.
+    // with its label replaced by the post-ground label, empty slots all-zero.  The library reports one winner bit per
+    // input point (the last writer of each (row, col) slot, :102-116); the slot is the point's own row*H + col.
     const pcdio::Cloud& c = b.clouds[k];
-    const uint32_t* owner = p.o_owner + (size_t)k * S; const int16_t* lab = p.o_label + (size_t)k * S;
+    const uint32_t* win = p.o_winner + (size_t)(b.offs[k] >> 5) + (size_t)k; const int16_t* lab = p.o_label + (size_t)k * S;
+    const size_t H = (size_t)sh.params.horizon_scan;
     std::string h = pcdio::header(S);
     std::vector<uint8_t> out(h.size() + S * 26, 0);
     memcpy(out.data(), h.data(), h.size());
     uint8_t* rec = out.data() + h.size();
-    for (size_t s = 0; s < S; s++) {
-      uint32_t o = owner[s];
-      if (o) { size_t i = o - 1; pcdio::pack_record(rec + s * 26, c.x[i], c.y[i], c.z[i], c.intensity[i], c.row[i], c.col[i], c.t[i], lab[s]); }
+    for (size_t i = 0, n = c.size(); i < n; i++) {
+      if (!((win[i >> 5] >> (i & 31)) & 1u)) continue;
+      const size_t s = (size_t)c.row[i] * H + c.col[i];
+      pcdio::pack_record(rec + s * 26, c.x[i], c.y[i], c.z[i], c.intensity[i], c.row[i], c.col[i], c.t[i], lab[s]);
     }
     if (!pcdio::write_file(sh.dirs.non_ground + name + ".pcd", out)) std::cerr << "Can not open file: " << sh.dirs.non_ground + name + ".pcd" << "\n";
   }
@@ -292,7 +296,8 @@ struct GpuWorker {
       }
       { std::lock_guard<std::mutex> l(sh.print_mu); for (int k = 0; k < cur->count; k++) std::cout << "Converting file: " << cur->names[k] << "\n"; }   // :744
       bevgen_points in{p->x, p->y, p->z, p->inten, p->row, p->col, p->label};
-      bevgen_outputs out{p->o_label, p->o_owner, p->o_single, p->o_multi};
+      bevgen_outputs out{p->o_label, p->o_winner, p->o_single, p->o_multi};
+      cur->offs = offs;
       if (bevgen_process_host(ctx, cur->count, offs.data(), &in, &out) != 0) {
         std::cerr << "bevgen_process_host: " << bevgen_last_error() << std::endl; sh.failed = true; give_pin(p); break;
       }

@@ -32,6 +32,20 @@ def test_synthetic_frames_bit_exact(gens, synth, O, sensor, nf):
     assert g.kernel_launches() > 0
 
 
+def test_sector_mean_sweep_fallback(pkg, synth, O, monkeypatch):
+    """Frames with more segments than the segment-form sector-mean kernel holds are swept by k_sector_mean; force that
+    with a tiny capacity and compare both routes with the oracle."""
+    batch = synth.make_batch("HDL_32E", 3, first=40)
+    ref = oracle_batch(O, "HDL_32E", batch)
+    for cap in ("0", "700", "4096"):          # all frames swept / some swept (~700 segments per frame) / none swept
+        monkeypatch.setenv("BEVGEN_SEG_CAP", cap)
+        g = pkg.BevGen("HDL_32E", device=0, max_frames_per_batch=4)
+        try:
+            assert_same(g.process_host(batch), ref, "seg_cap=" + cap)
+        finally:
+            g.close()
+
+
 def test_kitti_quirk_all_intensity_minus_one(gens, synth, O):
     batch = synth.make_batch("HDL_64E", 2, first=100, kitti_quirk=True)
     out = gens("HDL_64E", max_frames_per_batch=4).process_host(batch)
@@ -164,23 +178,26 @@ def test_submit_collect_and_device_path(gens, synth, O, pkg):
         g.submit(100 + f, fr(f))
     with pytest.raises(pkg.BevgenError, match="ring full"):
         g.submit(104, fr(4))
-    chk(2, g.collect(102))                           # out-of-order collect frees a slot
+    chk(2, g.collect(102, fr(2)))                    # out-of-order collect frees a slot
     g.submit(104, fr(4))
     for f in (4, 0, 1, 3):
-        chk(f, g.collect(100 + f))
+        chk(f, g.collect(100 + f, fr(f)))
     with pytest.raises(pkg.BevgenError):
         g.collect(999)
     # device-resident path: torch only owns the device memory
     dev = torch.device("cuda:0")
     din = {k: torch.from_numpy(np.ascontiguousarray(batch[k])).to(dev) for k in FIELDS}
     S = g.S
-    dout = dict(label=torch.empty((5, S), dtype=torch.int16, device=dev), owner=torch.empty((5, S), dtype=torch.int32, device=dev),
+    dout = dict(label=torch.empty((5, S), dtype=torch.int16, device=dev),
+                winner=torch.zeros(pkg.winner_words(int(offs[-1]), 5), dtype=torch.int32, device=dev),
                 single=torch.empty((5, 224 * 224), dtype=torch.uint8, device=dev),
                 multi=torch.empty((5, 24 * 224 * 224), dtype=torch.uint8, device=dev))
     torch.cuda.synchronize()
     g.process_device(5, offs, {k: v.data_ptr() for k, v in din.items()}, {k: v.data_ptr() for k, v in dout.items()})
     g.sync()
-    got = dict(label=dout["label"].cpu().numpy(), owner=dout["owner"].cpu().numpy().view(np.uint32),
+    own = pkg.owner_from_winner(dout["winner"].cpu().numpy().view(np.uint32), offs, np.ascontiguousarray(batch["row"], np.uint16),
+                                np.ascontiguousarray(batch["col"], np.uint16), g.params.horizon_scan, S)
+    got = dict(label=dout["label"].cpu().numpy(), owner=own,
                single=dout["single"].cpu().numpy().reshape(5, 224, 224), multi=dout["multi"].cpu().numpy().reshape(5, 24, 224, 224))
     assert_same(got, ref, "device path")
 
