@@ -37,7 +37,12 @@ static size_t wwords(size_t n_total, size_t frames) { return (n_total >> 5) + fr
 struct Scratch {            // device scratch for one wave of up to `frames` frames
   float4* rec = 0; uint16_t* gkey = 0; float* gz = 0; uint32_t* cnt = 0; float* avg = 0;
   uint4* gsum = 0; uint32_t* slow = 0;   // per (row, 32-column group) summaries; per-frame "use the sweep kernel" flag
-  uint32_t* owner = 0;                   // [frames][S] claim table, only for range images too large for k_order's shared memory
+  uint32_t* seg_start = 0; uint16_t* seg_len = 0;   // [frames][SEG_CAP] segments bucketed by sector, slot order inside a bucket
+  uint32_t* kdesc = 0; uint16_t* act = 0; uint32_t* n_act = 0;   // [frames][NSECT] bucket (base<<16|count), active sectors; [frames]
+  uint32_t* owner = 0;                   // [frames][S] claim table, only for range images too large for k_order_winners' shared memory
+  uint32_t* occ = 0;                     // [3][frames][ceil(S/32)] slot occupancy bits, contention bits, contended-id prefix
+  uint32_t* cwin = 0;                    // [frames][cw_stride] 1 + largest input index per contended slot
+  size_t frames = 0;
 };
 
 struct Lane {               // host-path double buffer: device staging of inputs/outputs + scratch
@@ -63,6 +68,7 @@ struct bevgen_ctx {
   int max_pts = 0, max_frames = 0;
   cudaStream_t s_copy = 0, s_comp = 0, s_d2h = 0;
   float* cnt_lut = 0;
+  int cw_stride = 1;         // max_points_per_frame / 2 + 1
   int seg_cap = SEG_CAP;     // BEVGEN_SEG_CAP (tests): frames with more segments take the sweep kernel
   Scratch sc_dev;            // scratch of the device path (waves on the compute stream)
   Scratch sc_aux;            // second scratch set for the waves that run on s_aux
@@ -79,7 +85,7 @@ struct bevgen_ctx {
   int64_t launches = 0;
 };
 
-static const char* kStageNames[BEVGEN_N_STAGES] = {"clear", "order", "order_fill", "ground_mark",
+static const char* kStageNames[BEVGEN_N_STAGES] = {"clear", "order_winners", "order_scatter", "ground_mark",
                                                    "sector_mean", "finalize_bin_scatter", "reserved6", "reserved7"};
 
 // ---- params ---------------------------------------------------------------------------------------------------
@@ -110,20 +116,28 @@ extern "C" void bevgen_host_free(void* p) { if (p) cudaFreeHost(p); }
 // ---- allocation helpers ---------------------------------------------------------------------------------------
 static size_t gsum_per_frame(const SensorDev& sp) { return (size_t)(sp.G + 1) * ((sp.H + 31) / 32); }
 static bool fused_order(const SensorDev& sp) { return ord_smem_bytes(sp.S) <= 200 * 1024; }
-static int alloc_scratch(Scratch& s, size_t frames, const SensorDev& sp) {
+static int alloc_scratch(Scratch& s, size_t frames, const SensorDev& sp, int max_pts) {
   const size_t S = sp.S;
+  s.frames = frames;
   if (!fused_order(sp)) CK(cudaMalloc(&s.owner, frames * S * sizeof(uint32_t)));
+  else {
+    CK(cudaMalloc(&s.occ, 3 * frames * ((S + 31) / 32) * sizeof(uint32_t)));
+    CK(cudaMalloc(&s.cwin, frames * (size_t)(max_pts / 2 + 1) * sizeof(uint32_t)));   // a contended slot holds >= 2 points
+  }
   CK(cudaMalloc(&s.gsum, frames * gsum_per_frame(sp) * sizeof(uint4)));
   CK(cudaMalloc(&s.slow, frames * sizeof(uint32_t)));
+  CK(cudaMalloc(&s.seg_start, frames * SEG_CAP * sizeof(uint32_t))); CK(cudaMalloc(&s.seg_len, frames * SEG_CAP * sizeof(uint16_t)));
+  CK(cudaMalloc(&s.kdesc, frames * NSECT * sizeof(uint32_t))); CK(cudaMalloc(&s.act, frames * NSECT * sizeof(uint16_t)));
+  CK(cudaMalloc(&s.n_act, frames * sizeof(uint32_t)));
   CK(cudaMalloc(&s.rec, frames * S * sizeof(float4)));
   CK(cudaMalloc(&s.gkey, frames * S * sizeof(uint16_t)));
-  CK(cudaMalloc(&s.gz, frames * S * sizeof(float)));
+  CK(cudaMalloc(&s.gz, (frames * S + 64) * sizeof(float)));   // + slack: k_seg_fold's last aligned window may pass the end
   CK(cudaMalloc(&s.cnt, frames * NSECT * sizeof(uint32_t)));
   CK(cudaMalloc(&s.avg, frames * NSECT * sizeof(float)));
   return 0;
 }
 static void free_scratch(Scratch& s) {
-  cudaFree(s.rec); cudaFree(s.gkey); cudaFree(s.gz); cudaFree(s.cnt); cudaFree(s.avg); cudaFree(s.gsum); cudaFree(s.slow); cudaFree(s.owner);
+  cudaFree(s.rec); cudaFree(s.gkey); cudaFree(s.gz); cudaFree(s.cnt); cudaFree(s.avg); cudaFree(s.gsum); cudaFree(s.slow); cudaFree(s.seg_start); cudaFree(s.seg_len); cudaFree(s.kdesc); cudaFree(s.act); cudaFree(s.n_act); cudaFree(s.owner); cudaFree(s.occ); cudaFree(s.cwin);
   s = Scratch();
 }
 static int alloc_io(DevIn& in, DevOut& out, size_t frames, size_t pts, size_t S) {
@@ -160,7 +174,7 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
     return fail("bevgen_create: no sm_100a kernel image usable on this device (library is built for B200 only)");
 
   bevgen_ctx* c = new bevgen_ctx();
-  c->device = device; c->p = *p; c->max_pts = max_pts; c->max_frames = max_frames;
+  c->device = device; c->p = *p; c->max_pts = max_pts; c->max_frames = max_frames; c->cw_stride = max_pts / 2 + 1;
   SensorDev& sp = c->sp;
   sp.N = p->n_scan; sp.H = p->horizon_scan; sp.G = p->ground_upper_scan; sp.S = sp.N * sp.H;
   sp.band_row0 = sp.N - sp.G - 1;
@@ -186,21 +200,23 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
   CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
   for (auto& e : c->pev) CK(cudaEventCreate(&e));
   CK(cudaFuncSetAttribute(k_finalize_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BIN));
-  CK(cudaFuncSetAttribute(k_sector_mean_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SEG));
-  CK(cudaFuncSetAttribute(k_order, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // function-wide: the largest any context may ask for
-  CK(cudaFuncSetAttribute(k_sector_mean_seg, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_seg_build, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SEG));
+  CK(cudaFuncSetAttribute(k_order_winners, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // function-wide: the largest any context may ask for
+  CK(cudaFuncSetAttribute(k_seg_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   if (const char* e = getenv("BEVGEN_SEG_CAP")) c->seg_cap = std::max(0, std::min(SEG_CAP, atoi(e)));
   // (measured: forcing the max-shared carveout on the ordering kernels makes k_order_fill 1.8x slower - it relies on L1)
   CK(cudaFuncSetAttribute(k_sector_mean, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_seg_fold<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+  CK(cudaFuncSetAttribute(k_seg_fold<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
   CK(cudaFuncSetAttribute(k_finalize_bin, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaMalloc(&c->cnt_lut, ((size_t)sp.S + 1) * sizeof(float)));
   k_build_cnt_lut<<<1, 32, 0, c->s_comp>>>(sp.S, c->cnt_lut);
   CK(cudaGetLastError());
   c->launches++;
-  if (alloc_scratch(c->sc_dev, max_frames, sp)) { delete c; return -1; }
+  if (alloc_scratch(c->sc_dev, max_frames, sp, max_pts)) { delete c; return -1; }
   if (const char* e = getenv("BEVGEN_STREAMS")) c->n_dev_streams = atoi(e) >= 2 ? 2 : 1;
   if (c->n_dev_streams == 2) {
-    if (alloc_scratch(c->sc_aux, max_frames, sp)) { delete c; return -1; }
+    if (alloc_scratch(c->sc_aux, max_frames, sp, max_pts)) { delete c; return -1; }
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     (void)lo; (void)hi;
@@ -251,9 +267,14 @@ static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
   if (!fused_order(sp)) CK(cudaMemsetAsync(w.sc->owner, 0, (size_t)w.nf * S * sizeof(uint32_t), st));
   mark(1);
   if (fused_order(sp)) {
-    k_order<<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, c->xf, w.offs_d, w.frame0, x, y, z, it, row, col, lab, w.sc->rec, w.out.wbits);
+    const size_t W = (S + 31) / 32;
+    uint32_t *occ = w.sc->occ, *cont = occ + (size_t)w.sc->frames * W, *cpre = cont + (size_t)w.sc->frames * W;
+    k_order_winners<<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, row, col, occ, cont, cpre, w.sc->cwin);
     mark(2);
-    c->launches += 1;
+    dim3 g((std::max<int>(w.max_n, (int)S) + 255) / 256, w.nf);
+    k_order_scatter<<<g, 256, 0, st>>>(sp, c->xf, w.offs_d, w.frame0, c->cw_stride, x, y, z, it, row, col, lab, occ, cont, cpre, w.sc->cwin,
+                                       w.sc->rec, w.out.wbits);
+    c->launches += 2;
   } else {   // range image too large for shared memory: claim table in global memory (two kernels + the winner bits)
     if (w.max_n > 0) {
       dim3 g((w.max_n + 511) / 512, w.nf);
@@ -280,12 +301,18 @@ static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
 }
 static int wave_sweep(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {
   // segment form first; frames it cannot hold (> seg_cap segments) raise slow[f] and are swept by k_sector_mean
-  k_sector_mean_seg<<<w.nf, SEGT, SMEM_SEG, st>>>(c->sp, c->seg_cap, w.sc->gsum, w.sc->gkey, w.sc->gz, w.sc->cnt, c->cnt_lut,
-                                                  w.sc->avg, w.sc->slow);
+  k_seg_build<<<w.nf, SEGT, SMEM_SEG, st>>>(c->sp, c->seg_cap, w.sc->gsum, w.sc->gkey, w.sc->avg, w.sc->slow, w.sc->seg_start,
+                                            w.sc->seg_len, w.sc->kdesc, w.sc->act, w.sc->n_act);
+  if ((c->sp.S & 3) == 0)   // every frame of gz starts on a 16-byte boundary: 128-bit loads
+    k_seg_fold<true><<<dim3(FOLD_PASSES, w.nf), 32, 0, st>>>(c->sp, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->slow, w.sc->seg_start, w.sc->seg_len,
+                                                             w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->avg);
+  else
+    k_seg_fold<false><<<dim3(FOLD_PASSES, w.nf), 32, 0, st>>>(c->sp, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->slow, w.sc->seg_start, w.sc->seg_len,
+                                                              w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->avg);
   k_sector_mean<<<w.nf, 32, NSECT * sizeof(float), st>>>(c->sp, w.sc->gkey, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->avg, w.sc->slow);
   if (prof) cudaEventRecord(c->pev[5], st);
   CK(cudaGetLastError());
-  c->launches += 2;
+  c->launches += 3;
   return 0;
 }
 static int wave_back(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {
@@ -298,7 +325,7 @@ static int wave_back(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pro
     for (int i = 0; i < 6; i++) {
       float ms = 0; CK(cudaEventElapsedTime(&ms, c->pev[i], c->pev[i + 1]));
       c->stage_ms[i] += ms;
-      c->stage_launches[i] += (i == 2 && fused_order(c->sp)) ? 0 : 1;
+      c->stage_launches[i] += 1;
     }
   }
   return 0;
@@ -338,6 +365,7 @@ extern "C" int bevgen_process_device(bevgen_ctx* c, int nf, const int64_t* offse
   CK(cudaSetDevice(c->device));
   int max_n_all = 0;
   if (upload_offsets(c, nf, offsets, c->s_comp, &max_n_all)) return -1;
+  if (max_n_all > c->max_pts) return fail("bevgen_process_device: a frame exceeds max_points_per_frame");
   const size_t S = c->sp.S;
   DevIn di; di.x = (float*)in->x; di.y = (float*)in->y; di.z = (float*)in->z; di.inten = (float*)in->intensity;
   di.row = (uint16_t*)in->row; di.col = (uint16_t*)in->col; di.label = (int16_t*)in->label;
@@ -377,7 +405,7 @@ static int host_chunk(const bevgen_ctx* c) { return std::min(c->max_frames, 48);
 static int ensure_lanes(bevgen_ctx* c) {
   if (c->lanes_ready) return 0;
   for (auto& l : c->lanes) {
-    if (alloc_scratch(l.sc, host_chunk(c), c->sp)) return -1;
+    if (alloc_scratch(l.sc, host_chunk(c), c->sp, c->max_pts)) return -1;
     if (alloc_io(l.in, l.out, host_chunk(c), c->max_pts, c->sp.S)) return -1;
     CK(cudaEventCreateWithFlags(&l.ev_h2d, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&l.ev_comp, cudaEventDisableTiming));
@@ -444,7 +472,7 @@ static int ensure_slots(bevgen_ctx* c) {
   c->slots.resize(ns);
   const size_t S = c->sp.S;
   for (auto& s : c->slots) {
-    if (alloc_scratch(s.sc, 1, c->sp)) return -1;
+    if (alloc_scratch(s.sc, 1, c->sp, c->max_pts)) return -1;
     if (alloc_io(s.in, s.out, 1, c->max_pts, S)) return -1;
     CK(cudaHostAlloc((void**)&s.pin_in, in_bytes(c->max_pts) + 16, cudaHostAllocPortable));
     CK(cudaHostAlloc((void**)&s.pin_out, ((size_t)c->max_pts / 32 + 4) * 4 + S * 2 + CELLS + (size_t)LAYERS * CELLS, cudaHostAllocPortable));

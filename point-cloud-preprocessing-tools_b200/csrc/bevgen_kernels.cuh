@@ -234,73 +234,90 @@ __global__ void __launch_bounds__(256) k_winner_bits(SensorDev sp, const int64_t
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K0 order (fused) — getOrderedCloud (BatchMultiBevGen.cpp:94-117) in ONE pass structure, one CTA per frame, with
-// the slot bookkeeping in shared memory instead of an S-entry table in L2:
+// K0 order, shared-memory form — getOrderedCloud (BatchMultiBevGen.cpp:94-117) as two kernels:
+//
+// k_order_winners (one CTA per frame): which input point survives in each slot, decided entirely in shared memory.
 //   occ  : 1 bit per slot, set by every valid point (atomicOr); a point that finds its bit already set marks the
 //   cont : "contended" bit of the slot (two or more input points map to it; 0.5 % of the slots on sensor data).
-// A point whose slot is not contended is the slot's only writer => it wins without any further communication and
-// scatters its record straight away.  Contended slots get a dense id (prefix popcount over `cont`), the serial
-// loop's last-writer-wins is max(input index) per id (shared-memory atomicMax), resolved in a second small pass.
-// Outputs: rec (ordered cloud, unowned slots zero = PointCloud::resize value-init, :98) and one WINNER bit per
-// input point (the host rebuilds the ordered cloud for savePCDFileBinary from it, :756).
-// Per point this costs one scattered 16-byte store to L2 and shared-memory atomics; the previous two-kernel form
-// (k_order_claim / k_order_fill, kept for range images too large for shared memory) paid an L2 atomic, an L2 probe
-// and the store.
-// grid F, block ORD_T, dynamic smem ord_smem_bytes(S).
+//   A point whose slot is not contended is the slot's only writer and wins without further communication.  Contended
+//   slots get a dense id (prefix popcount over `cont`); the serial loop's last-writer-wins is max(input index) per id
+//   (one global atomicMax per contended point into cwin[f][id]).  Reads only row/col (4 B per point, 128-bit loads);
+//   writes the occupancy / contention bits and the id prefix of the frame (3 x S/8 bytes).
+// k_order_scatter (grid over points x frames): a point wins iff its slot is uncontended or cwin says so; it emits
+//   the WINNER bit per input point, winners write their record into the ordered cloud `rec` (one scattered 16-byte
+//   store per point; all CTAs of a frame run together, so the two halves of a 32-byte sector meet in L2), unowned
+//   slots get the value-initialised record (:98).
+//
+// The previous form (k_order_claim / k_order_fill, kept for range images too large for shared memory) paid an L2
+// atomic and an L2 probe per point on top of the store.  A single fused CTA-per-frame kernel was measured and
+// rejected: with ~300 frames in flight the half-written sectors of `rec` are evicted before their second half
+// arrives (DRAM traffic 13.5 MB per frame).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int ORD_T = 512;
-constexpr int ORD_CCAP = 4096;   // contended slots resolved per round
-constexpr int ORD_LCAP = 4096;   // contended points remembered between the passes (else the frame is re-scanned)
-__host__ __device__ inline size_t ord_smem_bytes(int S) {
-  const size_t W = ((size_t)S + 31) / 32;
-  return W * 4 * 3 + ORD_CCAP * 4 + ORD_LCAP * 4 + 64;
+__host__ __device__ inline size_t ord_smem_bytes(int S) { return (((size_t)S + 31) / 32) * 4 * 2 + 256; }
+
+// 8 consecutive u16 as one 128-bit load: block v8 of the 16-byte aligned pointer.
+__device__ __forceinline__ uint4 ld8_u16(const uint16_t* aligned_base, int v8) {
+  return __ldg(reinterpret_cast<const uint4*>(aligned_base) + v8);
 }
 
-__global__ void __launch_bounds__(ORD_T) k_order(SensorDev sp, Xform xf, const int64_t* __restrict__ offs, int frame0,
-                                                  const float* __restrict__ x, const float* __restrict__ y,
-                                                  const float* __restrict__ z, const float* __restrict__ inten,
-                                                  const uint16_t* __restrict__ row, const uint16_t* __restrict__ col,
-                                                  const int16_t* __restrict__ label, float4* __restrict__ rec,
-                                                  uint32_t* __restrict__ winner_bits) {
+__global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int64_t* __restrict__ offs, int cw_stride,
+                                                          const uint16_t* __restrict__ row, const uint16_t* __restrict__ col,
+                                                          uint32_t* __restrict__ occ_bits, uint32_t* __restrict__ cont_bits,
+                                                          uint32_t* __restrict__ cont_pre, uint32_t* __restrict__ cwin) {
   extern __shared__ __align__(16) unsigned char ord_smem[];
   const int W = (sp.S + 31) >> 5;
   uint32_t* occ = reinterpret_cast<uint32_t*>(ord_smem);           // [W]
   uint32_t* cont = occ + W;                                        // [W]
-  uint32_t* cmax = cont + W;                                       // [ORD_CCAP] 1 + largest input index per contended slot
-  uint32_t* clist = cmax + ORD_CCAP;                               // [ORD_LCAP] contended input points
-  uint32_t* misc = clist + ORD_LCAP;                               // [16] counters / scan carries
-  uint32_t* cpre = misc + 16;                                      // [W] contended slots before word w
+  uint32_t* misc = cont + W;                                       // [64] scan carries
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t o = offs[f];
   const int n = (int)(offs[f + 1] - o);
-  const size_t fb = (size_t)f * sp.S;
-  const uint16_t* R = row + o; const uint16_t* C = col + o;
-  uint32_t* wb = winner_bits + (o >> 5) + (frame0 + f);            // this frame's winner words (see bevgen.h)
   const unsigned N = (unsigned)sp.N, H = (unsigned)sp.H;
+  // row and col start at the same element offset, so they share the misalignment (both arrays are 16-byte aligned)
+  const uint16_t* R = row + o; const uint16_t* C = col + o;
+  const int mis = (int)((reinterpret_cast<uintptr_t>(R) >> 1) & 7);
+  const bool vec = (((reinterpret_cast<uintptr_t>(R) ^ reinterpret_cast<uintptr_t>(C)) & 15) == 0);
+  const uint16_t* Ra = R - mis; const uint16_t* Ca = C - mis;
+  const int n8 = (n + mis + 7) >> 3;                                // 16-byte blocks that hold the frame's row/col
 
   for (int i = tid; i < W; i += ORD_T) { occ[i] = 0u; cont[i] = 0u; }
-  if (tid < 16) misc[tid] = 0u;
-  if (tid == 0)   // words between this frame's bits and the next frame's first word are defined as zero
-    for (int64_t w = (n + 31) >> 5; w < ((o + n) >> 5) + 1 - (o >> 5); w++) wb[w] = 0u;
   __syncthreads();
   // ---- scan 1: occupancy + contention bits ----
-  for (int i0 = tid; i0 < n; i0 += 4 * ORD_T) {
-    unsigned r[4], c[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) { const int i = i0 + u * ORD_T; r[u] = 0xFFFFu; c[u] = 0xFFFFu; if (i < n) { r[u] = R[i]; c[u] = C[i]; } }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int i = i0 + u * ORD_T;
-      if (i < n && r[u] < N && c[u] < H) {                         // :106-109
-        const unsigned slot = r[u] * H + c[u], bit = 1u << (slot & 31);
-        if (atomicOr(&occ[slot >> 5], bit) & bit) atomicOr(&cont[slot >> 5], bit);
-      }
+  auto visit1 = [&](unsigned r, unsigned c, int i) {
+    if (i >= 0 && i < n && r < N && c < H) {                        // :106-109
+      const unsigned slot = r * H + c, bit = 1u << (slot & 31);
+      if (atomicOr(&occ[slot >> 5], bit) & bit) atomicOr(&cont[slot >> 5], bit);
     }
-  }
+  };
+  auto visit2 = [&](unsigned r, unsigned c, int i) {
+    if (i >= 0 && i < n && r < N && c < H) {
+      const unsigned slot = r * H + c, bit = 1u << (slot & 31), cw = cont[slot >> 5];
+      if (cw & bit) atomicMax(&cwin[(size_t)f * cw_stride + occ[slot >> 5] + __popc(cw & (bit - 1u))], (uint32_t)i + 1u);
+    }
+  };
+  auto scan = [&](auto visit) {
+    if (vec) {
+      for (int v = tid; v < n8; v += ORD_T) {
+        const int i = v * 8 - mis;
+        if (i < 0 || i + 8 > n) {                                   // head / tail block: stay inside the frame's elements
+          for (int k = max(i, 0); k < min(i + 8, n); k++) visit(R[k], C[k], k);
+          continue;
+        }
+        const uint4 rr = ld8_u16(Ra, v), cc = ld8_u16(Ca, v);
+        visit(rr.x & 0xFFFFu, cc.x & 0xFFFFu, i);     visit(rr.x >> 16, cc.x >> 16, i + 1);
+        visit(rr.y & 0xFFFFu, cc.y & 0xFFFFu, i + 2); visit(rr.y >> 16, cc.y >> 16, i + 3);
+        visit(rr.z & 0xFFFFu, cc.z & 0xFFFFu, i + 4); visit(rr.z >> 16, cc.z >> 16, i + 5);
+        visit(rr.w & 0xFFFFu, cc.w & 0xFFFFu, i + 6); visit(rr.w >> 16, cc.w >> 16, i + 7);
+      }
+    } else {
+      for (int i = tid; i < n; i += ORD_T) visit(R[i], C[i], i);
+    }
+  };
+  scan(visit1);
   __syncthreads();
-  // ---- unowned slots keep the value-initialised record (:98); dense ids of the contended slots ----
-  for (int sl = tid; sl < sp.S; sl += ORD_T)
-    if (!((occ[sl >> 5] >> (sl & 31)) & 1u)) rec[fb + sl] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // ---- occupancy / contention bits out; dense ids of the contended slots (prefix popcount, kept in `occ`) ----
+  for (int w = tid; w < W; w += ORD_T) { occ_bits[(size_t)f * W + w] = occ[w]; cont_bits[(size_t)f * W + w] = cont[w]; }
   {
     const int wpt = (W + ORD_T - 1) / ORD_T;                        // consecutive words per thread
     const int w0 = min(tid * wpt, W), w1 = min(w0 + wpt, W);
@@ -309,84 +326,63 @@ __global__ void __launch_bounds__(ORD_T) k_order(SensorDev sp, Xform xf, const i
     unsigned incl = loc;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-    uint32_t* wsum = occ;                                           // occ is dead from here on; reuse its first words
-    __syncthreads();
-    if (lane == 31) wsum[wid] = incl;
-    __syncthreads();
+    if (lane == 31) misc[wid] = incl;
+    __syncthreads();                                                // also: every thread is done reading occ
     unsigned wbase = 0, total = 0;
-    for (int w = 0; w < ORD_T / 32; w++) { const unsigned t = wsum[w]; if (w < wid) wbase += t; total += t; }
+    for (int w = 0; w < ORD_T / 32; w++) { const unsigned t = misc[w]; if (w < wid) wbase += t; total += t; }
     unsigned run = wbase + incl - loc;
-    for (int w = w0; w < w1; w++) { cpre[w] = run; run += __popc(cont[w]); }
-    if (tid == 0) misc[1] = total;
+    for (int w = w0; w < w1; w++) { occ[w] = run; cont_pre[(size_t)f * W + w] = run; run += __popc(cont[w]); }
+    // the serial loop's last writer (:102-116) = largest input index: one global atomicMax per contended point
+    for (unsigned j = tid; j < total; j += ORD_T) cwin[(size_t)f * cw_stride + j] = 0u;
+    if (total == 0) return;                                         // uniform
   }
   __syncthreads();
-  const unsigned ncont = misc[1];
-  // ---- scan 2: winners of uncontended slots scatter their record; contended points are listed ----
-  for (int i0 = tid; i0 < ((n + 31) & ~31); i0 += 2 * ORD_T) {
-    unsigned r[2], c[2]; float px[2], py[2], pz[2], pi[2]; int16_t lb[2];
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int i = i0 + u * ORD_T;
-      r[u] = 0xFFFFu; c[u] = 0xFFFFu; px[u] = py[u] = pz[u] = pi[u] = 0.f; lb[u] = 0;
-      if (i < n) { r[u] = R[i]; c[u] = C[i]; px[u] = x[o + i]; py[u] = y[o + i]; pz[u] = z[o + i]; pi[u] = inten[o + i]; lb[u] = label[o + i]; }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int i = i0 + u * ORD_T;
-      if (i - lane >= n) continue;                                  // whole warp past the end (uniform)
-      const bool valid = i < n && r[u] < N && c[u] < H;
-      const unsigned slot = valid ? r[u] * H + c[u] : 0u, bit = 1u << (slot & 31);
-      const bool contended = valid && (cont[slot >> 5] & bit);
-      const bool win = valid && !contended;
-      if (win) {
-        float ox = px[u], oy = py[u], oz = pz[u];
-        if (xf.on) {   // pcl::transformPointCloud, PCL >= 1.9 SSE order (CloudManip.cpp:128)
-          ox = __fadd_rn(__fmul_rn(px[u], xf.m[0]), __fadd_rn(__fmul_rn(py[u], xf.m[1]), __fadd_rn(__fmul_rn(pz[u], xf.m[2]), xf.m[3])));
-          oy = __fadd_rn(__fmul_rn(px[u], xf.m[4]), __fadd_rn(__fmul_rn(py[u], xf.m[5]), __fadd_rn(__fmul_rn(pz[u], xf.m[6]), xf.m[7])));
-          oz = __fadd_rn(__fmul_rn(px[u], xf.m[8]), __fadd_rn(__fmul_rn(py[u], xf.m[9]), __fadd_rn(__fmul_rn(pz[u], xf.m[10]), xf.m[11])));
-        }
-        const unsigned w = (unsigned)(uint16_t)lb[u] | W_OWNED | (pi[u] == -1.0f ? W_NEG1 : 0u);
-        rec[fb + slot] = make_float4(ox, oy, oz, __uint_as_float(w));
-      }
-      if (contended) { const unsigned j = atomicAdd(&misc[0], 1u); if (j < ORD_LCAP) clist[j] = (uint32_t)i; }
-      const unsigned wm = __ballot_sync(0xffffffffu, win);
-      if (lane == 0) wb[i >> 5] = wm;
-    }
+  scan(visit2);
+}
+
+// grid (ceil(max(max_n, S)/256), F), block 256.
+__global__ void __launch_bounds__(256) k_order_scatter(SensorDev sp, Xform xf, const int64_t* __restrict__ offs, int frame0, int cw_stride,
+                                                        const float* __restrict__ x, const float* __restrict__ y,
+                                                        const float* __restrict__ z, const float* __restrict__ inten,
+                                                        const uint16_t* __restrict__ row, const uint16_t* __restrict__ col,
+                                                        const int16_t* __restrict__ label, const uint32_t* __restrict__ occ_bits,
+                                                        const uint32_t* __restrict__ cont_bits, const uint32_t* __restrict__ cont_pre,
+                                                        const uint32_t* __restrict__ cwin, float4* __restrict__ rec,
+                                                        uint32_t* __restrict__ winner_bits) {
+  const int f = blockIdx.y;
+  const int64_t o = offs[f];
+  const int n = (int)(offs[f + 1] - o);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const size_t fb = (size_t)f * sp.S;
+  const int W = (sp.S + 31) >> 5;
+  const size_t fw = (size_t)f * W;
+  if (i < sp.S && !((occ_bits[fw + (i >> 5)] >> (i & 31)) & 1u)) rec[fb + i] = make_float4(0.f, 0.f, 0.f, 0.f);   // :98
+  uint32_t* wb = winner_bits + (o >> 5) + (frame0 + f);            // this frame's winner words (see bevgen.h)
+  if (i == 0)     // words between this frame's bits and the next frame's first word are defined as zero
+    for (int64_t w = (n + 31) >> 5; w < ((o + n) >> 5) + 1 - (o >> 5); w++) wb[w] = 0u;
+  if (i - lane >= n) return;                                        // whole warp past the end
+  // every load of the point is issued before the winner test: 99.5 % of the points win
+  unsigned r = 0xFFFFu, c = 0xFFFFu; float px = 0.f, py = 0.f, pz = 0.f, pi = 0.f; int16_t lb = 0;
+  if (i < n) { r = row[o + i]; c = col[o + i]; px = x[o + i]; py = y[o + i]; pz = z[o + i]; pi = inten[o + i]; lb = label[o + i]; }
+  const bool valid = r < (unsigned)sp.N && c < (unsigned)sp.H;      // :106-109
+  const unsigned slot = valid ? r * sp.H + c : 0u, bit = 1u << (slot & 31);
+  bool win = valid;
+  if (valid) {
+    const uint32_t cw = cont_bits[fw + (slot >> 5)];
+    if (cw & bit) win = cwin[(size_t)f * cw_stride + cont_pre[fw + (slot >> 5)] + __popc(cw & (bit - 1u))] == (uint32_t)i + 1u;
   }
-  __syncthreads();
-  // ---- contended slots: last writer = largest input index (:102-116 is a serial loop), ORD_CCAP ids per round ----
-  const unsigned nlist = misc[0];
-  const bool listed = nlist <= ORD_LCAP;
-  const unsigned npts = listed ? nlist : (unsigned)n;
-  for (unsigned base = 0; base < ncont; base += ORD_CCAP) {
-    for (int j = tid; j < ORD_CCAP; j += ORD_T) cmax[j] = 0u;
-    __syncthreads();
-    for (int pass = 0; pass < 2; pass++) {
-      for (unsigned j = tid; j < npts; j += ORD_T) {
-        const unsigned i = listed ? clist[j] : j;
-        const unsigned rr = R[i], cc = C[i];
-        if (!(rr < N && cc < H)) continue;
-        const unsigned slot = rr * H + cc, bit = 1u << (slot & 31), cw = cont[slot >> 5];
-        if (!(cw & bit)) continue;
-        const unsigned id = cpre[slot >> 5] + __popc(cw & (bit - 1u)) - base;              // wraps to >= ORD_CCAP below the window
-        if (id >= ORD_CCAP) continue;
-        if (pass == 0) atomicMax(&cmax[id], i + 1u);
-        else if (cmax[id] == i + 1u) {
-          float px = x[o + i], py = y[o + i], pz = z[o + i];
-          if (xf.on) {
-            const float ox = __fadd_rn(__fmul_rn(px, xf.m[0]), __fadd_rn(__fmul_rn(py, xf.m[1]), __fadd_rn(__fmul_rn(pz, xf.m[2]), xf.m[3])));
-            const float oy = __fadd_rn(__fmul_rn(px, xf.m[4]), __fadd_rn(__fmul_rn(py, xf.m[5]), __fadd_rn(__fmul_rn(pz, xf.m[6]), xf.m[7])));
-            const float oz = __fadd_rn(__fmul_rn(px, xf.m[8]), __fadd_rn(__fmul_rn(py, xf.m[9]), __fadd_rn(__fmul_rn(pz, xf.m[10]), xf.m[11])));
-            px = ox; py = oy; pz = oz;
-          }
-          const unsigned w = (unsigned)(uint16_t)label[o + i] | W_OWNED | (inten[o + i] == -1.0f ? W_NEG1 : 0u);
-          rec[fb + slot] = make_float4(px, py, pz, __uint_as_float(w));
-          atomicOr(&wb[i >> 5], 1u << (i & 31));
-        }
-      }
-      __syncthreads();
-    }
+  const unsigned wm = __ballot_sync(0xffffffffu, win);
+  if (lane == 0) wb[i >> 5] = wm;
+  if (!win) return;
+  if (xf.on) {   // pcl::transformPointCloud, PCL >= 1.9 SSE order (CloudManip.cpp:128)
+    const float ox = __fadd_rn(__fmul_rn(px, xf.m[0]), __fadd_rn(__fmul_rn(py, xf.m[1]), __fadd_rn(__fmul_rn(pz, xf.m[2]), xf.m[3])));
+    const float oy = __fadd_rn(__fmul_rn(px, xf.m[4]), __fadd_rn(__fmul_rn(py, xf.m[5]), __fadd_rn(__fmul_rn(pz, xf.m[6]), xf.m[7])));
+    const float oz = __fadd_rn(__fmul_rn(px, xf.m[8]), __fadd_rn(__fmul_rn(py, xf.m[9]), __fadd_rn(__fmul_rn(pz, xf.m[10]), xf.m[11])));
+    px = ox; py = oy; pz = oz;
   }
+  const unsigned w = (unsigned)(uint16_t)lb | W_OWNED | (pi == -1.0f ? W_NEG1 : 0u);
+  rec[fb + slot] = make_float4(px, py, pz, __uint_as_float(w));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -572,34 +568,38 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
 // order; chains of different sectors are independent.  k_ground_mark leaves one summary per (row, 32-column group);
 // from those this kernel cuts the band into segments = maximal stretches whose participating slots (ground, z != 0)
 // all lie in one sector.  gz is 0 on every other slot, and adding +-0 never changes a sum that starts at +0, so a
-// segment is folded by simply adding gz[start..end].  Segments are bucketed per sector in slot order (ordered list
-// + one warp assigning ranks with match_any), then one thread per sector folds its segments sequentially.
+// segment is folded by simply adding gz[start..end].  k_seg_build (one CTA per frame) buckets the segments per
+// sector in slot order (ordered list + one warp assigning ranks with match_any) and leaves the lists in global
+// memory; k_seg_fold then runs one LANE per sector over its segments.
 // HDL_64E synthetic frames: ~2.7 k segments, ~350 active sectors, longest chain ~3 k additions.
-// Frames with more than `cap` segments raise slow_flag[f] and are handled by k_sector_mean (the sweep form).
-// grid F, block SEGT.
+// Frames with more than `cap` segments (or a segment longer than 65535 slots) raise slow_flag[f] and are handled by
+// k_sector_mean (the sweep form).
+// k_seg_build: grid F, block SEGT, dynamic smem SMEM_SEG.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int SEG_CAP = 4096;
 constexpr int SEGT = 512;
-constexpr int SMEM_SEG = SEG_CAP * 8 + NSECT * 8 + SEGT * 8 + 256 + SEG_CAP * 4 + (NSECT + 2) * 2 + 16 + (SEGT / 32) * 256 * 4;   // 106,944 B
+constexpr int SMEM_SEG = SEG_CAP * 4 * 2 + NSECT * 4 + SEGT * 8 + 320 + SEG_CAP * 2 * 3 + (NSECT + 2) * 2;   // 84,264 B
+constexpr int FOLD_STEP = 32;           // heights per step of a chain in k_seg_fold
+constexpr int FOLD_PASSES = 12;         // warps per frame in k_seg_fold (32 sectors each; more sectors wrap around)
 
-__global__ void __launch_bounds__(SEGT) k_sector_mean_seg(SensorDev sp, int cap, const uint4* __restrict__ gsum,
-                                                           const uint16_t* __restrict__ gkey, const float* __restrict__ gz,
-                                                           const uint32_t* __restrict__ cnt, const float* __restrict__ cnt_lut,
-                                                           float* __restrict__ avg, uint32_t* __restrict__ slow_flag) {
+__global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const uint4* __restrict__ gsum,
+                                                     const uint16_t* __restrict__ gkey, float* __restrict__ avg,
+                                                     uint32_t* __restrict__ slow_flag, uint32_t* __restrict__ seg_start,
+                                                     uint16_t* __restrict__ seg_len, uint32_t* __restrict__ kdesc,
+                                                     uint16_t* __restrict__ act, uint32_t* __restrict__ n_act_out) {
   extern __shared__ __align__(16) unsigned char seg_smem[];
   uint32_t* s_start = reinterpret_cast<uint32_t*>(seg_smem);   // [SEG_CAP] first slot of the segment
-  uint32_t* s_end = s_start + SEG_CAP;                          // [SEG_CAP] last participating slot
-  uint32_t* s_kcnt = s_end + SEG_CAP;                           // [NSECT] segments per sector
-  uint32_t* s_kbase = s_kcnt + NSECT;                           // [NSECT] bucket base, later bucket end
-  uint32_t* s_lk = s_kbase + NSECT;                             // [SEGT] sector of the last participating slot of the thread's groups
+  uint32_t* s_endtmp = s_start + SEG_CAP;                       // [SEG_CAP] last participating slot of the segment
+  uint32_t* s_kcnt = s_endtmp + SEG_CAP;                        // [NSECT] segments per sector
+  uint32_t* s_lk = s_kcnt + NSECT;                              // [SEGT] sector of the last participating slot of the thread's groups
   int* s_lp = reinterpret_cast<int*>(s_lk + SEGT);              // [SEGT] its slot (relative to the frame), -1 if none
   uint32_t* s_scan = reinterpret_cast<uint32_t*>(s_lp + SEGT);  // [32]
   uint32_t* s_warp = s_scan + 32;                               // [32]
-  uint16_t* s_key = reinterpret_cast<uint16_t*>(s_warp + 32);   // [SEG_CAP] sector of the segment
+  uint32_t* s_misc = s_warp + 32;                               // [16]
+  uint16_t* s_len = reinterpret_cast<uint16_t*>(s_misc + 16);   // [SEG_CAP] last participating slot - first slot
+  uint16_t* s_key = s_len + SEG_CAP;                            // [SEG_CAP] sector of the segment
   uint16_t* s_order = s_key + SEG_CAP;                          // [SEG_CAP] segment ids bucketed by sector, slot order kept
-  uint16_t* s_act = s_order + SEG_CAP;                          // [NSECT + 2] sectors that own at least one segment
-  uint32_t* s_nact = reinterpret_cast<uint32_t*>(s_act + NSECT + 2);
-  float* s_zb = reinterpret_cast<float*>(s_nact + 4);           // [SEGT/32][8][32] per-warp staging of 8 chunks of heights
+  uint16_t* s_kbase = s_order + SEG_CAP;                        // [NSECT + 2] bucket base, later bucket end
 
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int H = sp.H, NG = (H + 31) >> 5;
@@ -608,12 +608,25 @@ __global__ void __launch_bounds__(SEGT) k_sector_mean_seg(SensorDev sp, int cap,
   const uint4* GS = gsum + (size_t)f * n_groups;
   const size_t fb = (size_t)f * sp.S;
   const uint16_t* K = gkey + fb;
-  const float* Z = gz + fb;
   const int g0 = min(tid * gpt, n_groups), g1 = min(g0 + gpt, n_groups);
   auto slot_of = [&](int g, int l) { const int rb = g / NG, cg = g - rb * NG; return (sp.band_row0 + rb) * H + cg * 32 + l; };
+  // exclusive block scan of one value per thread; returns the exclusive prefix, *total = sum over the block
+  auto block_scan = [&](unsigned v, unsigned* total) {
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    __syncthreads();
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    unsigned wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SEGT / 32; w++) { const unsigned c = s_warp[w]; if (w < wid) wbase += c; tot += c; }
+    *total = tot;
+    return wbase + incl - v;
+  };
 
   for (int i = tid; i < NSECT; i += SEGT) s_kcnt[i] = 0;
-  if (tid == 0) *s_nact = 0;
+  if (tid == 0) s_misc[0] = 0;
   // ---- pass 1: last participating slot / sector of this thread's groups ----
   {
     unsigned lk = NO_KEY; int lp = -1;
@@ -638,21 +651,13 @@ __global__ void __launch_bounds__(SEGT) k_sector_mean_seg(SensorDev sp, int cap,
       k = v.z >> 16;
     }
   }
-  // block exclusive scan of nh
-  unsigned incl = nh;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-  if (lane == 31) s_warp[wid] = incl;
-  __syncthreads();
-  unsigned wbase = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < SEGT / 32; w++) { const unsigned c = s_warp[w]; if (w < wid) wbase += c; total += c; }
+  unsigned total = 0;
+  const unsigned ebase = block_scan(nh, &total);
   const int nseg = (int)total;
   if (nseg > cap) { if (tid == 0) slow_flag[f] = 1u; return; }    // uniform: the sweep kernel takes this frame
-  if (tid == 0) slow_flag[f] = 0u;
-  // ---- pass 3: emit segments in slot order ----
+  // ---- pass 3: emit segments in slot order (lengths follow once every start is known) ----
   {
-    unsigned e = wbase + incl - nh;
+    unsigned e = ebase;
     unsigned k = ck; int lastp = cp;
     for (int g = g0; g < g1; g++) {
       const uint4 v = GS[g];
@@ -667,103 +672,147 @@ __global__ void __launch_bounds__(SEGT) k_sector_mean_seg(SensorDev sp, int cap,
         const int prev_end = below ? base + 31 - __clz(below) : lastp;
         s_start[e] = (uint32_t)(base + l);
         s_key[e] = K[base + l];
-        if (e > 0) s_end[e - 1] = (uint32_t)prev_end;
+        if (e > 0) s_endtmp[e - 1] = (uint32_t)prev_end;
         e++;
       }
       k = v.z >> 16; lastp = base + 31 - __clz(pm);
     }
   }
-  __syncthreads();
   if (tid == 0 && nseg > 0) {
     int lp = -1;
     for (int t = SEGT - 1; t >= 0; t--) if (s_lp[t] >= 0) { lp = s_lp[t]; break; }
-    s_end[nseg - 1] = (uint32_t)lp;
+    s_endtmp[nseg - 1] = (uint32_t)lp;
   }
-  // ---- segments per sector, exclusive scan over sectors ----
-  for (int e = tid; e < nseg; e += SEGT) atomicAdd(&s_kcnt[s_key[e]], 1u);
   __syncthreads();
+  for (int e = tid; e < nseg; e += SEGT) {
+    const unsigned d = s_endtmp[e] - s_start[e];
+    if (d > 0xFFFFu) s_misc[0] = 1u;                              // a segment longer than 65535 slots: sweep kernel
+    s_len[e] = (uint16_t)d;
+    atomicAdd(&s_kcnt[s_key[e]], 1u);
+  }
+  __syncthreads();
+  if (s_misc[0]) { if (tid == 0) slow_flag[f] = 1u; return; }     // uniform
+  if (tid == 0) slow_flag[f] = 0u;
+  // ---- exclusive scan of the segment counts over sectors; active sectors compacted in ascending order ----
+  constexpr int KPT = (NSECT + SEGT - 1) / SEGT;                  // 8 sectors per thread
+  unsigned n_act = 0;
   {
-    constexpr int KPT = (NSECT + SEGT - 1) / SEGT;              // 8 sectors per thread
-    unsigned loc = 0;
+    unsigned loc = 0, actn = 0;
 #pragma unroll
-    for (int j = 0; j < KPT; j++) { const int k = tid * KPT + j; if (k < NSECT) loc += s_kcnt[k]; }
-    unsigned inc2 = loc;
+    for (int j = 0; j < KPT; j++) { const int k = tid * KPT + j; if (k < NSECT) { const unsigned c = s_kcnt[k]; loc += c; actn += c ? 1u : 0u; } }
+    unsigned dummy;
+    unsigned run = block_scan(loc, &dummy);
+    unsigned arun = block_scan(actn, &n_act);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += y; }
-    if (lane == 31) s_scan[wid] = inc2;
-    __syncthreads();
-    unsigned wb = 0;
-#pragma unroll
-    for (int w = 0; w < SEGT / 32; w++) if (w < wid) wb += s_scan[w];
-    unsigned run = wb + inc2 - loc;
-#pragma unroll
-    for (int j = 0; j < KPT; j++) { const int k = tid * KPT + j; if (k < NSECT) { s_kbase[k] = run; run += s_kcnt[k]; } }
+    for (int j = 0; j < KPT; j++) {
+      const int k = tid * KPT + j;
+      if (k < NSECT) {
+        const unsigned c = s_kcnt[k];
+        s_kbase[k] = (uint16_t)run;
+        if (c) { act[(size_t)f * NSECT + arun] = (uint16_t)k; kdesc[(size_t)f * NSECT + k] = (run << 16) | c; arun++; }
+        else avg[(size_t)f * NSECT + k] = 0.0f;                     // 0 / num, num > 0
+        run += c;
+      }
+    }
+    if (tid == 0) n_act_out[f] = n_act;
   }
   __syncthreads();
-  // ---- one warp walks the ordered segment list and hands out positions: s_kbase[k] ends as the END of bucket k ----
+  // ---- one warp walks the ordered segment list and hands out positions inside the sector buckets ----
   if (wid == 0) {
     for (int b = 0; b < nseg; b += 32) {
       const int e = b + lane;
       const bool valid = e < nseg;
       const unsigned k = valid ? (unsigned)s_key[e] : NO_KEY;
       const unsigned peers = __match_any_sync(0xffffffffu, k);
-      const unsigned pos = valid ? s_kbase[k] + __popc(peers & ((1u << lane) - 1u)) : 0u;
+      const unsigned pos = valid ? (unsigned)s_kbase[k] + __popc(peers & ((1u << lane) - 1u)) : 0u;
       __syncwarp();
-      if (valid && (peers >> lane) == 1u) s_kbase[k] = pos + 1u;  // the group's highest lane publishes the new fill level
-      if (valid) s_order[pos] = (uint16_t)e;
+      if (valid && (peers >> lane) == 1u) s_kbase[k] = (uint16_t)(pos + 1u);  // the group's highest lane publishes the new fill level
+      if (valid) s_order[e] = (uint16_t)pos;
       __syncwarp();
     }
   }
   __syncthreads();
-  // ---- one WARP per active sector folds its segments in slot order (:198), then the IEEE divide (:210) ----
-  // The warp loads 32 consecutive heights with one coalesced access (the next chunk is in flight while the current one
-  // is folded), stages them in shared memory and every lane runs the same serial chain over broadcast 128-bit reads;
-  // chunks are padded with +0, which never changes the sum.
-  for (int k = tid; k < NSECT; k += SEGT) {
-    if (s_kcnt[k]) s_act[atomicAdd(s_nact, 1u)] = (uint16_t)k;
-    else avg[(size_t)f * NSECT + k] = 0.0f;                     // 0 / num, num > 0
+  // ---- the bucketed list goes to global memory: entry `pos` of the frame = (first slot, length - 1) ----
+  uint32_t* s_span = s_endtmp;                                    // [NSECT] slots a sector's chain walks over (its cost)
+  for (int k = tid; k < NSECT; k += SEGT) s_span[k] = 0u;
+  __syncthreads();
+  for (int e = tid; e < nseg; e += SEGT) {
+    const unsigned pos = s_order[e];
+    seg_start[(size_t)f * SEG_CAP + pos] = s_start[e];
+    seg_len[(size_t)f * SEG_CAP + pos] = s_len[e];
+    atomicAdd(&s_span[s_key[e]], (unsigned)s_len[e] + 1u);
   }
   __syncthreads();
-  const unsigned n_act = *s_nact;
-  constexpr int CH = 8;                                           // chunks (of 32 heights) loaded per round: 8 loads in flight per warp
-  float* zb = s_zb + wid * (CH * 32);
-  for (unsigned a = wid; a < n_act; a += SEGT / 32) {
-    const unsigned k = s_act[a];
-    const unsigned n = s_kcnt[k];
-    const unsigned b0 = s_kbase[k] - n;
+  // ---- active sectors sorted by chain cost, longest first: k_seg_fold gives 32 consecutive entries to one warp, and a
+  // warp runs as long as its longest chain ----
+  if (n_act > 1 && n_act <= 1024) {
+    uint32_t* c_span = s_kcnt;                                    // s_kcnt is dead (kdesc holds the counts)
+    uint16_t* c_key = reinterpret_cast<uint16_t*>(s_kcnt + 1024);
+    for (unsigned a = tid; a < n_act; a += SEGT) { const unsigned k = act[(size_t)f * NSECT + a]; c_key[a] = (uint16_t)k; c_span[a] = s_span[k]; }
+    __syncthreads();
+    for (unsigned a = tid; a < n_act; a += SEGT) {
+      const unsigned mine = c_span[a];
+      unsigned r = 0;
+      for (unsigned b = 0; b < n_act; b++) { const unsigned o = c_span[b]; r += (o > mine || (o == mine && b < a)) ? 1u : 0u; }
+      act[(size_t)f * NSECT + r] = c_key[a];
+    }
+  }
+}
+
+// k_seg_fold — one LANE per active sector runs the sector's serial chain sum = fl(sum + z) (:198) over its segments in
+// slot order, straight from gz (each lane streams its own short contiguous pieces; the kernel uses no shared memory,
+// so the lines it touches live in L1).  The lane walks a flat sequence of steps of up to FOLD_STEP heights (padded
+// with +0, which never changes the sum), so the 32 chains of a warp stay in lockstep whatever their segment boundaries
+// are.  Then the IEEE divide (:210).
+// grid (FOLD_PASSES, F), block 32: warp p of a frame owns the active sectors p*32 + lane (+ 32*FOLD_PASSES ...).
+template <bool VEC>
+__global__ void __launch_bounds__(32) k_seg_fold(SensorDev sp, const float* __restrict__ gz, const uint32_t* __restrict__ cnt,
+                                                  const float* __restrict__ cnt_lut, const uint32_t* __restrict__ slow_flag,
+                                                  const uint32_t* __restrict__ seg_start, const uint16_t* __restrict__ seg_len,
+                                                  const uint32_t* __restrict__ kdesc, const uint16_t* __restrict__ act,
+                                                  const uint32_t* __restrict__ n_act_in, float* __restrict__ avg) {
+  const int f = blockIdx.y;
+  if (slow_flag[f]) return;                                       // the sweep kernel takes this frame
+  const unsigned n_act = n_act_in[f];
+  const float* Z = gz + (size_t)f * sp.S;
+  const uint32_t* SS = seg_start + (size_t)f * SEG_CAP;
+  const uint16_t* SL = seg_len + (size_t)f * SEG_CAP;
+  for (unsigned a = blockIdx.x * 32 + threadIdx.x; a < n_act; a += 32 * FOLD_PASSES) {
+    const unsigned k = act[(size_t)f * NSECT + a];
+    const unsigned d = kdesc[(size_t)f * NSECT + k];
+    unsigned cur = d >> 16; const unsigned endseg = cur + (d & 0xFFFFu);
     float acc = 0.0f;
-    unsigned s = 0;                                               // cursor: segment s of this sector, `off` heights consumed
-    unsigned e = s_order[b0];
-    unsigned st = s_start[e]; int rem = (int)(s_end[e] - st) + 1;
-    while (s < n) {
-      unsigned cst[CH]; int ccur[CH];
+    unsigned j = SS[cur], hi = j + SL[cur];
+    unsigned st2 = 0u, en2 = 0u;                                    // the following segment, fetched one segment ahead
+    if (cur + 1 < endseg) { st2 = SS[cur + 1]; en2 = st2 + SL[cur + 1]; }
+    // One step = a 16-byte aligned window of FOLD_STEP heights around the current position, fetched with 128-bit loads
+    // (every lane reads its own lines: the kernel is bound by L1 wavefronts, one per lane and load, so loads are wide)
+    // and all issued before the first add.  Heights outside [j, hi] are replaced by +0.
+    while (true) {
+      float v[FOLD_STEP];
+      const unsigned jb = VEC ? (j & ~3u) : j;
+      if (VEC) {
 #pragma unroll
-      for (int c = 0; c < CH; c++) {
-        cst[c] = st; ccur[c] = s < n ? min(rem, 32) : 0;
-        st += 32; rem -= 32;
-        if (rem <= 0 && s < n) {
-          s++;
-          if (s < n) { e = s_order[b0 + s]; st = s_start[e]; rem = (int)(s_end[e] - st) + 1; }
+        for (int u = 0; u < FOLD_STEP / 4; u++) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(Z + jb) + u);   // gz is padded: the window may pass the frame's end
+          v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
         }
+#pragma unroll
+        for (int u = 0; u < FOLD_STEP; u++) { const unsigned q = jb + u; v[u] = (q >= j && q <= hi) ? v[u] : 0.0f; }
+      } else {
+#pragma unroll
+        for (int u = 0; u < FOLD_STEP; u++) { const unsigned q = j + u; v[u] = q <= hi ? Z[q] : 0.0f; }
       }
-      float v[CH];
 #pragma unroll
-      for (int c = 0; c < CH; c++) v[c] = lane < ccur[c] ? Z[cst[c] + lane] : 0.0f;
-#pragma unroll
-      for (int c = 0; c < CH; c++) zb[c * 32 + lane] = v[c];
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < CH; c++) {
-        const float4* z4 = reinterpret_cast<const float4*>(zb + c * 32);
-        const int nq = (ccur[c] + 3) >> 2;
-        for (int q = 0; q < nq; q++) {
-          const float4 t = z4[q];
-          acc = __fadd_rn(acc, t.x); acc = __fadd_rn(acc, t.y); acc = __fadd_rn(acc, t.z); acc = __fadd_rn(acc, t.w);
-        }
-      }
-      __syncwarp();
+      for (int u = 0; u < FOLD_STEP; u++) acc = __fadd_rn(acc, v[u]);
+      j = jb + FOLD_STEP;
+      if (j <= hi) continue;
+      cur++;
+      if (cur >= endseg) break;
+      j = st2; hi = en2;
+      if (cur + 1 < endseg) { st2 = SS[cur + 1]; en2 = st2 + SL[cur + 1]; }
     }
-    if (lane == 0) avg[(size_t)f * NSECT + k] = __fdiv_rn(acc, cnt_lut[cnt[(size_t)f * NSECT + k]]);
+    avg[(size_t)f * NSECT + k] = __fdiv_rn(acc, cnt_lut[cnt[(size_t)f * NSECT + k]]);   // :210
   }
 }
 
