@@ -71,9 +71,10 @@ struct bevgen_ctx {
   int cw_stride = 1;         // max_points_per_frame / 2 + 1
   int seg_cap = SEG_CAP;     // BEVGEN_SEG_CAP (tests): frames with more segments take the sweep kernel
   Scratch sc_dev;            // scratch of the device path (waves on the compute stream)
-  Scratch sc_aux;            // second scratch set for the waves that run on s_aux
-  cudaStream_t s_aux = 0;    // second compute stream for odd waves
-  cudaEvent_t ev_front[2] = {0, 0}, ev_sweep[2] = {0, 0}; int n_dev_streams = 2;
+  static constexpr int MAX_AUX = 7;
+  Scratch sc_aux[MAX_AUX];       // scratch sets of the auxiliary compute streams
+  cudaStream_t s_aux[MAX_AUX]{}; // waves rotate over s_comp, s_aux[0], s_aux[1], ...
+  cudaEvent_t ev_fork = 0, ev_join[MAX_AUX]{}; int n_dev_streams = 2;
   int64_t* offs_d = 0; size_t offs_cap = 0;
   bool lanes_ready = false; Lane lanes[3];
   std::vector<Slot> slots;
@@ -214,17 +215,12 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
   CK(cudaGetLastError());
   c->launches++;
   if (alloc_scratch(c->sc_dev, max_frames, sp, max_pts)) { delete c; return -1; }
-  if (const char* e = getenv("BEVGEN_STREAMS")) c->n_dev_streams = atoi(e) >= 2 ? 2 : 1;
-  if (c->n_dev_streams == 2) {
-    if (alloc_scratch(c->sc_aux, max_frames, sp, max_pts)) { delete c; return -1; }
-    int lo = 0, hi = 0;
-    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    (void)lo; (void)hi;
-    CK(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-      CK(cudaEventCreateWithFlags(&c->ev_front[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&c->ev_sweep[i], cudaEventDisableTiming));
-    }
+  if (const char* e = getenv("BEVGEN_STREAMS")) c->n_dev_streams = std::max(1, std::min(bevgen_ctx::MAX_AUX + 1, atoi(e)));
+  CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i + 1 < c->n_dev_streams; i++) {
+    if (alloc_scratch(c->sc_aux[i], max_frames, sp, max_pts)) { delete c; return -1; }
+    CK(cudaStreamCreateWithFlags(&c->s_aux[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
   }
   CK(cudaStreamSynchronize(c->s_comp));
   *out = c;
@@ -236,7 +232,8 @@ extern "C" void bevgen_destroy(bevgen_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_scratch(c->sc_dev);
-  if (c->s_aux) { free_scratch(c->sc_aux); cudaStreamDestroy(c->s_aux); for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_front[i]); cudaEventDestroy(c->ev_sweep[i]); } }
+  for (int i = 0; i < bevgen_ctx::MAX_AUX; i++) if (c->s_aux[i]) { free_scratch(c->sc_aux[i]); cudaStreamDestroy(c->s_aux[i]); cudaEventDestroy(c->ev_join[i]); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->lanes_ready) for (auto& l : c->lanes) { free_scratch(l.sc); free_io(l.in, l.out); cudaEventDestroy(l.ev_h2d); cudaEventDestroy(l.ev_comp); cudaEventDestroy(l.ev_d2h); }
   for (auto& s : c->slots) { free_scratch(s.sc); free_io(s.in, s.out); cudaFreeHost(s.pin_in); cudaFreeHost(s.pin_out); cudaFree(s.offs_d); cudaStreamDestroy(s.st); cudaEventDestroy(s.done); }
   cudaFree(c->cnt_lut); cudaFree(c->offs_d);
@@ -374,8 +371,8 @@ extern "C" int bevgen_process_device(bevgen_ctx* c, int nf, const int64_t* offse
   // Measured alternatives (profiles/r1_notes.md): a front/sweep/back software pipeline with a high-priority sweep
   // stream was slower - sweep and ordering kernels contend for the same L1/LSU data pipe.  Profiling serialises.
   const int nw = (nf + c->max_frames - 1) / c->max_frames;
-  const bool two = c->n_dev_streams == 2 && !c->prof && nw > 1;
-  if (two) { CK(cudaEventRecord(c->ev_front[0], c->s_comp)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_front[0], 0)); }
+  const int ns = (c->prof || nw == 1) ? 1 : std::min(c->n_dev_streams, nw);
+  if (ns > 1) { CK(cudaEventRecord(c->ev_fork, c->s_comp)); for (int i = 0; i + 1 < ns; i++) CK(cudaStreamWaitEvent(c->s_aux[i], c->ev_fork, 0)); }
   for (int w = 0; w < nw; w++) {
     const int f0 = w * c->max_frames;
     const int n = std::min(c->max_frames, nf - f0);
@@ -383,10 +380,10 @@ extern "C" int bevgen_process_device(bevgen_ctx* c, int nf, const int64_t* offse
     for (int f = f0; f < f0 + n; f++) max_n = std::max<int64_t>(max_n, offsets[f + 1] - offsets[f]);
     DevOut dout; dout.label = out->label + (size_t)f0 * S; dout.wbits = out->winner_bits;   // words are indexed by absolute offsets
     dout.single = out->single_bev + (size_t)f0 * CELLS; dout.multi = out->multi_bev + (size_t)f0 * LAYERS * CELLS;
-    const bool aux = two && (w & 1);
-    if (run_wave(c, aux ? c->s_aux : c->s_comp, aux ? c->sc_aux : c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout, c->prof, f0)) return -1;
+    const int si = w % ns;   // stream 0 = s_comp, i > 0 = s_aux[i - 1]; each stream owns one scratch set, its waves serialise on it
+    if (run_wave(c, si ? c->s_aux[si - 1] : c->s_comp, si ? c->sc_aux[si - 1] : c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout, c->prof, f0)) return -1;
   }
-  if (two) { CK(cudaEventRecord(c->ev_sweep[0], c->s_aux)); CK(cudaStreamWaitEvent(c->s_comp, c->ev_sweep[0], 0)); }
+  for (int i = 0; i + 1 < ns; i++) { CK(cudaEventRecord(c->ev_join[i], c->s_aux[i])); CK(cudaStreamWaitEvent(c->s_comp, c->ev_join[i], 0)); }
   return 0;
 }
 

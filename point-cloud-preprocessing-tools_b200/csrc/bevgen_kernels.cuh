@@ -579,6 +579,8 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
 constexpr int SEG_CAP = 4096;
 constexpr int SEGT = 512;
 constexpr int SMEM_SEG = SEG_CAP * 4 * 2 + NSECT * 4 + SEGT * 8 + 320 + SEG_CAP * 2 * 3 + (NSECT + 2) * 2;   // 84,264 B
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+constexpr int FOLD_AHEAD = 6;           // segments prefetched ahead of the chain in k_seg_fold
 constexpr int FOLD_STEP = 32;           // heights per step of a chain in k_seg_fold
 constexpr int FOLD_PASSES = 12;         // warps per frame in k_seg_fold (32 sectors each; more sectors wrap around)
 
@@ -628,10 +630,21 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
   for (int i = tid; i < NSECT; i += SEGT) s_kcnt[i] = 0;
   if (tid == 0) s_misc[0] = 0;
   // ---- pass 1: last participating slot / sector of this thread's groups ----
+  // the thread's group summaries: the first 8 live in registers (one round trip), further ones are re-read
+  uint4 gv[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) gv[i] = g0 + i < g1 ? GS[g0 + i] : make_uint4(0u, 0u, 0u, 0u);
+  auto summary = [&](int g) -> uint4 {
+    const int i = g - g0;
+    uint4 r = GS[min(g, n_groups - 1)];                           // only used (and only then waited for) when i >= 8
+#pragma unroll
+    for (int q = 0; q < 8; q++) if (i == q) r = gv[q];
+    return r;
+  };
   {
     unsigned lk = NO_KEY; int lp = -1;
     for (int g = g0; g < g1; g++) {
-      const uint4 v = GS[g];
+      const uint4 v = summary(g);
       if (v.x) { lk = v.z >> 16; lp = slot_of(g, 31 - __clz(v.x)); }
     }
     s_lk[tid] = lk; s_lp[tid] = lp;
@@ -645,7 +658,7 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
   {
     unsigned k = ck;
     for (int g = g0; g < g1; g++) {
-      const uint4 v = GS[g];
+      const uint4 v = summary(g);
       if (!v.x) continue;
       nh += __popc(v.y) + ((v.z & 0xFFFFu) != k ? 1u : 0u);
       k = v.z >> 16;
@@ -660,7 +673,7 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
     unsigned e = ebase;
     unsigned k = ck; int lastp = cp;
     for (int g = g0; g < g1; g++) {
-      const uint4 v = GS[g];
+      const uint4 v = summary(g);
       const unsigned pm = v.x;
       if (!pm) continue;
       unsigned hm = v.y;
@@ -671,7 +684,6 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
         const unsigned below = pm & ((1u << l) - 1u);
         const int prev_end = below ? base + 31 - __clz(below) : lastp;
         s_start[e] = (uint32_t)(base + l);
-        s_key[e] = K[base + l];
         if (e > 0) s_endtmp[e - 1] = (uint32_t)prev_end;
         e++;
       }
@@ -685,10 +697,11 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
   }
   __syncthreads();
   for (int e = tid; e < nseg; e += SEGT) {
-    const unsigned d = s_endtmp[e] - s_start[e];
+    const unsigned st = s_start[e], d = s_endtmp[e] - st;
+    const unsigned k = K[st];                                     // sector of the segment (independent loads, all in flight)
     if (d > 0xFFFFu) s_misc[0] = 1u;                              // a segment longer than 65535 slots: sweep kernel
-    s_len[e] = (uint16_t)d;
-    atomicAdd(&s_kcnt[s_key[e]], 1u);
+    s_len[e] = (uint16_t)d; s_key[e] = (uint16_t)k;
+    atomicAdd(&s_kcnt[k], 1u);
   }
   __syncthreads();
   if (s_misc[0]) { if (tid == 0) slow_flag[f] = 1u; return; }     // uniform
@@ -785,6 +798,8 @@ __global__ void __launch_bounds__(32) k_seg_fold(SensorDev sp, const float* __re
     unsigned j = SS[cur], hi = j + SL[cur];
     unsigned st2 = 0u, en2 = 0u;                                    // the following segment, fetched one segment ahead
     if (cur + 1 < endseg) { st2 = SS[cur + 1]; en2 = st2 + SL[cur + 1]; }
+#pragma unroll
+    for (int a2 = 1; a2 < FOLD_AHEAD; a2++) if (cur + a2 < endseg) prefetch_l1(Z + SS[cur + a2]);
     // One step = a 16-byte aligned window of FOLD_STEP heights around the current position, fetched with 128-bit loads
     // (every lane reads its own lines: the kernel is bound by L1 wavefronts, one per lane and load, so loads are wide)
     // and all issued before the first add.  Heights outside [j, hi] are replaced by +0.
@@ -806,11 +821,12 @@ __global__ void __launch_bounds__(32) k_seg_fold(SensorDev sp, const float* __re
 #pragma unroll
       for (int u = 0; u < FOLD_STEP; u++) acc = __fadd_rn(acc, v[u]);
       j = jb + FOLD_STEP;
-      if (j <= hi) continue;
+      if (j <= hi) { if (j + 3 * FOLD_STEP <= hi) prefetch_l1(Z + j + 3 * FOLD_STEP); continue; }
       cur++;
       if (cur >= endseg) break;
       j = st2; hi = en2;
       if (cur + 1 < endseg) { st2 = SS[cur + 1]; en2 = st2 + SL[cur + 1]; }
+      if (cur + FOLD_AHEAD < endseg) prefetch_l1(Z + SS[cur + FOLD_AHEAD]);   // the chain is latency bound: pull later segments in early
     }
     avg[(size_t)f * NSECT + k] = __fdiv_rn(acc, cnt_lut[cnt[(size_t)f * NSECT + k]]);   // :210
   }

@@ -46,6 +46,32 @@ def test_sector_mean_sweep_fallback(pkg, synth, O, monkeypatch):
             g.close()
 
 
+def test_large_range_image_global_claim_path(pkg, O):
+    """A range image too large for the shared-memory ordering kernel (S = 128 x 8192 > 640 k slots) takes the
+    global-memory claim path (k_order_claim / k_order_fill / k_winner_bits); same results expected."""
+    p = pkg.sensor_params("HDL_64E")
+    p.n_scan, p.horizon_scan, p.ground_upper_scan, p.height_res = 128, 8192, 100, 0.25
+    sp = O.Sensor(); sp.n_scan, sp.horizon_scan, sp.ground_upper_scan, sp.height_res = 128, 8192, 100, 0.25
+    rng = np.random.default_rng(99)
+    frames = [_rand_frame(rng, 128, 8192, n, spread=40.0) for n in (300_000, 70_001, 0)]
+    # a structured patch so that ground marking has something to do: a flat disc of points over many rows / columns
+    n = 200_000
+    rows = rng.integers(60, 128, n); cols = rng.integers(0, 8192, n)
+    ang = cols / 8192.0 * 2 * np.pi; rad = 3.0 + (127 - rows) * 0.3
+    frames.append(dict(x=(rad * np.cos(ang)).astype(np.float32), y=(rad * np.sin(ang)).astype(np.float32),
+                       z=(-1.7 + rng.normal(0, 0.02, n)).astype(np.float32), intensity=rng.random(n).astype(np.float32),
+                       row=rows.astype(np.uint16), col=cols.astype(np.uint16), label=np.full(n, -2, np.int16)))
+    batch = cat_frames(frames)
+    g = pkg.BevGen(p, device=0, max_frames_per_batch=2, max_points_per_frame=300_000)
+    try:
+        out = g.process_host(batch)
+    finally:
+        g.close()
+    ref = oracle_batch(O, sp, batch)
+    assert (ref["label"][3][ref["owner"][3] > 0] == 0).mean() > 0.3      # the disc really is ground
+    assert_same(out, ref, "large S")
+
+
 def test_kitti_quirk_all_intensity_minus_one(gens, synth, O):
     batch = synth.make_batch("HDL_64E", 2, first=100, kitti_quirk=True)
     out = gens("HDL_64E", max_frames_per_batch=4).process_host(batch)

@@ -21,6 +21,28 @@ __global__ void k_scatter16(const uint32_t* __restrict__ idx, float4* __restrict
   int f = blockIdx.y; int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < S) { uint32_t s = idx[(size_t)f * S + i]; rec[(size_t)f * S + s] = make_float4(i, f, s, 1.f); }
 }
+template <int MODE>
+__global__ void k_scatter16v(const uint32_t* __restrict__ idx, float4* __restrict__ rec, int F) {
+  int f = blockIdx.y; int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S) {
+    uint32_t s = idx[(size_t)f * S + i]; float4 v = make_float4(i, f, s, 1.f); float4* p = &rec[(size_t)f * S + s];
+    if (MODE == 0) __stcg(p, v); else if (MODE == 1) __stcs(p, v); else if (MODE == 2) __stwt(p, v);
+    else if (MODE == 3) { float2* q = reinterpret_cast<float2*>(p); *q = make_float2(v.x, v.y); }              // 8 B
+    else if (MODE == 4) { float4* q = &rec[((size_t)f * S + s) * 2]; q[0] = v; q[1] = v; }                      // 32 B per slot
+  }
+}
+// sorted-within-warp scatter: each warp sorts its 32 slots (bitonic via shuffles) before storing
+__global__ void k_scatter16_blocksort(const uint32_t* __restrict__ idx, float4* __restrict__ rec, int F) {
+  __shared__ uint32_t keys[1024];
+  int f = blockIdx.y; int i = blockIdx.x * 1024 + threadIdx.x;
+  uint32_t s = i < S ? idx[(size_t)f * S + i] : 0xFFFFFFFFu;
+  keys[threadIdx.x] = s; __syncthreads();
+  // rank by counting (O(n^2/1024) per thread = 1024 compares) - only to see whether store ORDER matters
+  uint32_t r = 0; for (int j = 0; j < 1024; j++) r += keys[j] < s;
+  __syncthreads(); if (s != 0xFFFFFFFFu) keys[r] = s; __syncthreads();
+  uint32_t t = keys[threadIdx.x];
+  if (i < S && t != 0xFFFFFFFFu) rec[(size_t)f * S + t] = make_float4(i, f, t, 1.f);
+}
 __global__ void k_scatter4(const uint32_t* __restrict__ idx, uint32_t* __restrict__ own, int F) {
   int f = blockIdx.y; int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < S) { uint32_t s = idx[(size_t)f * S + i]; own[(size_t)f * S + s] = i + 1; }
@@ -110,6 +132,13 @@ int main() {
   timeit("copy float4", 2.0 * n4 * 16, [&] { k_copy<<<148 * 8, 1024>>>(rec, rec2, n4); });
   dim3 g((S + 255) / 256, F);
   timeit("scatter16 (idx4 + st16)", n4 * 20.0, [&] { k_scatter16<<<g, 256>>>(idx, rec, F); });
+  timeit("scatter16 stcg", n4 * 20.0, [&] { k_scatter16v<0><<<g, 256>>>(idx, rec, F); });
+  timeit("scatter16 stcs", n4 * 20.0, [&] { k_scatter16v<1><<<g, 256>>>(idx, rec, F); });
+  timeit("scatter16 stwt", n4 * 20.0, [&] { k_scatter16v<2><<<g, 256>>>(idx, rec, F); });
+  timeit("scatter8", n4 * 12.0, [&] { k_scatter16v<3><<<g, 256>>>(idx, rec, F); });
+  timeit("scatter32 (half the frames)", n4 * 0.5 * 36.0, [&] { k_scatter16v<4><<<dim3(g.x, F / 2), 256>>>(idx, rec, F / 2); });
+  timeit("scatter16 sorted per 1024", n4 * 20.0, [&] { k_scatter16_blocksort<<<dim3((S + 1023) / 1024, F), 1024>>>(idx, rec, F); });
+  timeit("scatter16 256 frames only", n4 * 0.25 * 20.0, [&] { k_scatter16<<<dim3(g.x, F / 4), 256>>>(idx, rec, F / 4); });
   timeit("scatter4  (idx4 + st4)", n4 * 8.0, [&] { k_scatter4<<<g, 256>>>(idx, own, F); });
   timeit("gather16  (idx4+ld16+st16)", n4 * 36.0, [&] { k_gather16<<<g, 256>>>(idx, rec, rec2, F); });
   CK(cudaFuncSetAttribute(k_smem<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140000));
@@ -122,7 +151,7 @@ int main() {
   timeit("smem atomicMax u32 (ret)", n4 * 4.0, [&] { k_smem<3><<<F, 1024, 134000>>>(idx, out); });
 
   // cluster probes
-  for (int csz : {2, 4, 8, 16}) {
+  for (int csz : {0}) { if (csz == 0) break;
     cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
     int smem = 200 * 1024;
     cudaFuncSetAttribute(k_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
