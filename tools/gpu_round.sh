@@ -1,12 +1,11 @@
 #!/bin/bash
-# one gpurun call: parity tests, bench, launch list, ncu full capture, microbench
+# one gpurun call: parity tests, bench, launch list, ncu full capture
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json
-timeout 300 ./tools/microbench > gpurun_out/microbench.txt 2>&1; cat gpurun_out/microbench.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --frames 740 --wave 740 --e2e-frames 8 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_(order|ground|sector|finalize)" -s 15 -c 5 -o gpurun_out/prof python bench.py --steps 1 --warmup 3 --frames 740 --wave 740 --e2e-frames 8 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_(order|ground|sector|seg|finalize)" -s 21 -c 7 -f -o gpurun_out/prof python bench.py --steps 1 --warmup 3 --frames 740 --wave 740 --e2e-frames 8 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out
