@@ -106,6 +106,25 @@ BEVGEN_API int bevgen_process_device(bevgen_ctx *ctx, int n_frames, const int64_
                           const bevgen_outputs *out);
 BEVGEN_API int bevgen_sync(bevgen_ctx *ctx);
 
+/* SURVEY 8(f)-1 — packed-record staging: the frames arrive as the interleaved records of a binary PCD payload
+ * (what pcl::io::loadPCDFile parses at BatchMultiBevGen.cpp:730 and savePCDFileBinary writes at :756) and the
+ * de-interleave into SoA runs on the GPU, so host staging is one copy of the file payload into pinned memory.
+ * Field types are those of pcl::PointXYZIRCT (BatchMultiBevGen.h:43-66): x, y, z, intensity f32; row, col u16;
+ * label i16.  Offsets are bytes inside a record (any order, any padding, no alignment requirement); -1 = the field is
+ * absent and reads as 0 (pcl::fromPCLPointCloud2 leaves a missing field value-initialised). */
+typedef struct bevgen_record_layout {
+  int32_t stride;                              /* bytes per record, 1..256 */
+  int32_t off_x, off_y, off_z, off_intensity;  /* f32 */
+  int32_t off_row, off_col;                    /* u16 */
+  int32_t off_label;                           /* i16 */
+} bevgen_record_layout;
+/* The 26-byte layout of a PointXYZIRCT binary PCD: x@0 y@4 z@8 intensity@12 row@16 col@18 (t@20) label@24. */
+BEVGEN_API int bevgen_pcd_record_layout(bevgen_record_layout *out);
+/* Same contract as bevgen_process_host; `records` = HOST buffer with the concatenated records of all frames
+ * (frame f = records [offsets[f], offsets[f+1]), i.e. bytes from offsets[f]*stride). */
+BEVGEN_API int bevgen_process_packed_host(bevgen_ctx *ctx, int n_frames, const int64_t *offsets, const void *records,
+                               const bevgen_record_layout *layout, const bevgen_outputs *out);
+
 /* Asynchronous single-frame form used by pipelined callers (one frame of the loop at :727-757):
  * submit copies the frame into the context's pinned ring and enqueues H2D + kernels + D2H; collect blocks on that
  * frame's event and copies the results out.  At most `max_frames_per_batch` frames may be in flight.     */

@@ -40,6 +40,19 @@ class Outputs(C.Structure):
     _fields_ = [("label", C.c_void_p), ("winner_bits", C.c_void_p), ("single_bev", C.c_void_p), ("multi_bev", C.c_void_p)]
 
 
+class RecordLayout(C.Structure):
+    """bevgen_record_layout: byte offsets of the PointXYZIRCT fields inside an interleaved record (-1 = absent)."""
+    _fields_ = [("stride", C.c_int32), ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32),
+                ("off_intensity", C.c_int32), ("off_row", C.c_int32), ("off_col", C.c_int32), ("off_label", C.c_int32)]
+
+
+def pcd_record_layout():
+    """The 26-byte record of a PointXYZIRCT binary PCD (savePCDFileBinary, BatchMultiBevGen.cpp:756)."""
+    lay = RecordLayout()
+    _ck(lib().bevgen_pcd_record_layout(C.byref(lay)))
+    return lay
+
+
 def winner_words(n_total, n_frames):
     """bevgen_winner_words (include/bevgen.h)."""
     return (int(n_total) >> 5) + int(n_frames) + 1
@@ -72,7 +85,7 @@ EXPORTS = ["bevgen_sensor_params", "bevgen_create", "bevgen_destroy", "bevgen_la
            "bevgen_host_free", "bevgen_process_host", "bevgen_process_device", "bevgen_sync", "bevgen_submit",
            "bevgen_collect", "bevgen_select_major", "bevgen_labels", "bevgen_cloud_manip", "bevgen_set_profiling",
            "bevgen_stage_ms", "bevgen_kernel_launches", "bevgen_compute_stream", "bevgen_stage_name",
-           "bevgen_debug_atan2f"]
+           "bevgen_debug_atan2f", "bevgen_pcd_record_layout", "bevgen_process_packed_host"]
 
 
 def build(verbose=False):
@@ -204,6 +217,20 @@ class BevGen:
         _ck(lib().bevgen_process_host(self._ctx, C.c_int(F), _ptr(offs), C.byref(pts), C.byref(o)))
         if not user_out:   # convenience for tests: the ordered cloud as a gather table (host-side unpack of the winner bits)
             out["owner"] = owner_from_winner(out["winner"], offs, arrs[4], arrs[5], self.params.horizon_scan, self.S)
+        return out
+
+    def process_packed_host(self, records, offsets, layout=None, out=None):
+        """records: HOST uint8 array with the concatenated interleaved records of all frames (a binary PCD payload);
+        layout: RecordLayout (default = the 26-byte PCD record).  The de-interleave runs on the GPU."""
+        offs = np.ascontiguousarray(offsets, np.int64)
+        F = len(offs) - 1
+        layout = layout or pcd_record_layout()
+        rec = np.ascontiguousarray(records).view(np.uint8).reshape(-1)
+        if rec.size < int(offs[-1]) * layout.stride:
+            raise ValueError("records shorter than offsets[-1] * stride")
+        out = out or self.alloc_outputs(F, n_total=int(offs[-1]))
+        o = Outputs(_ptr(out["label"]), _ptr(out["winner"]), _ptr(out["single"]), _ptr(out["multi"]))
+        _ck(lib().bevgen_process_packed_host(self._ctx, C.c_int(F), _ptr(offs), _ptr(rec), C.byref(layout), C.byref(o)))
         return out
 
     def process_device(self, F, offsets, dev_in, dev_out):

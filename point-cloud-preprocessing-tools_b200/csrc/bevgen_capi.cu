@@ -42,11 +42,13 @@ struct Scratch {            // device scratch for one wave of up to `frames` fra
   uint32_t* owner = 0;                   // [frames][S] claim table, only for range images too large for k_order_winners' shared memory
   uint32_t* occ = 0;                     // [3][frames][ceil(S/32)] slot occupancy bits, contention bits, contended-id prefix
   uint32_t* cwin = 0;                    // [frames][cw_stride] 1 + largest input index per contended slot
+  uint32_t* cpt = 0; size_t cpt_words = 0;   // one bit per input point of the wave: the point's slot is contended
   size_t frames = 0;
 };
 
 struct Lane {               // host-path double buffer: device staging of inputs/outputs + scratch
   Scratch sc; DevIn in; DevOut out;
+  uint8_t* raw = 0; size_t raw_cap = 0;   // packed-record staging (bevgen_process_packed_host), sized on first use
   cudaEvent_t ev_h2d = 0, ev_comp = 0, ev_d2h = 0;
   bool used = false;
 };
@@ -124,6 +126,8 @@ static int alloc_scratch(Scratch& s, size_t frames, const SensorDev& sp, int max
   else {
     CK(cudaMalloc(&s.occ, 3 * frames * ((S + 31) / 32) * sizeof(uint32_t)));
     CK(cudaMalloc(&s.cwin, frames * (size_t)(max_pts / 2 + 1) * sizeof(uint32_t)));   // a contended slot holds >= 2 points
+    s.cpt_words = frames * (size_t)max_pts / 32 + 4;
+    CK(cudaMalloc(&s.cpt, s.cpt_words * sizeof(uint32_t)));
   }
   CK(cudaMalloc(&s.gsum, frames * gsum_per_frame(sp) * sizeof(uint4)));
   CK(cudaMalloc(&s.slow, frames * sizeof(uint32_t)));
@@ -138,7 +142,7 @@ static int alloc_scratch(Scratch& s, size_t frames, const SensorDev& sp, int max
   return 0;
 }
 static void free_scratch(Scratch& s) {
-  cudaFree(s.rec); cudaFree(s.gkey); cudaFree(s.gz); cudaFree(s.cnt); cudaFree(s.avg); cudaFree(s.gsum); cudaFree(s.slow); cudaFree(s.seg_start); cudaFree(s.seg_len); cudaFree(s.kdesc); cudaFree(s.act); cudaFree(s.n_act); cudaFree(s.owner); cudaFree(s.occ); cudaFree(s.cwin);
+  cudaFree(s.rec); cudaFree(s.gkey); cudaFree(s.gz); cudaFree(s.cnt); cudaFree(s.avg); cudaFree(s.gsum); cudaFree(s.slow); cudaFree(s.seg_start); cudaFree(s.seg_len); cudaFree(s.kdesc); cudaFree(s.act); cudaFree(s.n_act); cudaFree(s.owner); cudaFree(s.occ); cudaFree(s.cwin); cudaFree(s.cpt);
   s = Scratch();
 }
 static int alloc_io(DevIn& in, DevOut& out, size_t frames, size_t pts, size_t S) {
@@ -234,7 +238,7 @@ extern "C" void bevgen_destroy(bevgen_ctx* c) {
   free_scratch(c->sc_dev);
   for (int i = 0; i < bevgen_ctx::MAX_AUX; i++) if (c->s_aux[i]) { free_scratch(c->sc_aux[i]); cudaStreamDestroy(c->s_aux[i]); cudaEventDestroy(c->ev_join[i]); }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-  if (c->lanes_ready) for (auto& l : c->lanes) { free_scratch(l.sc); free_io(l.in, l.out); cudaEventDestroy(l.ev_h2d); cudaEventDestroy(l.ev_comp); cudaEventDestroy(l.ev_d2h); }
+  if (c->lanes_ready) for (auto& l : c->lanes) { cudaFree(l.raw); free_scratch(l.sc); free_io(l.in, l.out); cudaEventDestroy(l.ev_h2d); cudaEventDestroy(l.ev_comp); cudaEventDestroy(l.ev_d2h); }
   for (auto& s : c->slots) { free_scratch(s.sc); free_io(s.in, s.out); cudaFreeHost(s.pin_in); cudaFreeHost(s.pin_out); cudaFree(s.offs_d); cudaStreamDestroy(s.st); cudaEventDestroy(s.done); }
   cudaFree(c->cnt_lut); cudaFree(c->offs_d);
   for (auto& e : c->pev) cudaEventDestroy(e);
@@ -249,7 +253,8 @@ extern "C" void bevgen_destroy(bevgen_ctx* c) {
 //   front  = clear + order_claim + order_fill + ground_mark      (L2 / HBM bound)
 //   sweep  = sector_mean                                          (MIO / latency bound, few warps per SM)
 //   back   = finalize_bin_scatter                                 (HBM + shared-memory bound)
-struct WaveArgs { const Scratch* sc; int nf; const int64_t* offs_d; int64_t base; int max_n; DevIn in; DevOut out; int frame0; };
+struct WaveArgs { const Scratch* sc; int nf; const int64_t* offs_d; int64_t base; int max_n; DevIn in; DevOut out; int frame0;
+                  int64_t qbase, n_pts; };   // qbase: 32-aligned caller offset of the wave's first point; n_pts: points of the wave (+ alignment slack)
 
 static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {
   const SensorDev& sp = c->sp;
@@ -262,15 +267,16 @@ static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
   mark(0);
   CK(cudaMemsetAsync(w.sc->cnt, 0, (size_t)w.nf * NSECT * sizeof(uint32_t), st));
   if (!fused_order(sp)) CK(cudaMemsetAsync(w.sc->owner, 0, (size_t)w.nf * S * sizeof(uint32_t), st));
+  else CK(cudaMemsetAsync(w.sc->cpt, 0, std::min(w.sc->cpt_words, (size_t)(w.n_pts + 31) / 32 + 2) * sizeof(uint32_t), st));
   mark(1);
   if (fused_order(sp)) {
     const size_t W = (S + 31) / 32;
     uint32_t *occ = w.sc->occ, *cont = occ + (size_t)w.sc->frames * W, *cpre = cont + (size_t)w.sc->frames * W;
-    k_order_winners<<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, row, col, occ, cont, cpre, w.sc->cwin);
+    k_order_winners<<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, row, col, occ, cont, cpre, w.sc->cwin, w.qbase, w.sc->cpt);
     mark(2);
     dim3 g((std::max<int>(w.max_n, (int)S) + 255) / 256, w.nf);
     k_order_scatter<<<g, 256, 0, st>>>(sp, c->xf, w.offs_d, w.frame0, c->cw_stride, x, y, z, it, row, col, lab, occ, cont, cpre, w.sc->cwin,
-                                       w.sc->rec, w.out.wbits);
+                                       w.sc->rec, w.out.wbits, w.qbase, w.sc->cpt);
     c->launches += 2;
   } else {   // range image too large for shared memory: claim table in global memory (two kernels + the winner bits)
     if (w.max_n > 0) {
@@ -301,10 +307,10 @@ static int wave_sweep(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
   k_seg_build<<<w.nf, SEGT, SMEM_SEG, st>>>(c->sp, c->seg_cap, w.sc->gsum, w.sc->gkey, w.sc->avg, w.sc->slow, w.sc->seg_start,
                                             w.sc->seg_len, w.sc->kdesc, w.sc->act, w.sc->n_act);
   if ((c->sp.S & 3) == 0)   // every frame of gz starts on a 16-byte boundary: 128-bit loads
-    k_seg_fold<true><<<dim3(FOLD_PASSES, w.nf), 32, 0, st>>>(c->sp, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->slow, w.sc->seg_start, w.sc->seg_len,
+    k_seg_fold<true><<<dim3(w.nf, FOLD_PASSES), 32, 0, st>>>(c->sp, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->slow, w.sc->seg_start, w.sc->seg_len,
                                                              w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->avg);
   else
-    k_seg_fold<false><<<dim3(FOLD_PASSES, w.nf), 32, 0, st>>>(c->sp, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->slow, w.sc->seg_start, w.sc->seg_len,
+    k_seg_fold<false><<<dim3(w.nf, FOLD_PASSES), 32, 0, st>>>(c->sp, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->slow, w.sc->seg_start, w.sc->seg_len,
                                                               w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->avg);
   k_sector_mean<<<w.nf, 32, NSECT * sizeof(float), st>>>(c->sp, w.sc->gkey, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->avg, w.sc->slow);
   if (prof) cudaEventRecord(c->pev[5], st);
@@ -329,8 +335,9 @@ static int wave_back(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pro
 }
 // all three stages back to back on one stream
 static int run_wave(bevgen_ctx* c, cudaStream_t st, const Scratch& sc, int nf, const int64_t* offs_d, int64_t base, int max_n,
-                    const DevIn& in, const DevOut& out, bool prof, int frame0) {
-  WaveArgs w{&sc, nf, offs_d, base, max_n, in, out, frame0};
+                    const DevIn& in, const DevOut& out, bool prof, int frame0, int64_t first_pt, int64_t end_pt) {
+  const int64_t qbase = first_pt & ~(int64_t)31;
+  WaveArgs w{&sc, nf, offs_d, base, max_n, in, out, frame0, qbase, end_pt - qbase};
   if (wave_front(c, st, w, prof)) return -1;
   if (wave_sweep(c, st, w, prof)) return -1;
   return wave_back(c, st, w, prof);
@@ -381,7 +388,7 @@ extern "C" int bevgen_process_device(bevgen_ctx* c, int nf, const int64_t* offse
     DevOut dout; dout.label = out->label + (size_t)f0 * S; dout.wbits = out->winner_bits;   // words are indexed by absolute offsets
     dout.single = out->single_bev + (size_t)f0 * CELLS; dout.multi = out->multi_bev + (size_t)f0 * LAYERS * CELLS;
     const int si = w % ns;   // stream 0 = s_comp, i > 0 = s_aux[i - 1]; each stream owns one scratch set, its waves serialise on it
-    if (run_wave(c, si ? c->s_aux[si - 1] : c->s_comp, si ? c->sc_aux[si - 1] : c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout, c->prof, f0)) return -1;
+    if (run_wave(c, si ? c->s_aux[si - 1] : c->s_comp, si ? c->sc_aux[si - 1] : c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout, c->prof, f0, offsets[f0], offsets[f0 + n])) return -1;
   }
   for (int i = 0; i + 1 < ns; i++) { CK(cudaEventRecord(c->ev_join[i], c->s_aux[i])); CK(cudaStreamWaitEvent(c->s_comp, c->ev_join[i], 0)); }
   return 0;
@@ -412,9 +419,9 @@ static int ensure_lanes(bevgen_ctx* c) {
   return 0;
 }
 
-extern "C" int bevgen_process_host(bevgen_ctx* c, int nf, const int64_t* offsets, const bevgen_points* in, const bevgen_outputs* out) {
-  if (!c || !offsets || !in || !out) return fail("bevgen_process_host: null argument");
-  if (nf <= 0) return 0;
+// `in` (SoA) or `records` + `lay` (interleaved records, de-interleaved on the GPU by k_unpack_records) - exactly one is set.
+static int process_host_impl(bevgen_ctx* c, int nf, const int64_t* offsets, const bevgen_points* in, const uint8_t* records,
+                             const RecLayout* lay, const bevgen_outputs* out) {
   CK(cudaSetDevice(c->device));
   if (ensure_lanes(c)) return -1;
   int max_n_all = 0;
@@ -422,6 +429,15 @@ extern "C" int bevgen_process_host(bevgen_ctx* c, int nf, const int64_t* offsets
   if (max_n_all > c->max_pts) return fail("bevgen_process_host: a frame exceeds max_points_per_frame");
   const size_t S = c->sp.S;
   const int chunk = host_chunk(c);
+  if (records) {
+    const size_t need = (size_t)chunk * c->max_pts * lay->stride + 64;
+    for (auto& l : c->lanes)
+      if (l.raw_cap < need) {
+        CK(cudaStreamSynchronize(c->s_comp)); CK(cudaStreamSynchronize(c->s_copy));
+        cudaFree(l.raw); l.raw = 0; l.raw_cap = 0;
+        CK(cudaMalloc(&l.raw, need)); l.raw_cap = need;
+      }
+  }
   int k = 0;
   for (int f0 = 0; f0 < nf; f0 += chunk, k++) {
     Lane& l = c->lanes[k % 3];
@@ -432,20 +448,34 @@ extern "C" int bevgen_process_host(bevgen_ctx* c, int nf, const int64_t* offsets
     for (int f = f0; f < f0 + n; f++) max_n = std::max<int64_t>(max_n, offsets[f + 1] - offsets[f]);
     // inputs of this lane may be overwritten once the kernels of its previous wave are done
     if (l.used) CK(cudaStreamWaitEvent(c->s_copy, l.ev_comp, 0));
-    CK(cudaMemcpyAsync(l.in.x, in->x + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
-    CK(cudaMemcpyAsync(l.in.y, in->y + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
-    CK(cudaMemcpyAsync(l.in.z, in->z + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
-    CK(cudaMemcpyAsync(l.in.inten, in->intensity + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
-    CK(cudaMemcpyAsync(l.in.row, in->row + base, np * 2, cudaMemcpyHostToDevice, c->s_copy));
-    CK(cudaMemcpyAsync(l.in.col, in->col + base, np * 2, cudaMemcpyHostToDevice, c->s_copy));
-    CK(cudaMemcpyAsync(l.in.label, in->label + base, np * 2, cudaMemcpyHostToDevice, c->s_copy));
+    if (records) {
+      CK(cudaMemcpyAsync(l.raw, records + (size_t)base * lay->stride, np * lay->stride, cudaMemcpyHostToDevice, c->s_copy));
+    } else {
+      CK(cudaMemcpyAsync(l.in.x, in->x + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
+      CK(cudaMemcpyAsync(l.in.y, in->y + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
+      CK(cudaMemcpyAsync(l.in.z, in->z + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
+      CK(cudaMemcpyAsync(l.in.inten, in->intensity + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
+      CK(cudaMemcpyAsync(l.in.row, in->row + base, np * 2, cudaMemcpyHostToDevice, c->s_copy));
+      CK(cudaMemcpyAsync(l.in.col, in->col + base, np * 2, cudaMemcpyHostToDevice, c->s_copy));
+      CK(cudaMemcpyAsync(l.in.label, in->label + base, np * 2, cudaMemcpyHostToDevice, c->s_copy));
+    }
     CK(cudaEventRecord(l.ev_h2d, c->s_copy));
     CK(cudaStreamWaitEvent(c->s_comp, l.ev_h2d, 0));
     if (l.used) CK(cudaStreamWaitEvent(c->s_comp, l.ev_d2h, 0));   // outputs of the previous wave have left
+    if (records && max_n > 0) {   // interleaved records -> the lane's SoA arrays
+      bool even = (lay->stride & 1) == 0;
+      for (int q = 0; q < 7; q++) if (lay->off[q] >= 0 && (lay->off[q] & 1)) even = false;
+      dim3 g((max_n + 255) / 256, n);
+      const size_t sm = 256 * (size_t)lay->stride + 32;
+      if (even) k_unpack_records<true><<<g, 256, sm, c->s_comp>>>(*lay, c->offs_d + f0, base, l.raw, l.in.x, l.in.y, l.in.z, l.in.inten, l.in.row, l.in.col, l.in.label);
+      else k_unpack_records<false><<<g, 256, sm, c->s_comp>>>(*lay, c->offs_d + f0, base, l.raw, l.in.x, l.in.y, l.in.z, l.in.inten, l.in.row, l.in.col, l.in.label);
+      CK(cudaGetLastError());
+      c->launches++;
+    }
     // winner words of this chunk: [w0, w1) of the caller's array; the kernel indexes with absolute offsets / frame ids
     const size_t w0 = (size_t)(base >> 5) + (size_t)f0, w1 = (size_t)(offsets[f0 + n] >> 5) + (size_t)(f0 + n);
     DevOut lo = l.out; lo.wbits = l.out.wbits - w0;
-    if (run_wave(c, c->s_comp, l.sc, n, c->offs_d + f0, base, max_n, l.in, lo, false, f0)) return -1;
+    if (run_wave(c, c->s_comp, l.sc, n, c->offs_d + f0, base, max_n, l.in, lo, false, f0, offsets[f0], offsets[f0 + n])) return -1;
     CK(cudaEventRecord(l.ev_comp, c->s_comp));
     CK(cudaStreamWaitEvent(c->s_d2h, l.ev_comp, 0));
     CK(cudaMemcpyAsync(out->label + (size_t)f0 * S, l.out.label, (size_t)n * S * 2, cudaMemcpyDeviceToHost, c->s_d2h));
@@ -459,6 +489,36 @@ extern "C" int bevgen_process_host(bevgen_ctx* c, int nf, const int64_t* offsets
   CK(cudaStreamSynchronize(c->s_comp));
   CK(cudaStreamSynchronize(c->s_copy));
   return 0;
+}
+
+extern "C" int bevgen_process_host(bevgen_ctx* c, int nf, const int64_t* offsets, const bevgen_points* in, const bevgen_outputs* out) {
+  if (!c || !offsets || !in || !out) return fail("bevgen_process_host: null argument");
+  if (nf <= 0) return 0;
+  return process_host_impl(c, nf, offsets, in, nullptr, nullptr, out);
+}
+
+// The 26-byte record savePCDFileBinary writes for pcl::PointXYZIRCT (BatchMultiBevGen.h:56-66; `t` at byte 20 is skipped).
+extern "C" int bevgen_pcd_record_layout(bevgen_record_layout* out) {
+  if (!out) return fail("bevgen_pcd_record_layout: null argument");
+  out->stride = 26; out->off_x = 0; out->off_y = 4; out->off_z = 8; out->off_intensity = 12;
+  out->off_row = 16; out->off_col = 18; out->off_label = 24;
+  return 0;
+}
+
+extern "C" int bevgen_process_packed_host(bevgen_ctx* c, int nf, const int64_t* offsets, const void* records,
+                                          const bevgen_record_layout* layout, const bevgen_outputs* out) {
+  if (!c || !offsets || !records || !layout || !out) return fail("bevgen_process_packed_host: null argument");
+  if (nf <= 0) return 0;
+  RecLayout L;
+  L.stride = layout->stride;
+  const int offs[7] = {layout->off_x, layout->off_y, layout->off_z, layout->off_intensity, layout->off_row, layout->off_col, layout->off_label};
+  if (L.stride < 1 || L.stride > 256) return fail("bevgen_process_packed_host: record stride must be 1..256 bytes");
+  for (int q = 0; q < 7; q++) {
+    const int w = q < 4 ? 4 : 2;
+    if (offs[q] < -1 || (offs[q] >= 0 && offs[q] + w > L.stride)) return fail("bevgen_process_packed_host: field offset outside the record");
+    L.off[q] = offs[q];
+  }
+  return process_host_impl(c, nf, offsets, nullptr, (const uint8_t*)records, &L, out);
 }
 
 // ---- submit / collect (single frames in flight, one stream per ring slot) ---------------------------------------
@@ -507,7 +567,7 @@ extern "C" int bevgen_submit(bevgen_ctx* c, int frame_id, int n_in, const float*
   CK(cudaMemcpyAsync(s->in.row, pr, n * 2, cudaMemcpyHostToDevice, s->st));
   CK(cudaMemcpyAsync(s->in.col, pc, n * 2, cudaMemcpyHostToDevice, s->st));
   CK(cudaMemcpyAsync(s->in.label, pl, n * 2, cudaMemcpyHostToDevice, s->st));
-  if (run_wave(c, s->st, s->sc, 1, s->offs_d, 0, n_in, s->in, s->out, false, 0)) return -1;
+  if (run_wave(c, s->st, s->sc, 1, s->offs_d, 0, n_in, s->in, s->out, false, 0, 0, n_in)) return -1;
   char* q = s->pin_out;
   const size_t ww = ((size_t)c->max_pts / 32 + 4) * 4;
   CK(cudaMemcpyAsync(q, s->out.wbits, ((n + 31) / 32) * 4, cudaMemcpyDeviceToHost, s->st)); q += ww;

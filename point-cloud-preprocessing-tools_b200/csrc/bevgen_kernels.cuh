@@ -156,6 +156,56 @@ __device__ __forceinline__ unsigned sector_of(float px, float py) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Kp unpack_records — SURVEY §8(f)-1: the de-interleave of pcl::io::loadPCDFile (BatchMultiBevGen.cpp:730) moved to the
+// GPU.  A binary PCD payload is an array of interleaved records (26 packed bytes for PointXYZIRCT as written by
+// savePCDFileBinary: x y z intensity f32 | row col u16 | t u32 | label i16, BatchMultiBevGen.h:56-66); the host only
+// copies the payload into pinned memory, this kernel turns it into the SoA arrays the ordering kernels read.
+// Fields are addressed by byte offset inside a record (any order / padding; -1 = field absent => 0, like
+// pcl::fromPCLPointCloud2 leaves a missing field value-initialised).  A CTA stages its 256 records through shared
+// memory with 16-byte coalesced loads (records are only 2-byte aligned), then every thread assembles its record.
+// grid (ceil(max_n/256), F), block 256, dynamic smem 256*stride + 32.
+// ------------------------------------------------------------------------------------------------------------
+struct RecLayout { int stride; int off[7]; };   // x, y, z, intensity (f32), row, col (u16), label (i16)
+
+template <bool EVEN>   // EVEN: stride and every offset are even => 16-bit shared-memory reads instead of bytes
+__global__ void __launch_bounds__(256) k_unpack_records(RecLayout L, const int64_t* __restrict__ offs, int64_t base,
+                                                         const uint8_t* __restrict__ raw, float* __restrict__ x,
+                                                         float* __restrict__ y, float* __restrict__ z, float* __restrict__ inten,
+                                                         uint16_t* __restrict__ row, uint16_t* __restrict__ col,
+                                                         int16_t* __restrict__ label) {
+  extern __shared__ __align__(16) unsigned char urec[];
+  const int f = blockIdx.y;
+  const int64_t o = offs[f] - base;                    // first point of the frame inside the staged chunk
+  const int n = (int)(offs[f + 1] - offs[f]);
+  const int i0 = blockIdx.x * 256;
+  if (i0 >= n) return;
+  const int cnt = min(256, n - i0);
+  const int64_t b0 = (o + i0) * (int64_t)L.stride;     // first byte of the tile; `raw` is 16-byte aligned and padded
+  const int64_t a0 = b0 & ~(int64_t)15;
+  const int head = (int)(b0 - a0);
+  const int n16 = (head + cnt * L.stride + 15) >> 4;
+  const uint4* src = reinterpret_cast<const uint4*>(raw + a0);
+  for (int v = threadIdx.x; v < n16; v += 256) reinterpret_cast<uint4*>(urec)[v] = __ldcs(src + v);
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t >= cnt) return;
+  const unsigned char* r = urec + head + t * L.stride;
+  auto u16 = [&](int off) -> unsigned {
+    if (EVEN) return *reinterpret_cast<const uint16_t*>(r + off);
+    return (unsigned)r[off] | ((unsigned)r[off + 1] << 8);
+  };
+  auto u32 = [&](int off) -> unsigned { return u16(off) | (u16(off + 2) << 16); };
+  const int64_t q = o + i0 + t;
+  x[q] = L.off[0] >= 0 ? __uint_as_float(u32(L.off[0])) : 0.0f;
+  y[q] = L.off[1] >= 0 ? __uint_as_float(u32(L.off[1])) : 0.0f;
+  z[q] = L.off[2] >= 0 ? __uint_as_float(u32(L.off[2])) : 0.0f;
+  inten[q] = L.off[3] >= 0 ? __uint_as_float(u32(L.off[3])) : 0.0f;
+  row[q] = L.off[4] >= 0 ? (uint16_t)u16(L.off[4]) : (uint16_t)0;
+  col[q] = L.off[5] >= 0 ? (uint16_t)u16(L.off[5]) : (uint16_t)0;
+  label[q] = L.off[6] >= 0 ? (int16_t)u16(L.off[6]) : (int16_t)0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // K0a order_claim — getOrderedCloud (BatchMultiBevGen.cpp:94-117), pass 1: the serial loop makes the LAST input
 // point of a slot win; atomicMax over (input index + 1) reproduces that deterministically.
 // grid (ceil(max_n/256), F), block 256.
@@ -264,7 +314,8 @@ __device__ __forceinline__ uint4 ld8_u16(const uint16_t* aligned_base, int v8) {
 __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int64_t* __restrict__ offs, int cw_stride,
                                                           const uint16_t* __restrict__ row, const uint16_t* __restrict__ col,
                                                           uint32_t* __restrict__ occ_bits, uint32_t* __restrict__ cont_bits,
-                                                          uint32_t* __restrict__ cont_pre, uint32_t* __restrict__ cwin) {
+                                                          uint32_t* __restrict__ cont_pre, uint32_t* __restrict__ cwin,
+                                                          int64_t qbase, uint32_t* __restrict__ cpt_bits) {
   extern __shared__ __align__(16) unsigned char ord_smem[];
   const int W = (sp.S + 31) >> 5;
   uint32_t* occ = reinterpret_cast<uint32_t*>(ord_smem);           // [W]
@@ -290,10 +341,18 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
       if (atomicOr(&occ[slot >> 5], bit) & bit) atomicOr(&cont[slot >> 5], bit);
     }
   };
+  // cpt_bits: one bit per INPUT point (bit index = o + i - qbase, qbase = 32-aligned first point of the wave), set iff the
+  // point's slot is contended.  k_order_scatter reads it coalesced, so only the 0.5 % contended points pay the random
+  // cont_bits / cont_pre / cwin lookups (ncu: those lookups were 0.76 L2 sector reads per point, a fifth of its L2 traffic).
+  const int64_t q0 = o - qbase;
   auto visit2 = [&](unsigned r, unsigned c, int i) {
     if (i >= 0 && i < n && r < N && c < H) {
       const unsigned slot = r * H + c, bit = 1u << (slot & 31), cw = cont[slot >> 5];
-      if (cw & bit) atomicMax(&cwin[(size_t)f * cw_stride + occ[slot >> 5] + __popc(cw & (bit - 1u))], (uint32_t)i + 1u);
+      if (cw & bit) {
+        atomicMax(&cwin[(size_t)f * cw_stride + occ[slot >> 5] + __popc(cw & (bit - 1u))], (uint32_t)i + 1u);
+        const int64_t q = q0 + i;
+        atomicOr(&cpt_bits[q >> 5], 1u << (q & 31));
+      }
     }
   };
   auto scan = [&](auto visit) {
@@ -348,7 +407,8 @@ __global__ void __launch_bounds__(256) k_order_scatter(SensorDev sp, Xform xf, c
                                                         const int16_t* __restrict__ label, const uint32_t* __restrict__ occ_bits,
                                                         const uint32_t* __restrict__ cont_bits, const uint32_t* __restrict__ cont_pre,
                                                         const uint32_t* __restrict__ cwin, float4* __restrict__ rec,
-                                                        uint32_t* __restrict__ winner_bits) {
+                                                        uint32_t* __restrict__ winner_bits, int64_t qbase,
+                                                        const uint32_t* __restrict__ cpt_bits) {
   const int f = blockIdx.y;
   const int64_t o = offs[f];
   const int n = (int)(offs[f + 1] - o);
@@ -364,13 +424,14 @@ __global__ void __launch_bounds__(256) k_order_scatter(SensorDev sp, Xform xf, c
   if (i - lane >= n) return;                                        // whole warp past the end
   // every load of the point is issued before the winner test: 99.5 % of the points win
   unsigned r = 0xFFFFu, c = 0xFFFFu; float px = 0.f, py = 0.f, pz = 0.f, pi = 0.f; int16_t lb = 0;
-  if (i < n) { r = row[o + i]; c = col[o + i]; px = x[o + i]; py = y[o + i]; pz = z[o + i]; pi = inten[o + i]; lb = label[o + i]; }
+  if (i < n) { r = row[o + i]; c = col[o + i]; px = __ldcs(x + o + i); py = __ldcs(y + o + i); pz = __ldcs(z + o + i); pi = __ldcs(inten + o + i); lb = __ldcs(label + o + i); }
   const bool valid = r < (unsigned)sp.N && c < (unsigned)sp.H;      // :106-109
   const unsigned slot = valid ? r * sp.H + c : 0u, bit = 1u << (slot & 31);
   bool win = valid;
-  if (valid) {
+  const int64_t q = o + i - qbase;
+  if (valid && ((cpt_bits[q >> 5] >> (q & 31)) & 1u)) {   // contended slot (rare): the serial loop's last writer = largest index
     const uint32_t cw = cont_bits[fw + (slot >> 5)];
-    if (cw & bit) win = cwin[(size_t)f * cw_stride + cont_pre[fw + (slot >> 5)] + __popc(cw & (bit - 1u))] == (uint32_t)i + 1u;
+    win = cwin[(size_t)f * cw_stride + cont_pre[fw + (slot >> 5)] + __popc(cw & (bit - 1u))] == (uint32_t)i + 1u;
   }
   const unsigned wm = __ballot_sync(0xffffffffu, win);
   if (lane == 0) wb[i >> 5] = wm;
@@ -777,20 +838,22 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
 // so the lines it touches live in L1).  The lane walks a flat sequence of steps of up to FOLD_STEP heights (padded
 // with +0, which never changes the sum), so the 32 chains of a warp stay in lockstep whatever their segment boundaries
 // are.  Then the IEEE divide (:210).
-// grid (FOLD_PASSES, F), block 32: warp p of a frame owns the active sectors p*32 + lane (+ 32*FOLD_PASSES ...).
+// grid (F, FOLD_PASSES), block 32: warp p of a frame owns the active sectors p*32 + lane (+ 32*FOLD_PASSES ...).
 template <bool VEC>
 __global__ void __launch_bounds__(32) k_seg_fold(SensorDev sp, const float* __restrict__ gz, const uint32_t* __restrict__ cnt,
                                                   const float* __restrict__ cnt_lut, const uint32_t* __restrict__ slow_flag,
                                                   const uint32_t* __restrict__ seg_start, const uint16_t* __restrict__ seg_len,
                                                   const uint32_t* __restrict__ kdesc, const uint16_t* __restrict__ act,
                                                   const uint32_t* __restrict__ n_act_in, float* __restrict__ avg) {
-  const int f = blockIdx.y;
+  // grid (F, FOLD_PASSES): CTAs are dispatched in linear order, so every frame's pass 0 (its 32 longest chains, the
+  // list is sorted by cost) starts before any short pass - longest-processing-time-first keeps the tail short.
+  const int f = blockIdx.x;
   if (slow_flag[f]) return;                                       // the sweep kernel takes this frame
   const unsigned n_act = n_act_in[f];
   const float* Z = gz + (size_t)f * sp.S;
   const uint32_t* SS = seg_start + (size_t)f * SEG_CAP;
   const uint16_t* SL = seg_len + (size_t)f * SEG_CAP;
-  for (unsigned a = blockIdx.x * 32 + threadIdx.x; a < n_act; a += 32 * FOLD_PASSES) {
+  for (unsigned a = blockIdx.y * 32 + threadIdx.x; a < n_act; a += 32 * FOLD_PASSES) {
     const unsigned k = act[(size_t)f * NSECT + a];
     const unsigned d = kdesc[(size_t)f * NSECT + k];
     unsigned cur = d >> 16; const unsigned endseg = cur + (d & 0xFFFFu);
@@ -872,15 +935,24 @@ __global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const fl
   const float4* R = rec + fb;
   const uint16_t* K = gkey + fb;
   const int first = sp.band_row0 * sp.H;
-  constexpr int UB = 4;
+  // Register double buffer: the loads of batch k+1 are in flight while batch k goes through the shared-memory atomics
+  // (ncu: the loop was load-batch -> wait -> process, the memory pipe idled during every process phase).
+  constexpr int UB = 3;
+  float4 nv[UB]; unsigned nk[UB];
+  auto fetch = [&](int s0) {
+#pragma unroll
+    for (int u = 0; u < UB; u++) {
+      const int sl = s0 + u * 1024;
+      nv[u] = sl < sp.S ? __ldcs(R + sl) : make_float4(0.f, 0.f, 0.f, 0.f);       // read once: streaming (evict-first) loads
+      nk[u] = (sl < sp.S && sl >= first) ? (unsigned)__ldcs(K + sl) : NO_KEY;
+    }
+  };
+  fetch(tid);
   for (int slot0 = tid; slot0 < sp.S; slot0 += 1024 * UB) {
    float4 pv[UB]; unsigned kv[UB];
 #pragma unroll
-   for (int u = 0; u < UB; u++) {
-     const int sl = slot0 + u * 1024;
-     pv[u] = sl < sp.S ? R[sl] : make_float4(0.f, 0.f, 0.f, 0.f);
-     kv[u] = (sl < sp.S && sl >= first) ? (unsigned)K[sl] : NO_KEY;
-   }
+   for (int u = 0; u < UB; u++) { pv[u] = nv[u]; kv[u] = nk[u]; }
+   if (slot0 + 1024 * UB < sp.S) fetch(slot0 + 1024 * UB);
 #pragma unroll
    for (int u = 0; u < UB; u++) {
     const int slot = slot0 + u * 1024;
@@ -901,7 +973,7 @@ __global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const fl
         if (!cleared) lab = 0;                   // :244-245
       }
     }
-    label_out[fb + slot] = lab;
+    __stcs(label_out + fb + slot, lab);     // outputs are never re-read on the device: streaming stores
     if (lab == 0) continue;                      // :285 / :349
     const float vx = __fadd_rn(p.x, 112.0f), vy = __fadd_rn(p.y, 112.0f);   // (pi.x + MAX_RANGE) / 1.0f
     // x = round(v + 0.5) in double, valid 0..223  <=>  -1 < v < 223 and then x = floor(v) + 1   (:279-284)
@@ -936,7 +1008,7 @@ __global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const fl
   __syncthreads();
 
   uint4* so = reinterpret_cast<uint4*>(single + (size_t)f * CELLS);
-  for (int i = tid; i < CELL_WORDS / 4; i += 1024) so[i] = reinterpret_cast<const uint4*>(hgt)[i];
+  for (int i = tid; i < CELL_WORDS / 4; i += 1024) __stcs(so + i, reinterpret_cast<const uint4*>(hgt)[i]);
   uint4* mo = reinterpret_cast<uint4*>(multi + (size_t)f * LAYERS * CELLS);
   constexpr int Q = CELL_WORDS / 4;   // uint4 per layer = 3136
   for (int i = tid; i < LAYERS * Q; i += 1024) {
@@ -946,7 +1018,7 @@ __global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const fl
     uint4 o;
     o.x = ((v.x >> l) & 0x01010101u) * 255u; o.y = ((v.y >> l) & 0x01010101u) * 255u;
     o.z = ((v.z >> l) & 0x01010101u) * 255u; o.w = ((v.w >> l) & 0x01010101u) * 255u;
-    mo[i] = o;
+    __stcs(mo + i, o);
   }
 }
 

@@ -308,3 +308,44 @@ def test_full_size_properties(gens, synth):
         # a cell with occupancy in a layer >= 1 has z >= -1.875+... > -2 => positive single height
         assert (a["single"][f][a["multi"][f][2:].max(0) > 0] > 0).all()
         assert occ.sum() > 100
+
+
+def _pack_records(batch, layout, rng):
+    """Interleave the SoA batch into records of the given layout (padding filled with random bytes)."""
+    n = len(batch["x"])
+    rec = rng.integers(0, 256, size=(n, layout.stride), dtype=np.uint8)
+    put = lambda off, a: rec.__setitem__((slice(None), slice(off, off + a.dtype.itemsize)),
+                                         np.ascontiguousarray(a).view(np.uint8).reshape(n, a.dtype.itemsize))
+    for name, off, t in (("x", layout.off_x, np.float32), ("y", layout.off_y, np.float32), ("z", layout.off_z, np.float32),
+                         ("intensity", layout.off_intensity, np.float32), ("row", layout.off_row, np.uint16),
+                         ("col", layout.off_col, np.uint16), ("label", layout.off_label, np.int16)):
+        if off >= 0:
+            put(off, np.asarray(batch[name], t))
+    return rec.reshape(-1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["pcd26", "reordered_odd", "missing_fields"])
+def test_packed_records_deinterleave_on_gpu(gens, synth, O, pkg, kind):
+    """SURVEY 8(f)-1: frames handed over as the interleaved records of a binary PCD payload (loadPCDFile, :730);
+    the GPU de-interleave must give exactly what the SoA path gives (bit-exact vs the oracle)."""
+    sensor = "HDL_32E"
+    batch = synth.make_batch(sensor, 7, first=300)           # 7 frames > host chunking of max_frames_per_batch=3
+    rng = np.random.default_rng(5)
+    if kind == "pcd26":
+        lay = pkg.pcd_record_layout()
+        assert (lay.stride, lay.off_x, lay.off_y, lay.off_z, lay.off_intensity, lay.off_row, lay.off_col, lay.off_label) == (26, 0, 4, 8, 12, 16, 18, 24)
+    elif kind == "reordered_odd":                              # odd stride and offsets: byte-wise shared-memory reads
+        lay = pkg.RecordLayout(37, 21, 3, 9, 29, 1, 33, 15)
+    else:                                                      # intensity and label absent -> 0 (value-initialised)
+        lay = pkg.RecordLayout(20, 0, 4, 8, -1, 12, 14, -1)
+        batch = dict(batch); batch["intensity"] = np.zeros_like(batch["intensity"]); batch["label"] = np.zeros_like(batch["label"])
+    ref = oracle_batch(O, sensor, batch)
+    g = gens(sensor, max_frames_per_batch=3)
+    rec = _pack_records(batch, lay, rng)
+    out = g.process_packed_host(rec, batch["offsets"], lay)
+    out["owner"] = pkg.owner_from_winner(out["winner"], batch["offsets"], np.asarray(batch["row"], np.uint16), np.asarray(batch["col"], np.uint16),
+                                         g.params.horizon_scan, g.S)
+    assert_same(out, ref, "packed " + kind)
+    with pytest.raises(pkg.BevgenError, match="offset outside"):
+        g.process_packed_host(rec, batch["offsets"], pkg.RecordLayout(26, 24, 4, 8, 12, 16, 18, 24))
