@@ -67,12 +67,16 @@ typedef struct bevgen_points {
  *                               bit (i & 31) of word (i >> 5) from there.  bevgen_winner_words(n_total, F) words in all;
  *                               words between two frames are unspecified.
  *   single_bev [F][224][224]    computeAndSaveSingleBev matrix (:340-356)
- *   multi_bev  [F][24][224][224] computeAndSaveMultiBev layers = the .bin payload (:271-292, :307-314)          */
+ *   multi_bev  [F][24][224][224] computeAndSaveMultiBev layers = the .bin payload (:271-292, :307-314)
+ *   bvm        [F][201][201] f32 OPTIONAL (NULL = not computed): batch_cloud_manip's bird-view map, saveAsMat of
+ *                               BatchCloudManip.cpp:201-226 with interval 1.0f on the ground-removed ordered cloud
+ *                               (max of z + 2.0f per 1 m cell, label == 0 skipped) - SURVEY 8(f)-3                */
 typedef struct bevgen_outputs {
   int16_t *label;
   uint32_t *winner_bits;
   uint8_t *single_bev;
   uint8_t *multi_bev;
+  float *bvm;
 } bevgen_outputs;
 
 /* Number of 32-bit words of bevgen_outputs.winner_bits for F frames holding n_total points. */

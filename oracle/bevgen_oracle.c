@@ -417,6 +417,23 @@ ORACLE_API void oracle_save_as_mat(int64_t n, const float *x, const float *y, co
   }
 }
 
+/* batch_cloud_manip's saveAsMat, BatchCloudManip.cpp:201-226, called with interval_res = 1.0f (:310) on the ordered,
+ * ground-marked cloud (:305-320) => MAT_SIZE = 201 (static, fixed by the first call).  Differs from CloudManip.cpp's
+ * version only by the `pi.label == 0` skip (:214).  x/y/z/label: the S slots of the ordered cloud. */
+ORACLE_API void oracle_bvm(int64_t n, const float *x, const float *y, const float *z, const int16_t *label,
+                           float *cart_bv /*201*201*/) {
+  const int MAXR = 100; const float interval = 1.0f;
+  const int MS = (int)(MAXR * 2 / interval + 1);                                   /* :208 */
+  for (int i = 0; i < MS * MS; i++) cart_bv[i] = 0.0f;                             /* :209 cv::Mat::zeros */
+  for (int64_t i = 0; i < n; i++) {
+    int xi = x86_cvtt(round((double)((x[i] + (float)MAXR) / interval) + 0.5));     /* :211 */
+    int yi = x86_cvtt(round((double)((y[i] + (float)MAXR) / interval) + 0.5));     /* :212 */
+    if (xi < 0 || xi >= MS || yi < 0 || yi >= MS || label[i] == 0) continue;       /* :214 */
+    float v = z[i] + 2.0f;
+    if (v > cart_bv[xi * MS + yi]) cart_bv[xi * MS + yi] = v;                      /* :218-220 */
+  }
+}
+
 /* Exposed for tests: the float libm the oracle was built against. */
 ORACLE_API float oracle_atan2f(float y, float x) { return atan2f(y, x); }
 ORACLE_API float oracle_angle_deg(float dz, float dx, float dy) {

@@ -173,6 +173,15 @@ def save_as_mat(x, y, z):
     return m.reshape(201, 201)
 
 
+def bvm(oc, label):
+    """batch_cloud_manip's bird-view map (BatchCloudManip.cpp:201-226) of the ordered cloud oc with post-ground labels."""
+    x, px = _f(oc["x"]); y, py = _f(oc["y"]); z, pz = _f(oc["z"])
+    label = np.ascontiguousarray(label, np.int16)
+    m = np.empty(201 * 201, np.float32)
+    lib().oracle_bvm(C.c_int64(len(x)), px, py, pz, _p(label, C.c_int16), _p(m, C.c_float))
+    return m.reshape(201, 201)
+
+
 # ---- reference KD-tree (oracle/_ref) ---------------------------------------------------------------
 def ref_knn_many(pts, qs, k):
     r = ref_lib()

@@ -17,6 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libbevgen_cuda.so")
 CLI_PATH = os.path.join(_HERE, "bin", "batch_multi_bev_gen")
 CLOUD_MANIP_PATH = os.path.join(_HERE, "bin", "cloud_manip")
+BATCH_CLOUD_MANIP_PATH = os.path.join(_HERE, "bin", "batch_cloud_manip")
 GRID, LAYERS, CELLS = 224, 24, 224 * 224
 N_STAGES = 8
 
@@ -37,7 +38,8 @@ class Points(C.Structure):
 
 
 class Outputs(C.Structure):
-    _fields_ = [("label", C.c_void_p), ("winner_bits", C.c_void_p), ("single_bev", C.c_void_p), ("multi_bev", C.c_void_p)]
+    _fields_ = [("label", C.c_void_p), ("winner_bits", C.c_void_p), ("single_bev", C.c_void_p), ("multi_bev", C.c_void_p),
+                ("bvm", C.c_void_p)]     # bvm: optional [F][201][201] f32 bird-view map (batch_cloud_manip), None = skip
 
 
 class RecordLayout(C.Structure):
@@ -197,11 +199,13 @@ class BevGen:
             pass
 
     # ---- hot loop -------------------------------------------------------------------------------------------
-    def alloc_outputs(self, F, pinned=False, n_total=None):
+    def alloc_outputs(self, F, pinned=False, n_total=None, bvm=False):
         mk = pinned_empty if pinned else np.empty
         n_total = F * self.max_pts if n_total is None else n_total
         out = dict(label=mk((F, self.S), np.int16), winner=mk((winner_words(n_total, F),), np.uint32),
                    single=mk((F, GRID, GRID), np.uint8), multi=mk((F, LAYERS, GRID, GRID), np.uint8))
+        if bvm:
+            out["bvm"] = mk((F, 201, 201), np.float32)
         out["winner"][...] = 0      # the library writes every word of a frame's range and zeroes the gaps; the tail word is spare
         return out
 
@@ -213,7 +217,7 @@ class BevGen:
         out = out or self.alloc_outputs(F, n_total=int(offs[-1]))
         arrs = [_as(batch[k], t) for k, t in _FIELDS]      # keep converted temporaries alive across the call
         pts = Points(*[_ptr(a) for a in arrs])
-        o = Outputs(_ptr(out["label"]), _ptr(out["winner"]), _ptr(out["single"]), _ptr(out["multi"]))
+        o = Outputs(_ptr(out["label"]), _ptr(out["winner"]), _ptr(out["single"]), _ptr(out["multi"]), _ptr(out.get("bvm")))
         _ck(lib().bevgen_process_host(self._ctx, C.c_int(F), _ptr(offs), C.byref(pts), C.byref(o)))
         if not user_out:   # convenience for tests: the ordered cloud as a gather table (host-side unpack of the winner bits)
             out["owner"] = owner_from_winner(out["winner"], offs, arrs[4], arrs[5], self.params.horizon_scan, self.S)
@@ -229,7 +233,7 @@ class BevGen:
         if rec.size < int(offs[-1]) * layout.stride:
             raise ValueError("records shorter than offsets[-1] * stride")
         out = out or self.alloc_outputs(F, n_total=int(offs[-1]))
-        o = Outputs(_ptr(out["label"]), _ptr(out["winner"]), _ptr(out["single"]), _ptr(out["multi"]))
+        o = Outputs(_ptr(out["label"]), _ptr(out["winner"]), _ptr(out["single"]), _ptr(out["multi"]), _ptr(out.get("bvm")))
         _ck(lib().bevgen_process_packed_host(self._ctx, C.c_int(F), _ptr(offs), _ptr(rec), C.byref(layout), C.byref(o)))
         return out
 
@@ -238,7 +242,7 @@ class BevGen:
         offs = np.ascontiguousarray(offsets, np.int64)
         pts = Points(*[C.c_void_p(int(dev_in[k])) for k, _ in _FIELDS])
         o = Outputs(C.c_void_p(int(dev_out["label"])), C.c_void_p(int(dev_out["winner"])), C.c_void_p(int(dev_out["single"])),
-                    C.c_void_p(int(dev_out["multi"])))
+                    C.c_void_p(int(dev_out["multi"])), C.c_void_p(int(dev_out["bvm"])) if dev_out.get("bvm") else None)
         _ck(lib().bevgen_process_device(self._ctx, C.c_int(F), _ptr(offs), C.byref(pts), C.byref(o)))
 
     def sync(self):

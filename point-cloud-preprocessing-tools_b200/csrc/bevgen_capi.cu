@@ -31,7 +31,8 @@ static int fail(const std::string& m) { g_err = m; return -1; }
 namespace {
 
 struct DevIn { float *x = 0, *y = 0, *z = 0, *inten = 0; uint16_t *row = 0, *col = 0; int16_t* label = 0; };
-struct DevOut { int16_t* label = 0; uint32_t* wbits = 0; uint8_t* single = 0; uint8_t* multi = 0; };
+struct DevOut { int16_t* label = 0; uint32_t* wbits = 0; uint8_t* single = 0; uint8_t* multi = 0; float* bvm = 0; };
+constexpr size_t BVM_CELLS = (size_t)MGRID * MGRID;
 static size_t wwords(size_t n_total, size_t frames) { return (n_total >> 5) + frames + 1; }
 
 struct Scratch {            // device scratch for one wave of up to `frames` frames
@@ -49,6 +50,7 @@ struct Scratch {            // device scratch for one wave of up to `frames` fra
 struct Lane {               // host-path double buffer: device staging of inputs/outputs + scratch
   Scratch sc; DevIn in; DevOut out;
   uint8_t* raw = 0; size_t raw_cap = 0;   // packed-record staging (bevgen_process_packed_host), sized on first use
+  float* bvm = 0;                         // bird-view-map staging (bevgen_outputs.bvm), allocated on first use
   cudaEvent_t ev_h2d = 0, ev_comp = 0, ev_d2h = 0;
   bool used = false;
 };
@@ -206,6 +208,7 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
   for (auto& e : c->pev) CK(cudaEventCreate(&e));
   CK(cudaFuncSetAttribute(k_finalize_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BIN));
   CK(cudaFuncSetAttribute(k_seg_build, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SEG));
+  CK(cudaFuncSetAttribute(k_float_bev, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BVM));
   CK(cudaFuncSetAttribute(k_order_winners, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // function-wide: the largest any context may ask for
   CK(cudaFuncSetAttribute(k_seg_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   if (const char* e = getenv("BEVGEN_SEG_CAP")) c->seg_cap = std::max(0, std::min(SEG_CAP, atoi(e)));
@@ -238,7 +241,7 @@ extern "C" void bevgen_destroy(bevgen_ctx* c) {
   free_scratch(c->sc_dev);
   for (int i = 0; i < bevgen_ctx::MAX_AUX; i++) if (c->s_aux[i]) { free_scratch(c->sc_aux[i]); cudaStreamDestroy(c->s_aux[i]); cudaEventDestroy(c->ev_join[i]); }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-  if (c->lanes_ready) for (auto& l : c->lanes) { cudaFree(l.raw); free_scratch(l.sc); free_io(l.in, l.out); cudaEventDestroy(l.ev_h2d); cudaEventDestroy(l.ev_comp); cudaEventDestroy(l.ev_d2h); }
+  if (c->lanes_ready) for (auto& l : c->lanes) { cudaFree(l.raw); cudaFree(l.bvm); free_scratch(l.sc); free_io(l.in, l.out); cudaEventDestroy(l.ev_h2d); cudaEventDestroy(l.ev_comp); cudaEventDestroy(l.ev_d2h); }
   for (auto& s : c->slots) { free_scratch(s.sc); free_io(s.in, s.out); cudaFreeHost(s.pin_in); cudaFreeHost(s.pin_out); cudaFree(s.offs_d); cudaStreamDestroy(s.st); cudaEventDestroy(s.done); }
   cudaFree(c->cnt_lut); cudaFree(c->offs_d);
   for (auto& e : c->pev) cudaEventDestroy(e);
@@ -323,6 +326,11 @@ static int wave_back(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pro
   if (prof) cudaEventRecord(c->pev[6], st);
   CK(cudaGetLastError());
   c->launches += 1;
+  if (w.out.bvm) {   // batch_cloud_manip's float bird-view map, from the labels just written
+    k_float_bev<<<w.nf, 512, SMEM_BVM, st>>>(c->sp, w.sc->rec, w.out.label, w.out.bvm);
+    CK(cudaGetLastError());
+    c->launches += 1;
+  }
   if (prof) {
     CK(cudaEventSynchronize(c->pev[6]));
     for (int i = 0; i < 6; i++) {
@@ -387,6 +395,7 @@ extern "C" int bevgen_process_device(bevgen_ctx* c, int nf, const int64_t* offse
     for (int f = f0; f < f0 + n; f++) max_n = std::max<int64_t>(max_n, offsets[f + 1] - offsets[f]);
     DevOut dout; dout.label = out->label + (size_t)f0 * S; dout.wbits = out->winner_bits;   // words are indexed by absolute offsets
     dout.single = out->single_bev + (size_t)f0 * CELLS; dout.multi = out->multi_bev + (size_t)f0 * LAYERS * CELLS;
+    dout.bvm = out->bvm ? out->bvm + (size_t)f0 * BVM_CELLS : nullptr;
     const int si = w % ns;   // stream 0 = s_comp, i > 0 = s_aux[i - 1]; each stream owns one scratch set, its waves serialise on it
     if (run_wave(c, si ? c->s_aux[si - 1] : c->s_comp, si ? c->sc_aux[si - 1] : c->sc_dev, n, c->offs_d + f0, 0, max_n, di, dout, c->prof, f0, offsets[f0], offsets[f0 + n])) return -1;
   }
@@ -438,6 +447,8 @@ static int process_host_impl(bevgen_ctx* c, int nf, const int64_t* offsets, cons
         CK(cudaMalloc(&l.raw, need)); l.raw_cap = need;
       }
   }
+  if (out->bvm)
+    for (auto& l : c->lanes) if (!l.bvm) CK(cudaMalloc(&l.bvm, (size_t)chunk * BVM_CELLS * sizeof(float)));
   int k = 0;
   for (int f0 = 0; f0 < nf; f0 += chunk, k++) {
     Lane& l = c->lanes[k % 3];
@@ -474,7 +485,7 @@ static int process_host_impl(bevgen_ctx* c, int nf, const int64_t* offsets, cons
     }
     // winner words of this chunk: [w0, w1) of the caller's array; the kernel indexes with absolute offsets / frame ids
     const size_t w0 = (size_t)(base >> 5) + (size_t)f0, w1 = (size_t)(offsets[f0 + n] >> 5) + (size_t)(f0 + n);
-    DevOut lo = l.out; lo.wbits = l.out.wbits - w0;
+    DevOut lo = l.out; lo.wbits = l.out.wbits - w0; lo.bvm = out->bvm ? l.bvm : nullptr;
     if (run_wave(c, c->s_comp, l.sc, n, c->offs_d + f0, base, max_n, l.in, lo, false, f0, offsets[f0], offsets[f0 + n])) return -1;
     CK(cudaEventRecord(l.ev_comp, c->s_comp));
     CK(cudaStreamWaitEvent(c->s_d2h, l.ev_comp, 0));
@@ -482,6 +493,7 @@ static int process_host_impl(bevgen_ctx* c, int nf, const int64_t* offsets, cons
     CK(cudaMemcpyAsync(out->winner_bits + w0, l.out.wbits, (w1 - w0) * 4, cudaMemcpyDeviceToHost, c->s_d2h));
     CK(cudaMemcpyAsync(out->single_bev + (size_t)f0 * CELLS, l.out.single, (size_t)n * CELLS, cudaMemcpyDeviceToHost, c->s_d2h));
     CK(cudaMemcpyAsync(out->multi_bev + (size_t)f0 * LAYERS * CELLS, l.out.multi, (size_t)n * LAYERS * CELLS, cudaMemcpyDeviceToHost, c->s_d2h));
+    if (out->bvm) CK(cudaMemcpyAsync(out->bvm + (size_t)f0 * BVM_CELLS, l.bvm, (size_t)n * BVM_CELLS * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
     CK(cudaEventRecord(l.ev_d2h, c->s_d2h));
     l.used = true;
   }

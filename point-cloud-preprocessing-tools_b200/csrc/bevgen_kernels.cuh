@@ -1140,6 +1140,38 @@ __device__ __forceinline__ void manip_scatter(float px, float py, float pz, bool
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// batch_cloud_manip's bird-view map - saveAsMat of BatchCloudManip.cpp:201-226 on the ground-removed
+// ordered cloud: 201x201 floats, cell <- z + 2.0f when strictly greater (cells start at 0), points with label == 0
+// (ground, or empty slot) skipped (:214).  Same order-free int max on positive float patterns as manip_scatter, with
+// the frame's whole grid in shared memory.  Reads the labels k_finalize_bin wrote and the ordered cloud `rec`.
+// grid F, block 512, dynamic smem SMEM_BVM.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SMEM_BVM = MGRID * MGRID * 4;   // 161,604 B
+
+__global__ void __launch_bounds__(512) k_float_bev(SensorDev sp, const float4* __restrict__ rec, const int16_t* __restrict__ label,
+                                                    float* __restrict__ bvm) {
+  extern __shared__ __align__(16) int bvm_s[];
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const size_t fb = (size_t)f * sp.S;
+  for (int i = tid; i < MGRID * MGRID; i += 512) bvm_s[i] = 0;
+  __syncthreads();
+  for (int slot = tid; slot < sp.S; slot += 512) {
+    if (label[fb + slot] == 0) continue;                                     // :214
+    const float4 p = rec[fb + slot];
+    const float vx = __fadd_rn(p.x, 100.0f), vy = __fadd_rn(p.y, 100.0f);   // (pi.x + MAX_RANGE) / interval, interval = 1.0f (:211-212)
+    const float v = __fadd_rn(p.z, 2.0f);                                    // :218
+    // x = round(vx + 0.5) in double, valid 0..200  <=>  -1 < vx < 200 and then x = floor(vx) + 1
+    if (!(vx > -1.0f && vx < 200.0f && vy > -1.0f && vy < 200.0f && v > 0.0f)) continue;
+    const int cell = (__float2int_rd(vx) + 1) * MGRID + (__float2int_rd(vy) + 1);
+    const int m = __float_as_int(v);
+    if (*reinterpret_cast<volatile int*>(&bvm_s[cell]) < m) atomicMax(&bvm_s[cell], m);
+  }
+  __syncthreads();
+  float* o = bvm + (size_t)f * MGRID * MGRID;
+  for (int i = tid; i < MGRID * MGRID; i += 512) o[i] = __int_as_float(bvm_s[i]);
+}
+
 __global__ void __launch_bounds__(256) k_cloud_manip(int64_t n, Xform xf, const float* __restrict__ x, const float* __restrict__ y,
                                                       const float* __restrict__ z, float* __restrict__ tx, float* __restrict__ ty,
                                                       float* __restrict__ tz, int* __restrict__ bev_in, int* __restrict__ bev_out) {

@@ -8,7 +8,11 @@
 //   (bin / 25 PNG / CSV / PCD), so file encoding is off the GPU critical path.  Frames shard over GPUs by batch index;
 //   label rows are split per GPU and gathered on the host; no collective.
 // Extra trailing options (not in the reference): --gpus N, --batch B, --threads T, --no-encode, --no-pcd,
-//   --png-level L, --json-metrics FILE.
+//   --png-level L, --json-metrics FILE, --no-packed (parse every PCD on the host instead of de-interleaving binary
+//   payloads on the GPU).
+// Compiled a second time with -DBATCH_CLOUD_MANIP as `batch_cloud_manip <keyframes_root_dir>` (BatchCloudManip.cpp:269-331,
+// SURVEY 8(f)-3): same ordering + ground removal with the HDL-64E shape hard-coded there (:12-13, :85), the 201x201 float
+// bird-view map of saveAsMat (:201-239) into output_bvm/<name>.csv/.png, and non_ground_point_cloud/<name>.pcd; no labels.
 #include <dirent.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -62,13 +66,14 @@ struct ThreadPool {
 struct Options {
   std::string root, sensor;
   int gpus = 1, batch = 16, threads = 0, png_level = 1;
-  bool encode = true, write_pcd = true;
+  bool encode = true, write_pcd = true, packed = true;
+  bool bvm_mode = false;     // batch_cloud_manip
   std::string json_metrics;
 };
 
-struct Dirs { std::string pcd_in, non_ground, multi_bin, multi_img, single_csv, single_img, pose_file, label_file; };
+struct Dirs { std::string pcd_in, non_ground, multi_bin, multi_img, single_csv, single_img, pose_file, label_file, bvm; };
 
-static void usage_and_exit(const char* argv0) {   // BatchMultiBevGen.cpp:666-689
+[[maybe_unused]] static void usage_and_exit(const char* argv0) {   // BatchMultiBevGen.cpp:666-689
   std::cout << "Usage: " << argv0 << " [keyframes_root_dir] [sensor_type]\n\n"
             << "[keyframes_root_dir] should be organized as follows: \n"
             << "[keyframes_root_dir]\n"
@@ -143,7 +148,15 @@ struct PinnedSet {     // pinned staging of one batch: SoA inputs + outputs
   size_t cap_pts = 0; int cap_frames = 0; size_t S = 0;
   float *x = 0, *y = 0, *z = 0, *inten = 0; uint16_t *row = 0, *col = 0; int16_t* label = 0;
   int16_t* o_label = 0; uint32_t* o_winner = 0; uint8_t *o_single = 0, *o_multi = 0;
-  bool alloc(size_t pts, int frames, size_t S_) {
+  float* o_bvm = 0;                        // batch_cloud_manip: [frames][201][201] bird-view maps
+  uint8_t* raw = 0; size_t raw_cap = 0;   // interleaved records of a packed batch (de-interleaved on the GPU)
+  bool ensure_raw(size_t bytes) {
+    if (raw_cap >= bytes) return true;
+    bevgen_host_free(raw); raw_cap = bytes + bytes / 4 + 4096; raw = (uint8_t*)bevgen_host_alloc(raw_cap);
+    if (!raw) raw_cap = 0;
+    return raw != nullptr;
+  }
+  bool alloc(size_t pts, int frames, size_t S_, bool with_bvm = false) {
     release(); cap_pts = pts; cap_frames = frames; S = S_;
     auto A = [](size_t n) { return bevgen_host_alloc(n); };
     x = (float*)A(pts * 4); y = (float*)A(pts * 4); z = (float*)A(pts * 4); inten = (float*)A(pts * 4);
@@ -151,11 +164,13 @@ struct PinnedSet {     // pinned staging of one batch: SoA inputs + outputs
     o_label = (int16_t*)A((size_t)frames * S * 2); o_winner = (uint32_t*)A(bevgen_winner_words((int64_t)pts, frames) * 4);
     o_single = (uint8_t*)A((size_t)frames * BEVGEN_GRID_SIZE * BEVGEN_GRID_SIZE);
     o_multi = (uint8_t*)A((size_t)frames * BEVGEN_NUM_LAYERS * BEVGEN_GRID_SIZE * BEVGEN_GRID_SIZE);
-    return x && y && z && inten && row && col && label && o_label && o_winner && o_single && o_multi;
+    if (with_bvm) o_bvm = (float*)A((size_t)frames * BEVGEN_MANIP_GRID * BEVGEN_MANIP_GRID * sizeof(float));
+    return x && y && z && inten && row && col && label && o_label && o_winner && o_single && o_multi && (!with_bvm || o_bvm);
   }
+  void release_all() { release(); bevgen_host_free(raw); raw = 0; raw_cap = 0; }
   void release() {
-    for (void* p : {(void*)x, (void*)y, (void*)z, (void*)inten, (void*)row, (void*)col, (void*)label, (void*)o_label, (void*)o_winner, (void*)o_single, (void*)o_multi}) bevgen_host_free(p);
-    x = y = z = inten = 0; row = col = 0; label = 0; o_label = 0; o_winner = 0; o_single = o_multi = 0;
+    for (void* p : {(void*)x, (void*)y, (void*)z, (void*)inten, (void*)row, (void*)col, (void*)label, (void*)o_label, (void*)o_winner, (void*)o_single, (void*)o_multi, (void*)o_bvm}) bevgen_host_free(p);
+    x = y = z = inten = 0; row = col = 0; label = 0; o_label = 0; o_winner = 0; o_single = o_multi = 0; o_bvm = 0;
   }
 };
 
@@ -163,6 +178,10 @@ struct Batch {
   int first = 0, count = 0;
   std::vector<int64_t> offs;       // point offsets of the batch's frames (winner words are addressed through them)
   std::vector<pcdio::Cloud> clouds;
+  // frames whose file is a binary PCD in the point type's own scalar types keep the file bytes instead of a parsed
+  // cloud: the payload goes to the GPU as it is
+  std::vector<std::vector<uint8_t>> files; std::vector<pcdio::PackedLayout> lays; std::vector<size_t> payload_pos, npts;
+  std::vector<char> is_packed; bool packed = false;
   std::vector<std::string> names;
   std::vector<std::future<void>> loads;
   PinnedSet* pin = nullptr;
@@ -185,7 +204,18 @@ static void encode_frame(Shared& sh, const Batch& b, int k) {
   const std::string& name = b.names[k];
   const uint8_t* multi = p.o_multi + (size_t)k * L * G * G;
   const uint8_t* single = p.o_single + (size_t)k * G * G;
-  if (sh.opt.encode) {
+  if (sh.opt.bvm_mode) {
+    if (sh.opt.encode) {   // saveAsMat, BatchCloudManip.cpp:223-238: FMT_CSV with set32fPrecision(4); imwrite converts CV_32F to 8 bit
+      const int M = BEVGEN_MANIP_GRID;
+      const float* g = p.o_bvm + (size_t)k * M * M;
+      std::string txt = imgio::format_csv_f32(g, M, M, 4);
+      std::string csv = sh.dirs.bvm + name + ".csv";
+      if (!imgio::write_bytes(csv, txt.data(), txt.size())) std::cerr << "Can not open file: " << csv << "\n";
+      std::vector<uint8_t> u8((size_t)M * M);
+      for (int i = 0; i < M * M; i++) u8[i] = imgio::f32_to_u8_sat(g[i]);
+      imgio::write_png_gray8(sh.dirs.bvm + name + ".png", u8.data(), M, M, sh.opt.png_level);
+    }
+  } else if (sh.opt.encode) {
     // .bin: 24 layers concatenated row-major (:294-314)
     std::string bin = sh.dirs.multi_bin + name + ".bin";
     if (!imgio::write_bytes(bin, multi, (size_t)L * G * G)) std::cerr << "Can not open file: " << bin << "\n";
@@ -205,17 +235,28 @@ static void encode_frame(Shared& sh, const Batch& b, int k) {
     // savePCDFileBinary(non_ground/<name>.pcd, cloud_ordered) (:755-756): S slots; slot record = winning input record
     // with its label replaced by the post-ground label, empty slots all-zero.  The library reports one winner bit per
     // input point (the last writer of each (row, col) slot, :102-116); the slot is the point's own row*H + col.
-    const pcdio::Cloud& c = b.clouds[k];
     const uint32_t* win = p.o_winner + (size_t)(b.offs[k] >> 5) + (size_t)k; const int16_t* lab = p.o_label + (size_t)k * S;
     const size_t H = (size_t)sh.params.horizon_scan;
     std::string h = pcdio::header(S);
     std::vector<uint8_t> out(h.size() + S * 26, 0);
     memcpy(out.data(), h.data(), h.size());
     uint8_t* rec = out.data() + h.size();
-    for (size_t i = 0, n = c.size(); i < n; i++) {
-      if (!((win[i >> 5] >> (i & 31)) & 1u)) continue;
-      const size_t s = (size_t)c.row[i] * H + c.col[i];
-      pcdio::pack_record(rec + s * 26, c.x[i], c.y[i], c.z[i], c.intensity[i], c.row[i], c.col[i], c.t[i], lab[s]);
+    if (b.packed) {   // winners straight from the file's own records
+      const uint8_t* pay = b.files[k].data() + b.payload_pos[k]; const pcdio::PackedLayout& L = b.lays[k];
+      for (size_t i = 0, n = b.npts[k]; i < n; i++) {
+        if (!((win[i >> 5] >> (i & 31)) & 1u)) continue;
+        float x, y, z, it; uint16_t r, c; uint32_t t; int16_t l;
+        pcdio::packed_get(pay, L, i, x, y, z, it, r, c, t, l);
+        const size_t s = (size_t)r * H + c;
+        pcdio::pack_record(rec + s * 26, x, y, z, it, r, c, t, lab[s]);
+      }
+    } else {
+      const pcdio::Cloud& c = b.clouds[k];
+      for (size_t i = 0, n = c.size(); i < n; i++) {
+        if (!((win[i >> 5] >> (i & 31)) & 1u)) continue;
+        const size_t s = (size_t)c.row[i] * H + c.col[i];
+        pcdio::pack_record(rec + s * 26, c.x[i], c.y[i], c.z[i], c.intensity[i], c.row[i], c.col[i], c.t[i], lab[s]);
+      }
     }
     if (!pcdio::write_file(sh.dirs.non_ground + name + ".pcd", out)) std::cerr << "Can not open file: " << sh.dirs.non_ground + name + ".pcd" << "\n";
   }
@@ -245,6 +286,8 @@ struct GpuWorker {
     bt->first = b * sh.opt.batch;
     bt->count = std::min<int>(sh.opt.batch, (int)sh.files.size() - bt->first);
     bt->clouds.resize(bt->count); bt->names.resize(bt->count);
+    bt->files.resize(bt->count); bt->lays.resize(bt->count); bt->payload_pos.assign(bt->count, 0); bt->npts.assign(bt->count, 0);
+    bt->is_packed.assign(bt->count, 0);
     for (int k = 0; k < bt->count; k++) {
       auto pr = std::make_shared<std::promise<void>>();
       bt->loads.push_back(pr->get_future());
@@ -253,7 +296,22 @@ struct GpuWorker {
         const std::string& f = s->files[raw->first + k];
         raw->names[k] = short_name_of(f);
         std::string err;
-        if (!pcdio::load(f, raw->clouds[k], &err)) std::cerr << "[pcd] " << err << std::endl;   // reference ignores the status (:730)
+        bool done = false;
+        if (s->opt.packed) {
+          pcdio::Header h;
+          if (pcdio::read_file(f, raw->files[k], &err) && pcdio::parse_header(raw->files[k], h)) {
+            if (pcdio::packed_layout(h, raw->lays[k])) {
+              raw->payload_pos[k] = h.payload_pos;
+              raw->npts[k] = std::min(h.n, (raw->files[k].size() - h.payload_pos) / (size_t)h.rec);
+              raw->is_packed[k] = 1; done = true;
+            } else {
+              done = pcdio::decode(raw->files[k], h, f, raw->clouds[k], &err);
+              raw->files[k].clear(); raw->files[k].shrink_to_fit();
+              if (!done) { std::cerr << "[pcd] " << err << std::endl; done = true; }
+            }
+          }
+        }
+        if (!done && !pcdio::load(f, raw->clouds[k], &err)) std::cerr << "[pcd] " << err << std::endl;   // reference ignores the status (:730)
         pr->set_value();
       });
     }
@@ -266,7 +324,7 @@ struct GpuWorker {
     PinnedSet* p = free_pins.back(); free_pins.pop_back();
     l.unlock();
     if (p->cap_pts < pts || p->cap_frames < sh.opt.batch) {
-      if (!p->alloc(pts + pts / 4 + 1024, sh.opt.batch, sh.S)) { std::cerr << "pinned allocation failed" << std::endl; sh.failed = true; }
+      if (!p->alloc(pts + pts / 4 + 1024, sh.opt.batch, sh.S, sh.opt.bvm_mode)) { std::cerr << "pinned allocation failed" << std::endl; sh.failed = true; }
     }
     return p;
   }
@@ -280,25 +338,48 @@ struct GpuWorker {
       std::shared_ptr<Batch> cur = next;
       next = grab();                                   // its PCD parsing overlaps this batch's GPU work
       for (auto& f : cur->loads) f.get();
+      // the batch goes through the packed path iff every frame is an interleaved payload of one and the same layout
+      cur->packed = sh.opt.packed && cur->count > 0;
+      for (int k = 0; k < cur->count && cur->packed; k++) cur->packed = cur->is_packed[k] && cur->lays[k] == cur->lays[0];
+      if (!cur->packed)
+        for (int k = 0; k < cur->count; k++)
+          if (cur->is_packed[k]) {   // mixed batch: parse this frame on the host after all
+            pcdio::Header h; std::string err;
+            if (!pcdio::parse_header(cur->files[k], h) || !pcdio::decode(cur->files[k], h, sh.files[cur->first + k], cur->clouds[k], &err)) std::cerr << "[pcd] " << err << std::endl;
+            cur->is_packed[k] = 0; cur->files[k].clear(); cur->files[k].shrink_to_fit();
+          }
+      auto frame_n = [&](int k) { return cur->packed ? cur->npts[k] : cur->clouds[k].size(); };
       std::vector<int64_t> offs(cur->count + 1, 0);
       int max_n = 0;
-      for (int k = 0; k < cur->count; k++) { offs[k + 1] = offs[k] + (int64_t)cur->clouds[k].size(); max_n = std::max<int>(max_n, (int)cur->clouds[k].size()); }
+      for (int k = 0; k < cur->count; k++) { offs[k + 1] = offs[k] + (int64_t)frame_n(k); max_n = std::max<int>(max_n, (int)frame_n(k)); }
       if (!ensure_ctx(max_n)) { sh.failed = true; break; }
       PinnedSet* p = take_pin((size_t)offs[cur->count]);
       if (sh.failed) break;
       cur->pin = p;
-      for (int k = 0; k < cur->count; k++) {           // SoA staging into pinned memory
-        const pcdio::Cloud& c = cur->clouds[k]; size_t o = (size_t)offs[k], n = c.size();
-        if (!n) continue;
-        memcpy(p->x + o, c.x.data(), n * 4); memcpy(p->y + o, c.y.data(), n * 4); memcpy(p->z + o, c.z.data(), n * 4);
-        memcpy(p->inten + o, c.intensity.data(), n * 4); memcpy(p->row + o, c.row.data(), n * 2); memcpy(p->col + o, c.col.data(), n * 2);
-        memcpy(p->label + o, c.label.data(), n * 2);
-      }
       { std::lock_guard<std::mutex> l(sh.print_mu); for (int k = 0; k < cur->count; k++) std::cout << "Converting file: " << cur->names[k] << "\n"; }   // :744
-      bevgen_points in{p->x, p->y, p->z, p->inten, p->row, p->col, p->label};
-      bevgen_outputs out{p->o_label, p->o_winner, p->o_single, p->o_multi};
+      bevgen_outputs out{p->o_label, p->o_winner, p->o_single, p->o_multi, sh.opt.bvm_mode ? p->o_bvm : nullptr};
       cur->offs = offs;
-      if (bevgen_process_host(ctx, cur->count, offs.data(), &in, &out) != 0) {
+      int rc;
+      if (cur->packed) {
+        const size_t stride = (size_t)cur->lays[0].stride;
+        if (!p->ensure_raw((size_t)offs[cur->count] * stride + 64)) { std::cerr << "pinned allocation failed" << std::endl; sh.failed = true; give_pin(p); break; }
+        for (int k = 0; k < cur->count; k++)           // staging = one copy of the file payload into pinned memory
+          if (cur->npts[k]) memcpy(p->raw + (size_t)offs[k] * stride, cur->files[k].data() + cur->payload_pos[k], cur->npts[k] * stride);
+        const int* o = cur->lays[0].off;
+        bevgen_record_layout lay{cur->lays[0].stride, o[0], o[1], o[2], o[3], o[4], o[5], o[7]};
+        rc = bevgen_process_packed_host(ctx, cur->count, offs.data(), p->raw, &lay, &out);
+      } else {
+        for (int k = 0; k < cur->count; k++) {           // SoA staging into pinned memory
+          const pcdio::Cloud& c = cur->clouds[k]; size_t o = (size_t)offs[k], n = c.size();
+          if (!n) continue;
+          memcpy(p->x + o, c.x.data(), n * 4); memcpy(p->y + o, c.y.data(), n * 4); memcpy(p->z + o, c.z.data(), n * 4);
+          memcpy(p->inten + o, c.intensity.data(), n * 4); memcpy(p->row + o, c.row.data(), n * 2); memcpy(p->col + o, c.col.data(), n * 2);
+          memcpy(p->label + o, c.label.data(), n * 2);
+        }
+        bevgen_points in{p->x, p->y, p->z, p->inten, p->row, p->col, p->label};
+        rc = bevgen_process_host(ctx, cur->count, offs.data(), &in, &out);
+      }
+      if (rc != 0) {
         std::cerr << "bevgen_process_host: " << bevgen_last_error() << std::endl; sh.failed = true; give_pin(p); break;
       }
       cur->pending_encodes = cur->count;
@@ -314,11 +395,20 @@ struct GpuWorker {
 };
 
 int main(int argc, char** argv) {
+#ifdef BATCH_CLOUD_MANIP
+  if (argc < 2 || argv[1] == nullptr) { std::cout << "Usage: " << argv[0] << " <keyframes_root_dir>" << std::endl; exit(1); }   // BatchCloudManip.cpp:271-274
+  Shared sh;
+  Options& opt = sh.opt;
+  opt.root = argv[1]; opt.sensor = "HDL_64E"; opt.bvm_mode = true;   // N_SCAN 64, Horizon_SCAN 2083, groundScanInd 50 (:12-13, :85)
+  const int first_opt = 2;
+#else
   if (argc < 3 || argv[1] == nullptr || argv[2] == nullptr) usage_and_exit(argv[0]);
   Shared sh;
   Options& opt = sh.opt;
   opt.root = argv[1]; opt.sensor = argv[2];
-  for (int i = 3; i < argc; i++) {
+  const int first_opt = 3;
+#endif
+  for (int i = first_opt; i < argc; i++) {
     std::string a = argv[i];
     auto val = [&](const char* name) -> const char* { if (i + 1 >= argc) { std::cerr << name << " needs a value\n"; exit(1); } return argv[++i]; };
     if (a == "--gpus") opt.gpus = atoi(val("--gpus"));
@@ -327,6 +417,7 @@ int main(int argc, char** argv) {
     else if (a == "--png-level") opt.png_level = atoi(val("--png-level"));
     else if (a == "--no-encode") opt.encode = false;
     else if (a == "--no-pcd") opt.write_pcd = false;
+    else if (a == "--no-packed") opt.packed = false;
     else if (a == "--json-metrics") opt.json_metrics = val("--json-metrics");
     else { std::cerr << "unknown option " << a << "\n"; exit(1); }
   }
@@ -341,10 +432,14 @@ int main(int argc, char** argv) {
   d.multi_bin = root + "output_multi_bev/binary/"; d.multi_img = root + "output_multi_bev/image/";
   d.single_csv = root + "output_single_bev/csv/"; d.single_img = root + "output_single_bev/image/";
 
+  d.bvm = root + "output_bvm/";
   reset_dir(d.non_ground);                                                    // :704-705
   sh.files = list_pcd(d.pcd_in);                                              // :708-709
-  reset_dir(root + "output_multi_bev/"); reset_dir(d.multi_bin); reset_dir(d.multi_img);   // initDirectories :39-71
-  reset_dir(d.single_csv); reset_dir(d.single_img);
+  if (opt.bvm_mode) reset_dir(d.bvm);                                         // BatchCloudManip.cpp:291-295
+  else {
+    reset_dir(root + "output_multi_bev/"); reset_dir(d.multi_bin); reset_dir(d.multi_img);   // initDirectories :39-71
+    reset_dir(d.single_csv); reset_dir(d.single_img);
+  }
 
   if (bevgen_sensor_params(opt.sensor.c_str(), &sh.params) < 0) {             // :718-719
     std::cerr << "Unknown sensor type: " << opt.sensor << "!" << std::endl;
@@ -352,8 +447,9 @@ int main(int argc, char** argv) {
     return 1;   // the reference would go on with uninitialised SensorParams (undefined behaviour); we stop
   }
   sh.S = (size_t)sh.params.n_scan * sh.params.horizon_scan;
-  std::cout << "Using sensor_type " << opt.sensor << ", with params: N_SCAN: " << sh.params.n_scan << ", Horizon_SCAN: "
-            << sh.params.horizon_scan << ", GROUND_UPPER_SCAN: " << sh.params.ground_upper_scan << "\n";   // :720-722
+  if (!opt.bvm_mode)
+    std::cout << "Using sensor_type " << opt.sensor << ", with params: N_SCAN: " << sh.params.n_scan << ", Horizon_SCAN: "
+              << sh.params.horizon_scan << ", GROUND_UPPER_SCAN: " << sh.params.ground_upper_scan << "\n";   // :720-722
 
   ThreadPool pool(opt.threads);
   sh.pool = &pool;
@@ -376,6 +472,15 @@ int main(int argc, char** argv) {
   // the reference averages its per-frame serial span (:749-759); here frames overlap, so this is wall time / frames
   std::cout << "[TIME] Average preprocessing and BEV generation: " << (sh.files.empty() ? 0.0 : total_ms / sh.files.size()) << "\n";
 
+  if (opt.bvm_mode) {   // batch_cloud_manip has no label stage (BatchCloudManip.cpp:327-330)
+    if (!opt.json_metrics.empty()) {
+      std::ofstream j(opt.json_metrics);
+      j << "{\"frames\": " << sh.files.size() << ", \"gpus\": " << workers.size() << ", \"frames_wall_ms\": " << total_ms << "}\n";
+    }
+    for (auto& wk : workers) { if (wk->ctx) bevgen_destroy(wk->ctx); for (auto& p : wk->pins) p.release_all(); }
+    std::cout << "Done. " << std::endl;
+    return 0;
+  }
   // Step 2: labels (:761-765)
   auto t1 = Clock::now();
   std::vector<float> xyz = read_poses(d.pose_file);
@@ -435,7 +540,7 @@ int main(int argc, char** argv) {
       << ", \"frames_wall_ms\": " << total_ms << ", \"frames_per_s\": " << (total_ms > 0 ? sh.files.size() / (total_ms * 1e-3) : 0.0)
       << ", \"keyframes\": " << K << ", \"majors\": " << M << ", \"labels_wall_ms\": " << label_ms << "}\n";
   }
-  for (auto& wk : workers) { if (wk->ctx) bevgen_destroy(wk->ctx); for (auto& p : wk->pins) p.release(); }
+  for (auto& wk : workers) { if (wk->ctx) bevgen_destroy(wk->ctx); for (auto& p : wk->pins) p.release_all(); }
   std::cout << "Done. " << std::endl;
   return 0;
 }

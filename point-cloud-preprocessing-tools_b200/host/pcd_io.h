@@ -79,22 +79,27 @@ inline int which_field(const std::string& n) {
   return -1;
 }
 
-// Returns false (and sets err) if the file cannot be read; the reference ignores loadPCDFile's status and carries
-// on with an empty cloud (BatchMultiBevGen.cpp:730), which callers reproduce by using the empty `c`.
-inline bool load(const std::string& path, Cloud& c, std::string* err = nullptr) {
-  c.resize(0);
+// Parsed PCD header: fields with their byte offsets inside a record, point count, DATA kind, payload position.
+struct Header {
+  std::vector<Field> fields;
+  size_t n = 0; int rec = 0; std::string data_kind; size_t payload_pos = 0;
+};
+
+inline bool read_file(const std::string& path, std::vector<uint8_t>& buf, std::string* err = nullptr) {
   FILE* fp = fopen(path.c_str(), "rb");
   if (!fp) { if (err) *err = "cannot open " + path; return false; }
-  std::vector<uint8_t> buf;
   fseek(fp, 0, SEEK_END); long sz = ftell(fp); fseek(fp, 0, SEEK_SET);
   if (sz < 0) { fclose(fp); if (err) *err = "cannot stat " + path; return false; }
   buf.resize((size_t)sz);
   if (sz && fread(buf.data(), 1, (size_t)sz, fp) != (size_t)sz) { fclose(fp); if (err) *err = "short read " + path; return false; }
   fclose(fp);
+  return true;
+}
 
-  std::vector<Field> fields;
+inline bool parse_header(const std::vector<uint8_t>& buf, Header& h) {
+  h = Header();
+  std::vector<Field>& fields = h.fields;
   size_t pos = 0, width = 0, height = 0, points = 0; bool have_points = false;
-  std::string data_kind;
   while (pos < buf.size()) {
     size_t e = pos; while (e < buf.size() && buf[e] != '\n') e++;
     std::string line((const char*)&buf[pos], e - pos); pos = e + 1;
@@ -108,11 +113,62 @@ inline bool load(const std::string& path, Cloud& c, std::string* err = nullptr) 
     else if (key == "WIDTH") ss >> width;
     else if (key == "HEIGHT") ss >> height;
     else if (key == "POINTS") { ss >> points; have_points = true; }
-    else if (key == "DATA") { ss >> data_kind; break; }
+    else if (key == "DATA") { ss >> h.data_kind; break; }
   }
-  if (fields.empty() || data_kind.empty()) { if (err) *err = "bad PCD header in " + path; return false; }
-  size_t n = have_points ? points : width * height;
+  if (fields.empty() || h.data_kind.empty()) return false;
+  h.n = have_points ? points : width * height;
   int rec = 0; for (auto& f : fields) { f.offset = rec; rec += f.size * f.count; }
+  h.rec = rec; h.payload_pos = pos;
+  return true;
+}
+
+// Interleaved-record view of a DATA binary payload for the GPU de-interleave (bevgen_process_packed_host): possible
+// when every PointXYZIRCT field that is present has the point type's own scalar type (BatchMultiBevGen.h:56-66), so
+// no value conversion is needed; any field order / extra fields / padding.  off: x y z intensity row col t label.
+struct PackedLayout {
+  int stride = 0; int off[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+  bool operator==(const PackedLayout& o) const { return stride == o.stride && !memcmp(off, o.off, sizeof off); }
+};
+inline bool packed_layout(const Header& h, PackedLayout& L) {
+  static const int cs[8] = {4, 4, 4, 4, 2, 2, 4, 2}; static const char ct[8] = {'F', 'F', 'F', 'F', 'U', 'U', 'U', 'I'};
+  L = PackedLayout();
+  if (h.data_kind != "binary" || h.rec < 1 || h.rec > 256) return false;
+  L.stride = h.rec;
+  for (auto& f : h.fields) {
+    int w = which_field(f.name);
+    if (w < 0) continue;
+    if (f.size != cs[w] || f.type != ct[w] || f.count != 1 || L.off[w] >= 0) return false;
+    L.off[w] = f.offset;
+  }
+  return true;
+}
+// Field values of record i of an interleaved payload (absent fields read as 0).
+inline void packed_get(const uint8_t* payload, const PackedLayout& L, size_t i, float& x, float& y, float& z, float& inten,
+                       uint16_t& row, uint16_t& col, uint32_t& t, int16_t& label) {
+  const uint8_t* p = payload + i * (size_t)L.stride;
+  x = L.off[0] >= 0 ? rd<float>(p + L.off[0]) : 0.f; y = L.off[1] >= 0 ? rd<float>(p + L.off[1]) : 0.f;
+  z = L.off[2] >= 0 ? rd<float>(p + L.off[2]) : 0.f; inten = L.off[3] >= 0 ? rd<float>(p + L.off[3]) : 0.f;
+  row = L.off[4] >= 0 ? rd<uint16_t>(p + L.off[4]) : (uint16_t)0; col = L.off[5] >= 0 ? rd<uint16_t>(p + L.off[5]) : (uint16_t)0;
+  t = L.off[6] >= 0 ? rd<uint32_t>(p + L.off[6]) : 0u; label = L.off[7] >= 0 ? rd<int16_t>(p + L.off[7]) : (int16_t)0;
+}
+
+inline bool decode(const std::vector<uint8_t>& buf, const Header& h, const std::string& path, Cloud& c, std::string* err = nullptr);
+
+// Returns false (and sets err) if the file cannot be read; the reference ignores loadPCDFile's status and carries
+// on with an empty cloud (BatchMultiBevGen.cpp:730), which callers reproduce by using the empty `c`.
+inline bool load(const std::string& path, Cloud& c, std::string* err = nullptr) {
+  c.resize(0);
+  std::vector<uint8_t> buf;
+  if (!read_file(path, buf, err)) return false;
+  Header h;
+  if (!parse_header(buf, h)) { if (err) *err = "bad PCD header in " + path; return false; }
+  return decode(buf, h, path, c, err);
+}
+
+inline bool decode(const std::vector<uint8_t>& buf, const Header& h, const std::string& path, Cloud& c, std::string* err) {
+  const std::vector<Field>& fields = h.fields;
+  const std::string& data_kind = h.data_kind;
+  size_t n = h.n; const int rec = h.rec; const size_t pos = h.payload_pos;
   c.resize(n);   // value-initialised: missing fields stay zero
 
   if (data_kind == "ascii") {

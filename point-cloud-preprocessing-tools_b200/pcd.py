@@ -49,3 +49,22 @@ def write_ascii(path, f, fields=("x", "y", "z", "intensity", "row", "col", "t", 
                                                                       " ".join(typ[k] for k in fields), " ".join("1" for _ in fields), n, n))
         for i in range(n):
             fp.write(" ".join(repr(float(f[k][i])) if typ[k] == "F" else str(int(f[k][i])) for k in fields) + "\n")
+
+
+def write_binary_layout(path, f, fields=("label", "x", "_", "y", "z", "col", "row", "intensity", "t")):
+    """Binary PCD with an arbitrary field order; "_" is a 3-byte padding field (SIZE 1 TYPE U COUNT 3) as PCL writes
+    for alignment holes.  Exercises the by-name field mapping and the interleaved-record layout with odd offsets."""
+    n = len(f["x"])
+    base = {k: DTYPE.fields[k][0] for k in DTYPE.names}
+    dt = np.dtype([((k if k != "_" else "pad%d" % i), (base[k] if k != "_" else "V3")) for i, k in enumerate(fields)])
+    rec = np.zeros(n, dt)
+    for i, k in enumerate(fields):
+        if k != "_":
+            rec[k] = f[k]
+    size = [str(base[k].itemsize) if k != "_" else "1" for k in fields]
+    typ = [{"f": "F", "u": "U", "i": "I"}[base[k].kind] if k != "_" else "U" for k in fields]
+    cnt = ["1" if k != "_" else "3" for k in fields]
+    with open(path, "wb") as fp:
+        fp.write(("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS %s\nSIZE %s\nTYPE %s\nCOUNT %s\nWIDTH %d\nHEIGHT 1\n"
+                  "VIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary\n" % (" ".join(fields), " ".join(size), " ".join(typ), " ".join(cnt), n, n)).encode())
+        fp.write(rec.tobytes())

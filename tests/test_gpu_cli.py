@@ -11,7 +11,7 @@ from conftest import FIELDS, oracle_batch, cat_frames
 pytestmark = pytest.mark.gpu
 
 
-def make_folder(tmp, synth, pcd, sensor, n, ascii_idx=()):
+def make_folder(tmp, synth, pcd, sensor, n, ascii_idx=(), layout_all=False):
     root = os.path.join(tmp, "kf")
     os.makedirs(os.path.join(root, "keyframe_point_cloud"))
     frames = []
@@ -19,7 +19,9 @@ def make_folder(tmp, synth, pcd, sensor, n, ascii_idx=()):
         f = synth.make_frame(sensor, 300 + i)
         frames.append(f)
         p = os.path.join(root, "keyframe_point_cloud", "%06d.pcd" % i)
-        if i in ascii_idx:
+        if layout_all:
+            pcd.write_binary_layout(p, f)          # every file: reordered fields + a 3-byte "_" hole (29-byte records, odd offsets)
+        elif i in ascii_idx:
             pcd.write_ascii(p, f, fields=("label", "x", "y", "z", "col", "row", "intensity", "t"))   # shuffled field order
         else:
             pcd.write(p, f)
@@ -37,13 +39,18 @@ def parse_pose_xyz(root):
     return np.array([[np.float32(float(r[1])), np.float32(float(r[2])), np.float32(float(r[3]))] for r in rows], np.float32)
 
 
-@pytest.mark.parametrize("sensor,n,extra", [("HDL_32E", 7, ["--batch", "3"]), ("OS1_64", 4, ["--gpus", "1", "--batch", "16", "--threads", "3"])])
+# HDL_32E/7: batch 0 mixes an ascii file in (host parse), batches 1-2 go through the GPU de-interleave (packed records);
+# OS1_64/4: one mixed batch; "--no-packed": host parse only; "layout": non-canonical binary records through the packed path.
+@pytest.mark.parametrize("sensor,n,extra", [("HDL_32E", 7, ["--batch", "3"]), ("OS1_64", 4, ["--gpus", "1", "--batch", "16", "--threads", "3"]),
+                                            ("HDL_32E", 3, ["--batch", "2", "--no-packed"]), ("HDL_32E", 4, ["--batch", "3", "layout"])])
 def test_cli_folder_contract(tmp_path, pkg, synth, O, sensor, n, extra):
     import importlib
     pcd = importlib.import_module("pcpt_b200.pcd")
     cv2 = pytest.importorskip("cv2")
     assert os.path.exists(pkg.CLI_PATH), "CLI not built"
-    root, frames = make_folder(str(tmp_path), synth, pcd, sensor, n, ascii_idx=(1,))
+    layout_all = "layout" in extra
+    extra = [e for e in extra if e != "layout"]
+    root, frames = make_folder(str(tmp_path), synth, pcd, sensor, n, ascii_idx=(1,), layout_all=layout_all)
     r = subprocess.run([pkg.CLI_PATH, root, sensor] + extra, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     out = r.stdout
@@ -135,3 +142,37 @@ def test_cloud_manip_cli(tmp_path, pkg, O):
         np.testing.assert_allclose(got, m, rtol=6e-4)                                    # "%.4g"
         png = cv2.imread(str(tmp_path / ("cloud.pcd_%s.csv.png" % tag)), cv2.IMREAD_UNCHANGED)
         assert np.array_equal(png, np.clip(np.rint(m), 0, 255).astype(np.uint8))
+
+
+def test_batch_cloud_manip_cli(tmp_path, pkg, synth, O):
+    """`batch_cloud_manip <keyframes_root_dir>` (BatchCloudManip.cpp:269-331): HDL-64E shape hard-coded,
+    output_bvm/<name>.csv (FMT_CSV, %.4g) + .png (CV_32F -> 8 bit), non_ground_point_cloud/<name>.pcd, no labels."""
+    import importlib
+    pcd = importlib.import_module("pcpt_b200.pcd")
+    cv2 = pytest.importorskip("cv2")
+    r = subprocess.run([pkg.BATCH_CLOUD_MANIP_PATH], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("Usage: ") and "<keyframes_root_dir>" in r.stdout
+    sensor, n = "HDL_64E", 3
+    root, frames = make_folder(str(tmp_path), synth, pcd, sensor, n)
+    r = subprocess.run([pkg.BATCH_CLOUD_MANIP_PATH, root, "--batch", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.rstrip().endswith("Done.") and "[TIME] Average preprocessing and BEV generation: " in r.stdout
+    assert not os.path.exists(os.path.join(root, "keyframe_label.csv")) and not os.path.isdir(os.path.join(root, "output_single_bev"))
+    sp = O.sensor(sensor)
+    for i in range(n):
+        name = "%06d" % i
+        assert "Converting file: %s\n" % name in r.stdout
+        f = frames[i]
+        oc = O.order(sp, *[f[k] for k in FIELDS])
+        lab = O.mark_ground(sp, oc)[0]
+        m = O.bvm(oc, lab)
+        rows = open(os.path.join(root, "output_bvm", name + ".csv")).read().splitlines()
+        got = np.array([[float(v) for v in row.split(", ")] for row in rows])
+        assert got.shape == (201, 201)
+        want_txt = "\n".join(", ".join("%.4g" % v for v in row) for row in m) + "\n"
+        assert open(os.path.join(root, "output_bvm", name + ".csv")).read() == want_txt
+        png = cv2.imread(os.path.join(root, "output_bvm", name + ".png"), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(png, np.clip(np.rint(m), 0, 255).astype(np.uint8))
+        got_pcd, hdr = pcd.read(os.path.join(root, "non_ground_point_cloud", name + ".pcd"))
+        assert hdr.encode() == pcd.header(sp.S) and np.array_equal(got_pcd["label"], lab)
+        assert np.array_equal(got_pcd["z"], oc["z"]) and np.array_equal(got_pcd["x"], oc["x"])

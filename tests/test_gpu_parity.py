@@ -348,4 +348,24 @@ def test_packed_records_deinterleave_on_gpu(gens, synth, O, pkg, kind):
                                          g.params.horizon_scan, g.S)
     assert_same(out, ref, "packed " + kind)
     with pytest.raises(pkg.BevgenError, match="offset outside"):
-        g.process_packed_host(rec, batch["offsets"], pkg.RecordLayout(26, 24, 4, 8, 12, 16, 18, 24))
+        g.process_packed_host(rec, batch["offsets"], pkg.RecordLayout(lay.stride, lay.stride - 2, 4, 8, -1, 12, 14, -1))   # x (f32) overruns the record
+
+
+def test_bird_view_map_of_batch_cloud_manip(gens, synth, O):
+    """the optional `bvm` output = saveAsMat of BatchCloudManip.cpp:201-226 on the ground-removed ordered
+    cloud (f32 max of z + 2 per 1 m cell, label == 0 skipped); bit-exact against the oracle, SoA and device chunking."""
+    sensor = "HDL_64E"                                      # batch_cloud_manip hard-codes the HDL-64E shape (:12-13)
+    batch = synth.make_batch(sensor, 5, first=20)
+    sp = O.sensor(sensor)
+    g = gens(sensor, max_frames_per_batch=2)
+    offs = batch["offsets"]
+    out = g.process_host(batch, out=g.alloc_outputs(5, n_total=int(offs[-1]), bvm=True))
+    for f in range(5):
+        fr = [batch[k][offs[f]:offs[f + 1]] for k in FIELDS]
+        oc = O.order(sp, *fr)
+        lab = O.mark_ground(sp, oc)[0]
+        want = O.bvm(oc, lab)
+        assert np.array_equal(out["label"][f], lab)
+        got = out["bvm"][f]
+        assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (f, int((got != want).sum()))
+        assert want.max() > 0 and (want > 0).sum() > 500   # the map is not trivially empty

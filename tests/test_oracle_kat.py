@@ -275,3 +275,19 @@ def test_transform_and_save_as_mat(O):
     assert tx[0] == want and ty[0] == 3.0 and tz[0] == 7.0
     m = O.save_as_mat(np.array([0, 0, -100.5, 99.99, 100.0], f32), np.array([0, 0, 0, 0, 0], f32), np.array([-2, 1, 5, 5, 5], f32))
     assert m[101, 101] == 3.0 and m[0, 101] == 7.0 and m[200, 101] == 7.0 and (m > 0).sum() == 3
+
+
+def test_bvm_label_filter_and_strict_max(O):
+    """BatchCloudManip.cpp:201-226: label == 0 skipped (:214), cell starts at 0 and takes z + 2 only if strictly greater,
+    x = round(px + 100 + 0.5) in [0, 201)."""
+    x = np.array([0.2, 0.2, 0.2, -100.9, 99.99, 100.0, 5.0], np.float32)
+    y = np.array([0.7, 0.7, 0.7, -100.9, 99.99, 0.0, 5.0], np.float32)
+    z = np.array([1.0, 3.0, 9.0, 0.5, 0.25, 1.0, -2.5], np.float32)
+    lab = np.array([-2, 7, 0, 1, 1, 1, 1], np.int16)       # the 9.0 point is ground (label 0) and must not count
+    m = O.bvm(dict(x=x, y=y, z=z), lab)
+    assert m.shape == (201, 201)
+    assert m[101, 101] == np.float32(5.0)                   # max(1+2, 3+2); x = floor(100.2)+1 = 101
+    assert m[0, 0] == np.float32(2.5)                       # v = -0.9 -> round(-0.4) = -0 -> cell 0
+    assert m[200, 200] == np.float32(2.25)                  # v = 199.99 -> 200
+    assert m[105 + 1 - 0, 105 + 1 - 0] == 0                 # z + 2 = -0.5 is not > 0: never stored
+    assert (m > 0).sum() == 3                               # px = 100.0 -> x = 201: out of range
