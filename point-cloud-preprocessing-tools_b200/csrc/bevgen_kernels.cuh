@@ -533,9 +533,13 @@ __global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4*
     const float4 direct = nxt;
     if (r >= 2) nxt = pr[-2 * H];                                 // next iteration's upper: in flight during this row's math
     float4 up = direct;
-    if (is_neg1(up)) up = pr[-H + dplus];                         // :146-149
-    if (is_neg1(up)) up = pr[-H + dminus];                        // :151-154
-    if (is_neg1(up) && r >= 2) up = pr[-2 * H];                   // :157-160
+    if (is_neg1(up)) {                                            // -1 markers are rare: one branch on the common path
+      up = pr[-H + dplus];                                        // :146-149
+      if (is_neg1(up)) {
+        up = pr[-H + dminus];                                     // :151-154
+        if (is_neg1(up) && r >= 2) up = pr[-2 * H];               // :157-160
+      }
+    }
     const bool invalid = is_neg1(lower) || is_neg1(up);           // :162
     const bool ground = !invalid && ground_decision(sp, up, lower);
     emit(lower, !invalid && (ground || ground_prev));

@@ -368,4 +368,4 @@ def test_bird_view_map_of_batch_cloud_manip(gens, synth, O):
         assert np.array_equal(out["label"][f], lab)
         got = out["bvm"][f]
         assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (f, int((got != want).sum()))
-        assert want.max() > 0 and (want > 0).sum() > 500   # the map is not trivially empty
+        assert want.max() > 0 and (want > 0).sum() > 200   # the map is not trivially empty
