@@ -154,6 +154,18 @@ BEVGEN_API int bevgen_labels(bevgen_ctx *ctx, int K, const float *xyz, int M, co
 BEVGEN_API int bevgen_cloud_manip(bevgen_ctx *ctx, int64_t n, const float *rt, const float *x, const float *y, const float *z,
                        float *tx, float *ty, float *tz, float *bev_in, float *bev_out);
 
+/* SURVEY 8(f)-2 — the per-point projection of the keyframe extractors, i.e. the producer of the `row` / `col` fields:
+ *   BEVGEN_PROJECT_MULRAN_OS1_64  (MulranPointCloudSelect.cpp:112-126): row = k % 64, col = round(azimuth / 360 * 1024)
+ *                                 (col may come out equal to 1024; getOrderedCloud drops such points, :106-109)
+ *   BEVGEN_PROJECT_OXFORD_HDL_32E (OxfordPointCloudSelect.cpp:201-219): x and z are NEGATED IN PLACE (sensor mounted
+ *                                 upside-down), row from the elevation angle clamped to 0..31, col wrapped at 1056.
+ * Host arrays of n points in file order; z may be NULL for MULRAN.  KittiPointCloudSelect's ring detection
+ * (KittiPointCloudSelect.cpp:188-243) is a sequential state machine over the scan and is not covered. */
+#define BEVGEN_PROJECT_MULRAN_OS1_64 0
+#define BEVGEN_PROJECT_OXFORD_HDL_32E 1
+BEVGEN_API int bevgen_project(bevgen_ctx *ctx, int kind, int64_t n, float *x, const float *y, float *z, uint16_t *row,
+                   uint16_t *col);
+
 /* ---- introspection for bench / tests (no reference counterpart) ---------------------------------------------- */
 #define BEVGEN_N_STAGES 8
 /* Stage order: 0 clear, 1 order (claim), 2 order_fill (large range images only), 3 ground_mark, 4 sector_mean,

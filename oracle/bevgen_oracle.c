@@ -434,6 +434,45 @@ ORACLE_API void oracle_bvm(int64_t n, const float *x, const float *y, const floa
   }
 }
 
+/* Projection step of the keyframe extractors.  atan2 / sqrt / round are called unqualified on float
+ * arguments; as for the ground criterion (8a.1-G3) the float overloads are normative (-DORACLE_DOUBLE_LIBM: double). */
+#ifdef ORACLE_DOUBLE_LIBM
+#define P_ATAN2(a, b) atan2((double)(a), (double)(b))
+#define P_SQRT(a) sqrt((double)(a))
+#else
+#define P_ATAN2(a, b) ((double)atan2f((a), (b)))
+#define P_SQRT(a) sqrtf(a)
+#endif
+static uint16_t u16_cast(float v) { return (uint16_t)(x86_cvtt((double)v) & 0xFFFF); }   /* cvttss2si + truncation */
+
+/* MulranPointCloudSelect.cpp:112-126 */
+ORACLE_API void oracle_project_mulran(int64_t n, const float *x, const float *y, uint16_t *row, uint16_t *col) {
+  for (int64_t k = 0; k < n; k++) {
+    row[k] = (uint16_t)(k % 64);                                                    /* :120 */
+    float azimuthal_angle = (float)(P_ATAN2(y[k], x[k]) / M_PI * 180.0f);           /* :121 */
+    if (azimuthal_angle > 360.0f) azimuthal_angle = azimuthal_angle - 360.0f;       /* :122 */
+    else if (azimuthal_angle < 0.0f) azimuthal_angle = azimuthal_angle + 360.0f;    /* :123 */
+    col[k] = u16_cast(roundf(azimuthal_angle / 360.0f * 1024));                     /* :125 */
+  }
+}
+
+/* OxfordPointCloudSelect.cpp:201-219; x and z are negated in place. */
+ORACLE_API void oracle_project_oxford(int64_t n, float *x, const float *y, float *z, uint16_t *row, uint16_t *col) {
+  for (int64_t k = 0; k < n; k++) {
+    x[k] = -x[k]; z[k] = -z[k];                                                     /* :203-204 */
+    float elevation_angle = (float)((double)P_ATAN2(z[k], P_SQRT(x[k] * x[k] + y[k] * y[k])) / M_PI * 180.0f);   /* :208 */
+    int row_idx = x86_cvtt(round((-elevation_angle + 10.67) / 1.3335));             /* :209 */
+    row_idx = row_idx > 0 ? row_idx : 0; row_idx = row_idx < 31 ? row_idx : 31;     /* :210 */
+    row[k] = (uint16_t)row_idx;
+    float azimuthal_angle = (float)(P_ATAN2(y[k], x[k]) / M_PI * 180.0f);           /* :213 */
+    if (azimuthal_angle > 360.0f) azimuthal_angle = azimuthal_angle - 360.0f;
+    else if (azimuthal_angle < 0.0f) azimuthal_angle = azimuthal_angle + 360.0f;
+    uint16_t c = u16_cast(roundf(azimuthal_angle / 360.0f * 1056));                 /* :216 */
+    if (c >= 1056) c -= 1056;                                                       /* :217 (:218 is dead code for an unsigned) */
+    col[k] = c;
+  }
+}
+
 /* Exposed for tests: the float libm the oracle was built against. */
 ORACLE_API float oracle_atan2f(float y, float x) { return atan2f(y, x); }
 ORACLE_API float oracle_angle_deg(float dz, float dx, float dy) {

@@ -182,6 +182,22 @@ def bvm(oc, label):
     return m.reshape(201, 201)
 
 
+def project_mulran(x, y):
+    """MulranPointCloudSelect.cpp:112-126 -> (row, col)."""
+    x, px = _f(x); y, py = _f(y)
+    row = np.empty(len(x), np.uint16); col = np.empty(len(x), np.uint16)
+    lib().oracle_project_mulran(C.c_int64(len(x)), px, py, _p(row, C.c_uint16), _p(col, C.c_uint16))
+    return row, col
+
+
+def project_oxford(x, y, z):
+    """OxfordPointCloudSelect.cpp:201-219 -> (x_negated, z_negated, row, col)."""
+    x = np.array(x, np.float32); z = np.array(z, np.float32); y, py = _f(y)
+    row = np.empty(len(x), np.uint16); col = np.empty(len(x), np.uint16)
+    lib().oracle_project_oxford(C.c_int64(len(x)), _p(x, C.c_float), py, _p(z, C.c_float), _p(row, C.c_uint16), _p(col, C.c_uint16))
+    return x, z, row, col
+
+
 # ---- reference KD-tree (oracle/_ref) ---------------------------------------------------------------
 def ref_knn_many(pts, qs, k):
     r = ref_lib()

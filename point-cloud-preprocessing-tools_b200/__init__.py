@@ -87,7 +87,7 @@ EXPORTS = ["bevgen_sensor_params", "bevgen_create", "bevgen_destroy", "bevgen_la
            "bevgen_host_free", "bevgen_process_host", "bevgen_process_device", "bevgen_sync", "bevgen_submit",
            "bevgen_collect", "bevgen_select_major", "bevgen_labels", "bevgen_cloud_manip", "bevgen_set_profiling",
            "bevgen_stage_ms", "bevgen_kernel_launches", "bevgen_compute_stream", "bevgen_stage_name",
-           "bevgen_debug_atan2f", "bevgen_pcd_record_layout", "bevgen_process_packed_host"]
+           "bevgen_debug_atan2f", "bevgen_pcd_record_layout", "bevgen_process_packed_host", "bevgen_project"]
 
 
 def build(verbose=False):
@@ -295,6 +295,16 @@ class BevGen:
         _ck(lib().bevgen_cloud_manip(self._ctx, C.c_int64(n), _ptr(rt), _ptr(x), _ptr(y), _ptr(z), _ptr(t[0]), _ptr(t[1]),
                                      _ptr(t[2]), _ptr(bi), _ptr(bo)))
         return t, bi, bo
+
+    # ---- projection step of the keyframe extractors -----------------------------------------------------------
+    def project(self, kind, x, y, z=None):
+        """kind: 0 = MulRan OS1-64 (row = k % 64), 1 = Oxford HDL-32E (returns the negated x, z too).  -> dict."""
+        x = np.array(x, np.float32); y = _as(y, np.float32)
+        z = None if z is None else np.array(z, np.float32)
+        n = len(x)
+        row = np.empty(n, np.uint16); col = np.empty(n, np.uint16)
+        _ck(lib().bevgen_project(self._ctx, C.c_int(kind), C.c_int64(n), _ptr(x), _ptr(y), _ptr(z), _ptr(row), _ptr(col)))
+        return dict(x=x, y=y, z=z, row=row, col=col)
 
     # ---- introspection ----------------------------------------------------------------------------------------
     def set_profiling(self, on):

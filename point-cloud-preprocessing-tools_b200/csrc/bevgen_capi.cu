@@ -695,6 +695,36 @@ extern "C" int bevgen_cloud_manip(bevgen_ctx* c, int64_t n, const float* rt, con
   return 0;
 }
 
+// ---- projection step of the keyframe extractors ---------------------------------------------------
+extern "C" int bevgen_project(bevgen_ctx* c, int kind, int64_t n, float* x, const float* y, float* z, uint16_t* row, uint16_t* col) {
+  if (!c || !x || !y || !row || !col) return fail("bevgen_project: null argument");
+  if (kind != BEVGEN_PROJECT_MULRAN_OS1_64 && kind != BEVGEN_PROJECT_OXFORD_HDL_32E) return fail("bevgen_project: unknown kind");
+  if (kind == BEVGEN_PROJECT_OXFORD_HDL_32E && !z) return fail("bevgen_project: the Oxford projection needs z");
+  if (n < 0) return fail("bevgen_project: n < 0");
+  if (n == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  float* d[3] = {0, 0, 0}; uint16_t* r[2] = {0, 0};
+  for (int i = 0; i < 3; i++) CK(cudaMalloc(&d[i], (size_t)n * 4));
+  for (int i = 0; i < 2; i++) CK(cudaMalloc(&r[i], (size_t)n * 2));
+  CK(cudaMemcpyAsync(d[0], x, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
+  CK(cudaMemcpyAsync(d[1], y, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
+  if (z) CK(cudaMemcpyAsync(d[2], z, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (kind == BEVGEN_PROJECT_MULRAN_OS1_64) k_project<PROJECT_MULRAN><<<blocks, 256, 0, c->s_comp>>>(n, d[0], d[1], d[2], r[0], r[1]);
+  else k_project<PROJECT_OXFORD><<<blocks, 256, 0, c->s_comp>>>(n, d[0], d[1], d[2], r[0], r[1]);
+  CK(cudaGetLastError()); c->launches++;
+  if (kind == BEVGEN_PROJECT_OXFORD_HDL_32E) {   // x and z come back negated (OxfordPointCloudSelect.cpp:203-204)
+    CK(cudaMemcpyAsync(x, d[0], (size_t)n * 4, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(cudaMemcpyAsync(z, d[2], (size_t)n * 4, cudaMemcpyDeviceToHost, c->s_comp));
+  }
+  CK(cudaMemcpyAsync(row, r[0], (size_t)n * 2, cudaMemcpyDeviceToHost, c->s_comp));
+  CK(cudaMemcpyAsync(col, r[1], (size_t)n * 2, cudaMemcpyDeviceToHost, c->s_comp));
+  CK(cudaStreamSynchronize(c->s_comp));
+  for (auto p : d) cudaFree(p);
+  for (auto p : r) cudaFree(p);
+  return 0;
+}
+
 // ---- introspection ----------------------------------------------------------------------------------------------
 extern "C" int bevgen_set_profiling(bevgen_ctx* c, int on) {
   if (!c) return fail("null ctx");

@@ -156,6 +156,55 @@ __device__ __forceinline__ unsigned sector_of(float px, float py) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Kr project — SURVEY 8(f)-2: the keyframe extractors' per-point projection (row / col of the range image), the step
+// that produces the `row` / `col` fields batch_multi_bev_gen consumes.
+//   MULRAN (MulranPointCloudSelect.cpp:112-126): row = k % 64; az = float(double(atan2(y, x)) / M_PI * 180.0f), wrapped
+//     into [0, 360]; col = uint16(round(az / 360.0f * 1024))  (col may equal 1024).
+//   OXFORD (OxfordPointCloudSelect.cpp:201-219): x, z negated (sensor mounted upside-down); elevation =
+//     float(double(atan2(z, sqrt(x*x + y*y))) / M_PI * 180.0f); row = clamp(int(round((-elevation + 10.67) / 1.3335)), 0, 31);
+//     col as above with 1056 columns, then `if (col >= 1056) col -= 1056`.
+// atan2 / sqrt are the float overloads (normative choice of SURVEY 8a.1-G3): atan2f_glibc is bit-exact to glibc.
+// One thread per point.  grid ceil(n/256), block 256.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PROJECT_MULRAN = 0, PROJECT_OXFORD = 1;
+
+__device__ __forceinline__ float rad2deg_ref(float t) {              // (float)((double)t / M_PI * 180.0f)
+  return __double2float_rn(__dmul_rn(__ddiv_rn((double)t, 3.14159265358979323846), 180.0));
+}
+__device__ __forceinline__ uint16_t u16_cast_x86(float v) {          // static_cast<uint16_t>(float): cvttss2si, low 16 bits
+  const int i = (v > -2147483904.0f && v < 2147483648.0f) ? __float2int_rz(v) : INT32_MIN;   // NaN / out of range -> INT_MIN
+  return (uint16_t)(i & 0xFFFF);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_project(int64_t n, float* __restrict__ x, const float* __restrict__ y, float* __restrict__ z,
+                                                  uint16_t* __restrict__ row, uint16_t* __restrict__ col) {
+  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (k >= n) return;
+  float px = x[k], py = y[k];
+  constexpr float COLS = KIND == PROJECT_MULRAN ? 1024.0f : 1056.0f;
+  if (KIND == PROJECT_MULRAN) {
+    row[k] = (uint16_t)(k % 64);                                     // :120
+  } else {
+    float pz = z[k];
+    px = -px; pz = -pz;                                              // :203-204
+    x[k] = px; z[k] = pz;
+    const float hyp = __fsqrt_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)));
+    const float elev = rad2deg_ref(atan2f_glibc(pz, hyp));           // :208
+    const double rr = round(__ddiv_rn(__dadd_rn((double)(-elev), 10.67), 1.3335));   // :209
+    int ri = cvtt_x86(rr);
+    ri = min(31, max(0, ri));                                        // :210
+    row[k] = (uint16_t)ri;
+  }
+  float az = rad2deg_ref(atan2f_glibc(py, px));                      // :121 / :213
+  if (az > 360.0f) az = __fsub_rn(az, 360.0f);
+  else if (az < 0.0f) az = __fadd_rn(az, 360.0f);
+  uint16_t c = u16_cast_x86(roundf(__fmul_rn(__fdiv_rn(az, 360.0f), COLS)));   // :125 / :216
+  if (KIND == PROJECT_OXFORD && c >= 1056) c -= 1056;                // :217
+  col[k] = c;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Kp unpack_records — SURVEY §8(f)-1: the de-interleave of pcl::io::loadPCDFile (BatchMultiBevGen.cpp:730) moved to the
 // GPU.  A binary PCD payload is an array of interleaved records (26 packed bytes for PointXYZIRCT as written by
 // savePCDFileBinary: x y z intensity f32 | row col u16 | t u32 | label i16, BatchMultiBevGen.h:56-66); the host only
@@ -533,13 +582,9 @@ __global__ void __launch_bounds__(128) k_ground_mark(SensorDev sp, const float4*
     const float4 direct = nxt;
     if (r >= 2) nxt = pr[-2 * H];                                 // next iteration's upper: in flight during this row's math
     float4 up = direct;
-    if (is_neg1(up)) {                                            // -1 markers are rare: one branch on the common path
-      up = pr[-H + dplus];                                        // :146-149
-      if (is_neg1(up)) {
-        up = pr[-H + dminus];                                     // :151-154
-        if (is_neg1(up) && r >= 2) up = pr[-2 * H];               // :157-160
-      }
-    }
+    if (is_neg1(up)) up = pr[-H + dplus];                         // :146-149
+    if (is_neg1(up)) up = pr[-H + dminus];                        // :151-154
+    if (is_neg1(up) && r >= 2) up = pr[-2 * H];                   // :157-160
     const bool invalid = is_neg1(lower) || is_neg1(up);           // :162
     const bool ground = !invalid && ground_decision(sp, up, lower);
     emit(lower, !invalid && (ground || ground_prev));

@@ -369,3 +369,27 @@ def test_bird_view_map_of_batch_cloud_manip(gens, synth, O):
         got = out["bvm"][f]
         assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (f, int((got != want).sum()))
         assert want.max() > 0 and (want > 0).sum() > 200   # the map is not trivially empty
+
+
+def test_projection_step_bit_exact(gens, O):
+    """row / col of the range image as the extractors compute them, bit-exact against the oracle on
+    random clouds plus zeros, axis points, huge / tiny / non-finite coordinates."""
+    rng = np.random.default_rng(11)
+    n = 300_001
+    x = rng.normal(0, 30, n).astype(np.float32); y = rng.normal(0, 30, n).astype(np.float32); z = rng.normal(-1, 3, n).astype(np.float32)
+    sp = [0.0, -0.0, 1.0, -1.0, 1e-30, -1e-30, 1e30, np.inf, -np.inf, np.nan, 1e-7, -1e-7]
+    k = 0
+    for a in sp:
+        for b in sp:
+            x[k], y[k], z[k] = a, b, sp[(k * 7) % len(sp)]; k += 1
+    g = gens("OS1_64")
+    got = g.project(0, x, y)
+    row, col = O.project_mulran(x, y)
+    assert np.array_equal(got["row"], row) and np.array_equal(got["col"], col)
+    assert col.max() == 1024                                            # the col == Horizon_SCAN quirk is exercised
+    got = g.project(1, x, y, z)
+    nx, nz, row, col = O.project_oxford(x, y, z)
+    assert np.array_equal(got["x"].view(np.uint32), nx.view(np.uint32)) and np.array_equal(got["z"].view(np.uint32), nz.view(np.uint32))
+    assert np.array_equal(got["row"], row), int((got["row"] != row).sum())
+    assert np.array_equal(got["col"], col), int((got["col"] != col).sum())
+    assert col.max() < 1056 and set(np.unique(row)) == set(range(32))

@@ -291,3 +291,24 @@ def test_bvm_label_filter_and_strict_max(O):
     assert m[200, 200] == np.float32(2.25)                  # v = 199.99 -> 200
     assert m[105 + 1 - 0, 105 + 1 - 0] == 0                 # z + 2 = -0.5 is not > 0: never stored
     assert (m > 0).sum() == 3                               # px = 100.0 -> x = 201: out of range
+
+
+def test_projection_known_answers(O):
+    """Projection step of the extractors: MulranPointCloudSelect.cpp:112-126, OxfordPointCloudSelect.cpp:201-219."""
+    x = np.array([1, 0, -1, 0, 1, 1], np.float32); y = np.array([0, 1, 0, -1, -1e-7, np.nan], np.float32)
+    row, col = O.project_mulran(x, y)
+    assert row.tolist() == [0, 1, 2, 3, 4, 5]                          # k % 64
+    # 0, 90, 180 deg; -90 -> 270; a tiny negative angle wraps to 360.0f -> col == 1024 (== Horizon_SCAN, dropped later); NaN -> 0
+    assert col.tolist() == [0, 256, 512, 768, 1024, 0]
+    r2, _ = O.project_mulran(np.ones(130, np.float32), np.zeros(130, np.float32))
+    assert r2[63] == 63 and r2[64] == 0 and r2[129] == 1
+    # Oxford: x, z negated; elevation 0 -> round(10.67 / 1.3335) = 8; +10.67 deg -> row 0; below -30.67 deg clamps to 31
+    xo = np.array([-1, -1, -1, 0], np.float32); yo = np.array([0, 0, 0, 1], np.float32)
+    zo = np.array([0, -np.tan(np.deg2rad(10.67)), 5, 0], np.float32)
+    nx, nz, row, col = O.project_oxford(xo, yo, zo)
+    assert nx.tolist() == [1, 1, 1, 0] and nz[2] == -5                 # (the 4th x is -0.0 == 0)
+    assert row.tolist() == [8, 0, 31, 8]
+    assert col.tolist() == [0, 0, 0, 264]                              # 90 deg of 1056 columns
+    # col wrap: an azimuth that rounds to 1056 comes back as 0 (:217)
+    _, _, _, c = O.project_oxford(np.array([-1], np.float32), np.array([-1e-7], np.float32), np.array([0], np.float32))
+    assert c.tolist() == [0]
