@@ -80,6 +80,7 @@ struct bevgen_ctx {
   cudaStream_t s_aux[MAX_AUX]{}; // waves rotate over s_comp, s_aux[0], s_aux[1], ...
   cudaEvent_t ev_fork = 0, ev_join[MAX_AUX]{}; int n_dev_streams = 2;
   int64_t* offs_d = 0; size_t offs_cap = 0;
+  char* tmp = 0; size_t tmp_cap = 0;   // grow-only device arena of the host-array entry points (labels, cloud_manip, project, ...)
   bool lanes_ready = false; Lane lanes[3];
   std::vector<Slot> slots;
   // profiling
@@ -243,7 +244,7 @@ extern "C" void bevgen_destroy(bevgen_ctx* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->lanes_ready) for (auto& l : c->lanes) { cudaFree(l.raw); cudaFree(l.bvm); free_scratch(l.sc); free_io(l.in, l.out); cudaEventDestroy(l.ev_h2d); cudaEventDestroy(l.ev_comp); cudaEventDestroy(l.ev_d2h); }
   for (auto& s : c->slots) { free_scratch(s.sc); free_io(s.in, s.out); cudaFreeHost(s.pin_in); cudaFreeHost(s.pin_out); cudaFree(s.offs_d); cudaStreamDestroy(s.st); cudaEventDestroy(s.done); }
-  cudaFree(c->cnt_lut); cudaFree(c->offs_d);
+  cudaFree(c->cnt_lut); cudaFree(c->offs_d); cudaFree(c->tmp);
   for (auto& e : c->pev) cudaEventDestroy(e);
   cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h);
   delete c;
@@ -367,6 +368,24 @@ static int upload_offsets(bevgen_ctx* c, int nf, const int64_t* offsets, cudaStr
   }
   *max_n_out = (int)mx;
   CK(cudaMemcpyAsync(c->offs_d, offsets, ((size_t)nf + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+// ---- device arena of the host-array entry points ----------------------------------------------------------------
+// One grow-only allocation per context instead of cudaMalloc / cudaFree per call (both synchronise the device and cost
+// far more than the kernels of these small entry points); carved into 256-byte aligned pieces.
+struct Carver {
+  char* p; size_t used = 0;
+  static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+  template <typename T> T* take(size_t n) { T* r = reinterpret_cast<T*>(p + used); used += pad(n * sizeof(T)); return r; }
+};
+static int tmp_reserve(bevgen_ctx* c, size_t bytes) {
+  if (bytes <= c->tmp_cap) return 0;
+  CK(cudaStreamSynchronize(c->s_comp));
+  cudaFree(c->tmp); c->tmp = 0; c->tmp_cap = 0;
+  const size_t cap = bytes + bytes / 4 + 4096;
+  CK(cudaMalloc(&c->tmp, cap));
+  c->tmp_cap = cap;
   return 0;
 }
 
@@ -622,9 +641,10 @@ extern "C" int bevgen_select_major(bevgen_ctx* c, int K, const float* xyz, int32
   if (!c || !xyz || !major_idx || !n_major) return fail("bevgen_select_major: null argument");
   if (K <= 0) { *n_major = 0; return 0; }
   CK(cudaSetDevice(c->device));
-  float *d_xyz = 0, *d_mpos = 0; int32_t *d_mi = 0, *d_ov = 0, *d_n = 0;
-  CK(cudaMalloc(&d_xyz, (size_t)K * 12)); CK(cudaMalloc(&d_mpos, (size_t)K * 12));
-  CK(cudaMalloc(&d_mi, (size_t)K * 4)); CK(cudaMalloc(&d_ov, (size_t)K * 4)); CK(cudaMalloc(&d_n, 4));
+  if (tmp_reserve(c, 2 * Carver::pad((size_t)K * 12) + 2 * Carver::pad((size_t)K * 4) + 256)) return -1;
+  Carver cv{c->tmp};
+  float* d_xyz = cv.take<float>((size_t)K * 3); float* d_mpos = cv.take<float>((size_t)K * 3);
+  int32_t* d_mi = cv.take<int32_t>(K); int32_t* d_ov = cv.take<int32_t>(K); int32_t* d_n = cv.take<int32_t>(1);
   CK(cudaMemcpyAsync(d_xyz, xyz, (size_t)K * 12, cudaMemcpyHostToDevice, c->s_comp));
   k_select_major<<<1, 32, 0, c->s_comp>>>(K, d_xyz, d_mpos, d_mi, d_ov, d_n);
   CK(cudaGetLastError()); c->launches++;
@@ -634,7 +654,6 @@ extern "C" int bevgen_select_major(bevgen_ctx* c, int K, const float* xyz, int32
   CK(cudaMemcpy(major_idx, d_mi, (size_t)M * 4, cudaMemcpyDeviceToHost));
   if (overlap_nn) CK(cudaMemcpy(overlap_nn, d_ov, (size_t)K * 4, cudaMemcpyDeviceToHost));
   *n_major = M;
-  cudaFree(d_xyz); cudaFree(d_mpos); cudaFree(d_mi); cudaFree(d_ov); cudaFree(d_n);
   return 0;
 }
 
@@ -647,10 +666,14 @@ extern "C" int bevgen_labels(bevgen_ctx* c, int K, const float* xyz, int M, cons
   const int rows = row_end - row_begin;
   if (rows == 0) return 0;
   CK(cudaSetDevice(c->device));
-  float *d_xyz = 0, *d_mpos = 0, *d_w = 0, *d_dense = 0; int32_t *d_mi = 0, *d_nn = 0;
-  CK(cudaMalloc(&d_xyz, (size_t)K * 12)); CK(cudaMalloc(&d_mpos, (size_t)M * 12)); CK(cudaMalloc(&d_mi, (size_t)M * 4));
-  CK(cudaMalloc(&d_nn, (size_t)rows * 8)); CK(cudaMalloc(&d_w, (size_t)rows * 8));
-  if (labels_out) { CK(cudaMalloc(&d_dense, (size_t)rows * M * 4)); CK(cudaMemsetAsync(d_dense, 0, (size_t)rows * M * 4, c->s_comp)); }
+  const size_t dense_n = labels_out ? (size_t)rows * M : 0;
+  if (tmp_reserve(c, Carver::pad((size_t)K * 12) + Carver::pad((size_t)M * 12) + Carver::pad((size_t)M * 4) + 2 * Carver::pad((size_t)rows * 8) +
+                         Carver::pad(dense_n * 4))) return -1;
+  Carver cv{c->tmp};
+  float* d_xyz = cv.take<float>((size_t)K * 3); float* d_mpos = cv.take<float>((size_t)M * 3); int32_t* d_mi = cv.take<int32_t>(M);
+  int32_t* d_nn = cv.take<int32_t>((size_t)rows * 2); float* d_w = cv.take<float>((size_t)rows * 2);
+  float* d_dense = labels_out ? cv.take<float>(dense_n) : nullptr;
+  if (labels_out) CK(cudaMemsetAsync(d_dense, 0, dense_n * 4, c->s_comp));
   CK(cudaMemcpyAsync(d_xyz, xyz, (size_t)K * 12, cudaMemcpyHostToDevice, c->s_comp));
   CK(cudaMemcpyAsync(d_mi, major_idx, (size_t)M * 4, cudaMemcpyHostToDevice, c->s_comp));
   k_gather_mpos<<<(M + 127) / 128, 128, 0, c->s_comp>>>(M, d_xyz, d_mi, d_mpos);
@@ -660,7 +683,6 @@ extern "C" int bevgen_labels(bevgen_ctx* c, int K, const float* xyz, int M, cons
   if (labels_out) CK(cudaMemcpy(labels_out, d_dense, (size_t)rows * M * 4, cudaMemcpyDeviceToHost));
   if (nn_idx) CK(cudaMemcpy(nn_idx, d_nn, (size_t)rows * 8, cudaMemcpyDeviceToHost));
   if (nn_w) CK(cudaMemcpy(nn_w, d_w, (size_t)rows * 8, cudaMemcpyDeviceToHost));
-  cudaFree(d_xyz); cudaFree(d_mpos); cudaFree(d_mi); cudaFree(d_nn); cudaFree(d_w); cudaFree(d_dense);
   return 0;
 }
 
@@ -670,10 +692,12 @@ extern "C" int bevgen_cloud_manip(bevgen_ctx* c, int64_t n, const float* rt, con
   if (!c || !rt || !x || !y || !z) return fail("bevgen_cloud_manip: null argument");
   if (n < 0) return fail("bevgen_cloud_manip: n < 0");
   CK(cudaSetDevice(c->device));
-  const size_t nb = (size_t)std::max<int64_t>(n, 1) * 4;
-  float* d[6] = {0, 0, 0, 0, 0, 0}; int* g[2] = {0, 0};
-  for (int i = 0; i < 6; i++) CK(cudaMalloc(&d[i], nb));
-  for (int i = 0; i < 2; i++) { CK(cudaMalloc(&g[i], MGRID * MGRID * 4)); CK(cudaMemsetAsync(g[i], 0, MGRID * MGRID * 4, c->s_comp)); }
+  const size_t np = (size_t)std::max<int64_t>(n, 1);
+  if (tmp_reserve(c, 6 * Carver::pad(np * 4) + 2 * Carver::pad(MGRID * MGRID * 4))) return -1;
+  Carver cv{c->tmp};
+  float* d[6]; int* g[2];
+  for (int i = 0; i < 6; i++) d[i] = cv.take<float>(np);
+  for (int i = 0; i < 2; i++) { g[i] = cv.take<int>(MGRID * MGRID); CK(cudaMemsetAsync(g[i], 0, MGRID * MGRID * 4, c->s_comp)); }
   CK(cudaMemcpyAsync(d[0], x, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
   CK(cudaMemcpyAsync(d[1], y, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
   CK(cudaMemcpyAsync(d[2], z, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
@@ -690,8 +714,6 @@ extern "C" int bevgen_cloud_manip(bevgen_ctx* c, int64_t n, const float* rt, con
   }
   if (bev_in) CK(cudaMemcpy(bev_in, g[0], MGRID * MGRID * 4, cudaMemcpyDeviceToHost));
   if (bev_out) CK(cudaMemcpy(bev_out, g[1], MGRID * MGRID * 4, cudaMemcpyDeviceToHost));
-  for (auto p : d) cudaFree(p);
-  for (auto p : g) cudaFree(p);
   return 0;
 }
 
@@ -703,9 +725,11 @@ extern "C" int bevgen_project(bevgen_ctx* c, int kind, int64_t n, float* x, cons
   if (n < 0) return fail("bevgen_project: n < 0");
   if (n == 0) return 0;
   CK(cudaSetDevice(c->device));
-  float* d[3] = {0, 0, 0}; uint16_t* r[2] = {0, 0};
-  for (int i = 0; i < 3; i++) CK(cudaMalloc(&d[i], (size_t)n * 4));
-  for (int i = 0; i < 2; i++) CK(cudaMalloc(&r[i], (size_t)n * 2));
+  if (tmp_reserve(c, 3 * Carver::pad((size_t)n * 4) + 2 * Carver::pad((size_t)n * 2))) return -1;
+  Carver cv{c->tmp};
+  float* d[3]; uint16_t* r[2];
+  for (int i = 0; i < 3; i++) d[i] = cv.take<float>((size_t)n);
+  for (int i = 0; i < 2; i++) r[i] = cv.take<uint16_t>((size_t)n);
   CK(cudaMemcpyAsync(d[0], x, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
   CK(cudaMemcpyAsync(d[1], y, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
   if (z) CK(cudaMemcpyAsync(d[2], z, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
@@ -720,8 +744,6 @@ extern "C" int bevgen_project(bevgen_ctx* c, int kind, int64_t n, float* x, cons
   CK(cudaMemcpyAsync(row, r[0], (size_t)n * 2, cudaMemcpyDeviceToHost, c->s_comp));
   CK(cudaMemcpyAsync(col, r[1], (size_t)n * 2, cudaMemcpyDeviceToHost, c->s_comp));
   CK(cudaStreamSynchronize(c->s_comp));
-  for (auto p : d) cudaFree(p);
-  for (auto p : r) cudaFree(p);
   return 0;
 }
 
