@@ -159,10 +159,16 @@ BEVGEN_API int bevgen_cloud_manip(bevgen_ctx *ctx, int64_t n, const float *rt, c
  *                                 (col may come out equal to 1024; getOrderedCloud drops such points, :106-109)
  *   BEVGEN_PROJECT_OXFORD_HDL_32E (OxfordPointCloudSelect.cpp:201-219): x and z are NEGATED IN PLACE (sensor mounted
  *                                 upside-down), row from the elevation angle clamped to 0..31, col wrapped at 1056.
- * Host arrays of n points in file order; z may be NULL for MULRAN.  KittiPointCloudSelect's ring detection
- * (KittiPointCloudSelect.cpp:188-243) is a sequential state machine over the scan and is not covered. */
+ *   BEVGEN_PROJECT_KITTI_HDL_64E  (KittiPointCloudSelect.cpp:188-243): ring detection from the azimuth sign changes
+ *                                 (a new ring only after more than 2083 * 0.60f points), col = round(az / (360.0 / 2083));
+ *                                 points the extractor does not place (point 0, rings outside 0..63) get row = col =
+ *                                 0xFFFF, which getOrderedCloud's bounds test drops.  The caller sets intensity = -1 and
+ *                                 label = -2 like :236-238.  A scan whose azimuth is NaN anywhere is undefined
+ *                                 behaviour in the reference (out-of-bounds index) and yields unplaced points here.
+ * Host arrays of n points in file order; z may be NULL except for OXFORD. */
 #define BEVGEN_PROJECT_MULRAN_OS1_64 0
 #define BEVGEN_PROJECT_OXFORD_HDL_32E 1
+#define BEVGEN_PROJECT_KITTI_HDL_64E 2
 BEVGEN_API int bevgen_project(bevgen_ctx *ctx, int kind, int64_t n, float *x, const float *y, float *z, uint16_t *row,
                    uint16_t *col);
 

@@ -473,6 +473,35 @@ ORACLE_API void oracle_project_oxford(int64_t n, float *x, const float *y, float
   }
 }
 
+/* KittiPointCloudSelect.cpp:188-243: azimuth per point, ring detection, column index.  row/col = 0xFFFF for the points
+ * the extractor does not place into the structured cloud (point 0; rings outside 0..63). */
+ORACLE_API void oracle_project_kitti(int64_t n, const float *x, const float *y, uint16_t *row, uint16_t *col) {
+  const int N_SCAN = 64, Horizon_SCAN = 2083;                                       /* :148-149 */
+  if (n <= 0) return;
+  float *azimuth_angle = (float *)malloc((size_t)n * sizeof(float));
+  for (int64_t i = 0; i < n; i++) azimuth_angle[i] = (float)(P_ATAN2(y[i], x[i]) / M_PI * 180.0f);   /* :191-194 */
+  int32_t ring_idx = azimuth_angle[0] > 0 ? 0 : -1;                                 /* :199-204 */
+  int num_points_on_this_ring = 0;
+  row[0] = col[0] = 0xFFFF;
+  for (int64_t i = 1; i < n; i++) {                                                 /* :211 */
+    if (azimuth_angle[i - 1] <= 0 && azimuth_angle[i] > 0) {                        /* :213 */
+      if (ring_idx == -1) { ring_idx = 0; num_points_on_this_ring = 0; }
+      else if ((float)num_points_on_this_ring > (float)Horizon_SCAN * 0.60f) { ring_idx++; num_points_on_this_ring = 0; }
+    }
+    float a = azimuth_angle[i];                                                     /* makeAngleSemiPositive :137-146 */
+    if (a >= 360.0f) a = a - 360.0f; else if (a < 0) a = a + 360.0f;
+    int col_idx = x86_cvtt(round((double)a / (360.0 / Horizon_SCAN)));              /* :226 */
+    row[i] = col[i] = 0xFFFF;
+    if (ring_idx >= 0 && ring_idx < N_SCAN) {                                       /* :228 */
+      if (col_idx >= Horizon_SCAN) col_idx = col_idx - Horizon_SCAN;
+      else if (col_idx < 0) col_idx = col_idx + Horizon_SCAN;
+      if (col_idx >= 0 && col_idx < Horizon_SCAN) { row[i] = (uint16_t)ring_idx; col[i] = (uint16_t)col_idx; }
+    }
+    num_points_on_this_ring++;                                                      /* :241 */
+  }
+  free(azimuth_angle);
+}
+
 /* Exposed for tests: the float libm the oracle was built against. */
 ORACLE_API float oracle_atan2f(float y, float x) { return atan2f(y, x); }
 ORACLE_API float oracle_angle_deg(float dz, float dx, float dy) {

@@ -190,6 +190,14 @@ def project_mulran(x, y):
     return row, col
 
 
+def project_kitti(x, y):
+    """KittiPointCloudSelect.cpp:188-243 -> (row, col); 0xFFFF = not placed."""
+    x, px = _f(x); y, py = _f(y)
+    row = np.empty(len(x), np.uint16); col = np.empty(len(x), np.uint16)
+    lib().oracle_project_kitti(C.c_int64(len(x)), px, py, _p(row, C.c_uint16), _p(col, C.c_uint16))
+    return row, col
+
+
 def project_oxford(x, y, z):
     """OxfordPointCloudSelect.cpp:201-219 -> (x_negated, z_negated, row, col)."""
     x = np.array(x, np.float32); z = np.array(z, np.float32); y, py = _f(y)

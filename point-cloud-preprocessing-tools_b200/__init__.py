@@ -298,7 +298,8 @@ class BevGen:
 
     # ---- projection step of the keyframe extractors -----------------------------------------------------------
     def project(self, kind, x, y, z=None):
-        """kind: 0 = MulRan OS1-64 (row = k % 64), 1 = Oxford HDL-32E (returns the negated x, z too).  -> dict."""
+        """kind: 0 = MulRan OS1-64 (row = k % 64), 1 = Oxford HDL-32E (returns the negated x, z too), 2 = KITTI HDL-64E ring
+        detection (row = col = 0xFFFF for points the extractor does not place).  -> dict."""
         x = np.array(x, np.float32); y = _as(y, np.float32)
         z = None if z is None else np.array(z, np.float32)
         n = len(x)

@@ -720,16 +720,33 @@ extern "C" int bevgen_cloud_manip(bevgen_ctx* c, int64_t n, const float* rt, con
 // ---- projection step of the keyframe extractors ---------------------------------------------------
 extern "C" int bevgen_project(bevgen_ctx* c, int kind, int64_t n, float* x, const float* y, float* z, uint16_t* row, uint16_t* col) {
   if (!c || !x || !y || !row || !col) return fail("bevgen_project: null argument");
-  if (kind != BEVGEN_PROJECT_MULRAN_OS1_64 && kind != BEVGEN_PROJECT_OXFORD_HDL_32E) return fail("bevgen_project: unknown kind");
+  if (kind != BEVGEN_PROJECT_MULRAN_OS1_64 && kind != BEVGEN_PROJECT_OXFORD_HDL_32E && kind != BEVGEN_PROJECT_KITTI_HDL_64E)
+    return fail("bevgen_project: unknown kind");
+  if (kind == BEVGEN_PROJECT_KITTI_HDL_64E && n > 0x7ffffff0) return fail("bevgen_project: scan too large");
   if (kind == BEVGEN_PROJECT_OXFORD_HDL_32E && !z) return fail("bevgen_project: the Oxford projection needs z");
   if (n < 0) return fail("bevgen_project: n < 0");
   if (n == 0) return 0;
   CK(cudaSetDevice(c->device));
-  if (tmp_reserve(c, 3 * Carver::pad((size_t)n * 4) + 2 * Carver::pad((size_t)n * 2))) return -1;
+  if (tmp_reserve(c, 3 * Carver::pad((size_t)n * 4) + 2 * Carver::pad((size_t)n * 2) + Carver::pad(((size_t)n / 2 + 2) * 4) +
+                         Carver::pad((KITTI_MAX_RINGS + 1) * 4) + 256)) return -1;
   Carver cv{c->tmp};
   float* d[3]; uint16_t* r[2];
   for (int i = 0; i < 3; i++) d[i] = cv.take<float>((size_t)n);
   for (int i = 0; i < 2; i++) r[i] = cv.take<uint16_t>((size_t)n);
+  if (kind == BEVGEN_PROJECT_KITTI_HDL_64E) {   // d[2] holds the azimuths instead of z
+    int* ev = cv.take<int>((size_t)n / 2 + 2); int* acc = cv.take<int>(KITTI_MAX_RINGS + 1); int* base = cv.take<int>(1);
+    CK(cudaMemcpyAsync(d[0], x, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
+    CK(cudaMemcpyAsync(d[1], y, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    k_kitti_azimuth<<<nb, 256, 0, c->s_comp>>>(n, d[0], d[1], d[2]);
+    k_kitti_rings<<<1, 1024, 0, c->s_comp>>>((int)n, d[2], ev, acc, base);
+    k_kitti_assign<<<nb, 256, 0, c->s_comp>>>((int)n, d[2], acc, base, r[0], r[1]);
+    CK(cudaGetLastError()); c->launches += 3;
+    CK(cudaMemcpyAsync(row, r[0], (size_t)n * 2, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(cudaMemcpyAsync(col, r[1], (size_t)n * 2, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(cudaStreamSynchronize(c->s_comp));
+    return 0;
+  }
   CK(cudaMemcpyAsync(d[0], x, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
   CK(cudaMemcpyAsync(d[1], y, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
   if (z) CK(cudaMemcpyAsync(d[2], z, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));

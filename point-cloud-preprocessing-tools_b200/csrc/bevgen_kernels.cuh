@@ -205,6 +205,84 @@ __global__ void __launch_bounds__(256) k_project(int64_t n, float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Kr' KITTI ring detection — KittiPointCloudSelect.cpp:188-243.  The scan file has no ring index; the extractor walks
+// the points in file order and starts a new ring when the azimuth crosses from <= 0 to > 0, but only if the current
+// ring already holds more than Horizon_SCAN * 0.60f points (:213-221).  That acceptance rule is a serial chain over
+// the CROSSINGS only (a few hundred per scan), so:
+//   k_kitti_azimuth : azimuth per point (parallel)
+//   k_kitti_rings   : one CTA compacts the crossing indices in file order, thread 0 runs the greedy acceptance chain
+//   k_kitti_assign  : ring(i) = base + #accepted crossings <= i (binary search), col = round(az' / (360.0 / 2083))
+// Point 0 is never placed (the loop starts at 1, :211); points of rings outside 0..63 are dropped (:228): both come
+// back as row = col = 0xFFFF, which getOrderedCloud's bounds test discards.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int KITTI_N = 64, KITTI_H = 2083;
+constexpr int KITTI_MAX_RINGS = 4096;        // accepted crossings kept (they are >= 1250 points apart)
+
+__global__ void __launch_bounds__(256) k_kitti_azimuth(int64_t n, const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ az) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) az[i] = rad2deg_ref(atan2f_glibc(y[i], x[i]));          // :191-194
+}
+
+// grid 1, block 1024.  ev: scratch for the crossing indices (capacity n/2 + 1); acc[0] = number of accepted crossings,
+// acc[1..] their indices; acc_base = ring index before the first accepted crossing (0 or -1, :199-204).
+__global__ void __launch_bounds__(1024) k_kitti_rings(int n, const float* __restrict__ az, int* __restrict__ ev, int* __restrict__ acc,
+                                                       int* __restrict__ acc_base) {
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int n_ev = 0;
+  for (int b = 1; b < n; b += 1024) {                                 // crossings in file order (stable compaction)
+    const int i = b + tid;
+    const bool e = i < n && az[i - 1] <= 0.0f && az[i] > 0.0f;        // :213
+    const unsigned m = __ballot_sync(0xffffffffu, e);
+    if (lane == 0) s_warp[wid] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 32; w++) { const int c = s_warp[w]; if (w < wid) before += c; total += c; }
+    if (e) ev[n_ev + before + __popc(m & ((1u << lane) - 1u))] = i;
+    n_ev += total;
+    __syncthreads();
+  }
+  if (tid == 0) s_total = n_ev;
+  __threadfence_block();
+  __syncthreads();
+  if (tid == 0) {                                                     // the serial acceptance chain (:214-220)
+    int ring = az[0] > 0.0f ? 0 : -1;                                 // :199-204
+    *acc_base = ring;
+    int last = 1;                                                     // num_points_on_this_ring == i - last at index i
+    int na = 0;
+    const float need = __fmul_rn((float)KITTI_H, 0.60f);
+    for (int k = 0; k < s_total; k++) {
+      const int i = ev[k];
+      bool take;
+      if (ring == -1) take = true;                                    // :214-216
+      else take = (float)(i - last) > need;                           // :217
+      if (take) { ring++; last = i; if (na < KITTI_MAX_RINGS) acc[1 + na] = i; na++; }
+    }
+    acc[0] = min(na, KITTI_MAX_RINGS);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_kitti_assign(int n, const float* __restrict__ az, const int* __restrict__ acc,
+                                                       const int* __restrict__ acc_base, uint16_t* __restrict__ row, uint16_t* __restrict__ col) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int na = acc[0];
+  int lo = 0, hi = na;                                               // number of accepted crossings with index <= i
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (acc[1 + mid] <= i) lo = mid + 1; else hi = mid; }
+  const int ring = *acc_base + lo;
+  float a = az[i];
+  if (a >= 360.0f) a = __fsub_rn(a, 360.0f); else if (a < 0.0f) a = __fadd_rn(a, 360.0f);            // makeAngleSemiPositive :137-146
+  int c = cvtt_x86(round(__ddiv_rn((double)a, __ddiv_rn(360.0, (double)KITTI_H))));                  // :226
+  uint16_t r16 = 0xFFFFu, c16 = 0xFFFFu;
+  if (i >= 1 && ring >= 0 && ring < KITTI_N) {                        // :211, :228
+    if (c >= KITTI_H) c -= KITTI_H; else if (c < 0) c += KITTI_H;    // :229-233
+    if (c >= 0 && c < KITTI_H) { r16 = (uint16_t)ring; c16 = (uint16_t)c; }   // (outside: the reference indexes out of bounds)
+  }
+  row[i] = r16; col[i] = c16;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Kp unpack_records — SURVEY §8(f)-1: the de-interleave of pcl::io::loadPCDFile (BatchMultiBevGen.cpp:730) moved to the
 // GPU.  A binary PCD payload is an array of interleaved records (26 packed bytes for PointXYZIRCT as written by
 // savePCDFileBinary: x y z intensity f32 | row col u16 | t u32 | label i16, BatchMultiBevGen.h:56-66); the host only

@@ -149,3 +149,26 @@ def pose_csv_lines(xyz):
         v = [x, y, z, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0]
         lines.append("%06d" % i + "".join(",%.6f" % a for a in v))
     return lines
+
+
+def make_kitti_scan(seed, n_rings=64, start_negative=False, short_rings=(17, 40), jitter=True):
+    """Raw HDL-64E scan in KITTI file order (ring after ring, every ring sweeping the azimuth 0+ .. 180, -180 .. 0-),
+    for the ring detection of KittiPointCloudSelect.cpp:188-243: rings in `short_rings` hold fewer than 1250 points
+    (their crossing must be ignored, :217), `jitter` adds sign flips right after a ring start (spurious crossings),
+    `start_negative` begins below 0 degrees (ring_idx starts at -1, :199-204)."""
+    rng = np.random.default_rng(0xC17 + seed)
+    az_all = []
+    if start_negative:
+        az_all.append(np.sort(rng.uniform(-20.0, -0.5, 37)))
+    for r in range(n_rings):
+        m = int(rng.integers(700, 1100)) if r in short_rings else int(rng.integers(1500, 2084))
+        a = np.sort(rng.uniform(0.05, 359.95, m))
+        a = np.where(a > 180.0, a - 360.0, a)
+        if jitter and r % 5 == 2:
+            a[1:6] = [-0.3, 0.2, -0.1, 0.4, 0.6]          # flips right after the ring start: too few points, ignored
+        az_all.append(a)
+    az = np.concatenate(az_all)
+    rad = rng.uniform(3.0, 70.0, len(az))
+    x = (rad * np.cos(np.deg2rad(az))).astype(np.float32); y = (rad * np.sin(np.deg2rad(az))).astype(np.float32)
+    z = rng.uniform(-2.0, 1.0, len(az)).astype(np.float32)
+    return x, y, z

@@ -395,3 +395,18 @@ def test_projection_step_bit_exact(gens, O):
     assert np.array_equal(got["row"], row), int((got["row"] != row).sum())
     assert np.array_equal(got["col"], col), int((got["col"] != col).sum())
     assert col.max() < 1056 and set(np.unique(row)) == set(range(32))
+
+
+@pytest.mark.parametrize("seed,kw", [(0, {}), (1, dict(start_negative=True)), (2, dict(n_rings=70, short_rings=(0, 1, 33))), (3, dict(n_rings=3, jitter=False))])
+def test_kitti_ring_detection_bit_exact(gens, synth, O, seed, kw):
+    """SURVEY 8(f)-2, KittiPointCloudSelect.cpp:188-243: row / col per point of a raw scan, equal to the oracle - short rings
+    whose crossing is ignored, spurious sign flips, a scan that starts below 0 degrees, more than 64 rings."""
+    x, y, _ = synth.make_kitti_scan(seed, **kw)
+    row, col = O.project_kitti(x, y)
+    got = gens("HDL_64E").project(2, x, y)
+    assert np.array_equal(got["row"], row), int((got["row"] != row).sum())
+    assert np.array_equal(got["col"], col), int((got["col"] != col).sum())
+    placed = row != 0xFFFF
+    assert row[0] == 0xFFFF and placed.sum() > 1000 and col[placed].max() < 2083 and row[placed].max() < 64
+    if kw.get("n_rings", 64) == 64 and not kw.get("start_negative"):
+        assert row[placed].max() == 61          # 64 rings, two short ones merged into their successors

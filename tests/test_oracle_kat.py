@@ -312,3 +312,24 @@ def test_projection_known_answers(O):
     # col wrap: an azimuth that rounds to 1056 comes back as 0 (:217)
     _, _, _, c = O.project_oxford(np.array([-1], np.float32), np.array([-1e-7], np.float32), np.array([0], np.float32))
     assert c.tolist() == [0]
+
+
+def test_kitti_ring_detection_rule(O):
+    """KittiPointCloudSelect.cpp:199-221: a crossing (az[i-1] <= 0 < az[i]) opens a new ring only when the current ring
+    holds more than 2083 * 0.60f = 1249.8 points; point 0 is never placed; a scan that starts at az <= 0 has no ring
+    until its first crossing."""
+    def scan(n_first, n_rest, first_az=10.0):
+        az = np.concatenate([np.full(n_first, first_az), [-10.0], np.full(n_rest, 10.0)])
+        return np.cos(np.deg2rad(az)).astype(np.float32), np.sin(np.deg2rad(az)).astype(np.float32)
+    x, y = scan(1300, 50)                     # crossing at i = 1301 with num = 1300 > 1249.8 -> ring 1
+    row, col = O.project_kitti(x, y)
+    assert row[0] == 0xFFFF and col[0] == 0xFFFF
+    assert set(row[1:1301]) == {0} and set(row[1301:]) == {1}
+    assert col[1] == round(10.0 / (360.0 / 2083)) and col[1300] == round(350.0 / (360.0 / 2083))
+    x, y = scan(1250, 50)                     # num = 1250 at the crossing: 1250 > 1249.8 -> accepted
+    assert set(O.project_kitti(x, y)[0][1251:]) == {1}
+    x, y = scan(1249, 50)                     # num = 1249: ignored, the ring index stays 0
+    assert set(O.project_kitti(x, y)[0][1:]) == {0}
+    x, y = scan(5, 50, first_az=-10.0)        # starts below 0: nothing is placed before the first crossing, which is always taken
+    row, _ = O.project_kitti(x, y)
+    assert set(row[:6]) == {0xFFFF} and set(row[6:]) == {0}

@@ -79,7 +79,7 @@ def main():
     n = 8 * 65536
     x = rng.normal(0, 30, n).astype(np.float32); y = rng.normal(0, 30, n).astype(np.float32); z = rng.normal(-1, 3, n).astype(np.float32)
     t_m = wall(lambda: g.project(0, x, y), 5); t_o = wall(lambda: g.project(1, x, y, z), 5)
-    print(json.dumps({"what": "bevgen_project, %d points (8 OS1-64 scans), host arrays in/out incl. cudaMalloc + copies" % n,
+    print(json.dumps({"what": "bevgen_project, %d points (8 OS1-64 scans), host (pageable) arrays in/out, copies included" % n,
                       "Mpts_per_s": {"mulran": n / t_m / 1e6, "oxford": n / t_o / 1e6}}), flush=True)
     # ---- configs[4]: cloud_manip, 2 M points ------------------------------------------------------------------------------
     n = 2_000_000
