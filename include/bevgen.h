@@ -172,6 +172,15 @@ BEVGEN_API int bevgen_cloud_manip(bevgen_ctx *ctx, int64_t n, const float *rt, c
 BEVGEN_API int bevgen_project(bevgen_ctx *ctx, int kind, int64_t n, float *x, const float *y, float *z, uint16_t *row,
                    uint16_t *col);
 
+/* SURVEY 8(f)-4 — extractTopAndFlatten (TopPartRegistration.cpp:79-141, BatchTopPartRegistration.cpp:90): the consumer
+ * of non_ground_point_cloud/.  Points with label != 0 are binned into a 10 x 10 grid of 20 m cells; every cell holding
+ * at least 20 points keeps its round(0.2f * count) highest points; output = those points cell after cell (grid_x major),
+ * highest first, with z dropped (the reference sets it to 0).  out_x / out_y / out_index (optional: index of the source
+ * point) need room for n entries; *n_out = number of points written.  Points of equal height keep their input order
+ * (the reference's std::sort leaves that order unspecified); NaN heights are undefined behaviour in the reference. */
+BEVGEN_API int bevgen_top_flatten(bevgen_ctx *ctx, int64_t n, const float *x, const float *y, const float *z, const int16_t *label,
+                       float *out_x, float *out_y, uint32_t *out_index, int64_t *n_out);
+
 /* ---- introspection for bench / tests (no reference counterpart) ---------------------------------------------- */
 #define BEVGEN_N_STAGES 8
 /* Stage order: 0 clear, 1 order (claim), 2 order_fill (large range images only), 3 ground_mark, 4 sector_mean,

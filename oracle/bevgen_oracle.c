@@ -502,6 +502,50 @@ ORACLE_API void oracle_project_kitti(int64_t n, const float *x, const float *y, 
   free(azimuth_angle);
 }
 
+/* extractTopAndFlatten, TopPartRegistration.cpp:79-141.  out_index[k] = index of the k-th output point, out_x/out_y its
+ * coordinates (z is set to 0 by the reference, :135).  Returns the number of output points.  The reference sorts every
+ * cell with std::sort (order of equal heights unspecified); this restatement uses a stable order (height descending,
+ * then input index), which is one of the orders std::sort may produce. */
+typedef struct { float z; int idx; } top_item;
+static int top_cmp(const void *a, const void *b) {
+  const top_item *p = (const top_item *)a, *q = (const top_item *)b;
+  if (p->z > q->z) return -1;                                                      /* :130-132: z_1 > z_2 first */
+  if (q->z > p->z) return 1;
+  return (p->idx > q->idx) - (p->idx < q->idx);
+}
+ORACLE_API int64_t oracle_top_flatten(int64_t n, const float *x, const float *y, const float *z, const int16_t *label,
+                                      float *out_x, float *out_y, uint32_t *out_index) {
+  const int NUM_GRID_X = 10, NUM_GRID_Y = 10;                                       /* :83-84 */
+  const float MAX_RADIUS_X = 100.0f, MAX_RADIUS_Y = 100.0f;                         /* :85-86 */
+  const float GRID_RES_X = 2.0f * MAX_RADIUS_X / NUM_GRID_X, GRID_RES_Y = 2.0f * MAX_RADIUS_Y / NUM_GRID_Y;   /* :87-88 */
+  const int MIN_GRID_POINTS_SIZE = 20;                                              /* :90 */
+  int *cell = (int *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int));
+  int cnt[100] = {0};
+  for (int64_t i = 0; i < n; i++) {
+    cell[i] = -1;
+    if (label[i] == 0) continue;                                                    /* :99-101 */
+    int grid_x = x86_cvtt((double)roundf((x[i] + MAX_RADIUS_X) / GRID_RES_X));      /* :104 */
+    int grid_y = x86_cvtt((double)roundf((y[i] + MAX_RADIUS_Y) / GRID_RES_Y));      /* :105 */
+    if (grid_x < 0 || grid_x >= NUM_GRID_X || grid_y < 0 || grid_y >= NUM_GRID_Y) continue;   /* :107-109 */
+    cell[i] = grid_x * NUM_GRID_Y + grid_y; cnt[cell[i]]++;
+  }
+  top_item *items = (top_item *)malloc((size_t)(n > 0 ? n : 1) * sizeof(top_item));
+  int64_t m = 0;
+  for (int c = 0; c < NUM_GRID_X * NUM_GRID_Y; c++) {                               /* :116-117 */
+    int num_points_in_grid = cnt[c];
+    int num_points_needed = x86_cvtt((double)roundf(0.2f * (float)num_points_in_grid));   /* :123 */
+    if (num_points_in_grid < MIN_GRID_POINTS_SIZE) continue;                        /* :124-126 */
+    int k = 0;
+    for (int64_t i = 0; i < n; i++) if (cell[i] == c) { items[k].z = z[i]; items[k].idx = (int)i; k++; }
+    qsort(items, (size_t)k, sizeof(top_item), top_cmp);                             /* :129-132 */
+    for (int j = 0; j < num_points_needed; j++) {                                   /* :134-139 */
+      out_x[m] = x[items[j].idx]; out_y[m] = y[items[j].idx]; out_index[m] = (uint32_t)items[j].idx; m++;
+    }
+  }
+  free(items); free(cell);
+  return m;
+}
+
 /* Exposed for tests: the float libm the oracle was built against. */
 ORACLE_API float oracle_atan2f(float y, float x) { return atan2f(y, x); }
 ORACLE_API float oracle_angle_deg(float dz, float dx, float dy) {

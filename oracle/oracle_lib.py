@@ -206,6 +206,18 @@ def project_oxford(x, y, z):
     return x, z, row, col
 
 
+def top_flatten(x, y, z, label):
+    """extractTopAndFlatten (TopPartRegistration.cpp:79-141) -> (out_x, out_y, source_index)."""
+    x, px = _f(x); y, py = _f(y); z, pz = _f(z)
+    label = np.ascontiguousarray(label, np.int16)
+    n = len(x)
+    ox = np.empty(max(n, 1), np.float32); oy = np.empty(max(n, 1), np.float32); oi = np.empty(max(n, 1), np.uint32)
+    f = lib().oracle_top_flatten
+    f.restype = C.c_int64
+    m = f(C.c_int64(n), px, py, pz, _p(label, C.c_int16), _p(ox, C.c_float), _p(oy, C.c_float), _p(oi, C.c_uint32))
+    return ox[:m].copy(), oy[:m].copy(), oi[:m].copy()
+
+
 # ---- reference KD-tree (oracle/_ref) ---------------------------------------------------------------
 def ref_knn_many(pts, qs, k):
     r = ref_lib()

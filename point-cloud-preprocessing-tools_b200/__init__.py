@@ -87,7 +87,7 @@ EXPORTS = ["bevgen_sensor_params", "bevgen_create", "bevgen_destroy", "bevgen_la
            "bevgen_host_free", "bevgen_process_host", "bevgen_process_device", "bevgen_sync", "bevgen_submit",
            "bevgen_collect", "bevgen_select_major", "bevgen_labels", "bevgen_cloud_manip", "bevgen_set_profiling",
            "bevgen_stage_ms", "bevgen_kernel_launches", "bevgen_compute_stream", "bevgen_stage_name",
-           "bevgen_debug_atan2f", "bevgen_pcd_record_layout", "bevgen_process_packed_host", "bevgen_project"]
+           "bevgen_debug_atan2f", "bevgen_pcd_record_layout", "bevgen_process_packed_host", "bevgen_project", "bevgen_top_flatten"]
 
 
 def build(verbose=False):
@@ -306,6 +306,16 @@ class BevGen:
         row = np.empty(n, np.uint16); col = np.empty(n, np.uint16)
         _ck(lib().bevgen_project(self._ctx, C.c_int(kind), C.c_int64(n), _ptr(x), _ptr(y), _ptr(z), _ptr(row), _ptr(col)))
         return dict(x=x, y=y, z=z, row=row, col=col)
+
+    # ---- extractTopAndFlatten -----------------------------------------------------------------------------------
+    def top_flatten(self, x, y, z, label):
+        """TopPartRegistration.cpp:79-141 -> (out_x, out_y, source_index)."""
+        x = _as(x, np.float32); y = _as(y, np.float32); z = _as(z, np.float32); label = _as(label, np.int16)
+        n = len(x)
+        ox = np.empty(max(n, 1), np.float32); oy = np.empty(max(n, 1), np.float32); oi = np.empty(max(n, 1), np.uint32)
+        m = C.c_int64(0)
+        _ck(lib().bevgen_top_flatten(self._ctx, C.c_int64(n), _ptr(x), _ptr(y), _ptr(z), _ptr(label), _ptr(ox), _ptr(oy), _ptr(oi), C.byref(m)))
+        return ox[:m.value].copy(), oy[:m.value].copy(), oi[:m.value].copy()
 
     # ---- introspection ----------------------------------------------------------------------------------------
     def set_profiling(self, on):

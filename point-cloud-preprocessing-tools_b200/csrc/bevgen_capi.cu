@@ -764,6 +764,53 @@ extern "C" int bevgen_project(bevgen_ctx* c, int kind, int64_t n, float* x, cons
   return 0;
 }
 
+// ---- extractTopAndFlatten ---------------------------------------------------------------------------
+extern "C" int bevgen_top_flatten(bevgen_ctx* c, int64_t n64, const float* x, const float* y, const float* z, const int16_t* label,
+                                  float* out_x, float* out_y, uint32_t* out_index, int64_t* n_out) {
+  if (!c || !x || !y || !z || !label || !out_x || !out_y || !n_out) return fail("bevgen_top_flatten: null argument");
+  if (n64 < 0 || n64 > (1 << 28)) return fail("bevgen_top_flatten: n out of range");
+  *n_out = 0;
+  if (n64 == 0) return 0;
+  const int n = (int)n64;
+  CK(cudaSetDevice(c->device));
+  const int n_tiles = (n + RS_TILE - 1) / RS_TILE;
+  const size_t np = (size_t)n;
+  if (tmp_reserve(c, 3 * Carver::pad(np * 4) + Carver::pad(np * 2) + 2 * Carver::pad(np * 8) + 2 * Carver::pad(np * 4) +
+                         Carver::pad((size_t)256 * n_tiles * 4) + 3 * Carver::pad(np * 4) + 4 * Carver::pad(TOP_CELLS * 4) + 256)) return -1;
+  Carver cv{c->tmp};
+  float* dx = cv.take<float>(np); float* dy = cv.take<float>(np); float* dz = cv.take<float>(np); int16_t* dl = cv.take<int16_t>(np);
+  uint64_t* k0 = cv.take<uint64_t>(np); uint64_t* k1 = cv.take<uint64_t>(np);
+  uint32_t* v0 = cv.take<uint32_t>(np); uint32_t* v1 = cv.take<uint32_t>(np);
+  uint32_t* hist = cv.take<uint32_t>((size_t)256 * n_tiles);
+  float* ox = cv.take<float>(np); float* oy = cv.take<float>(np); uint32_t* oi = cv.take<uint32_t>(np);
+  int* cstart = cv.take<int>(TOP_CELLS); int* cquota = cv.take<int>(TOP_CELLS); int* cout_ = cv.take<int>(TOP_CELLS); int* dn = cv.take<int>(1);
+  cudaStream_t st = c->s_comp;
+  CK(cudaMemcpyAsync(dx, x, np * 4, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(dy, y, np * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dz, z, np * 4, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(dl, label, np * 2, cudaMemcpyHostToDevice, st));
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  k_top_keys<<<nb, 256, 0, st>>>(n, dx, dy, dz, dl, k0, v0);
+  c->launches++;
+  for (int pass = 0; pass < 5; pass++) {       // 32 bits of height, then the 8 bits of the cell: stable, so ties keep input order
+    k_rs_hist<<<n_tiles, RS_T, 0, st>>>(n, pass * 8, k0, hist, n_tiles);
+    k_rs_scan<<<1, 1024, 0, st>>>(256 * n_tiles, hist);
+    k_rs_scatter<<<n_tiles, RS_T, 0, st>>>(n, pass * 8, k0, v0, hist, n_tiles, k1, v1);
+    std::swap(k0, k1); std::swap(v0, v1);
+    c->launches += 3;
+  }
+  k_top_cells<<<1, 128, 0, st>>>(n, k0, cstart, cquota, cout_, dn);
+  k_top_gather<<<nb, 256, 0, st>>>(n, k0, v0, cstart, cquota, cout_, dx, dy, ox, oy, oi);
+  CK(cudaGetLastError()); c->launches += 2;
+  int m = 0;
+  CK(cudaMemcpyAsync(&m, dn, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (m > 0) {
+    CK(cudaMemcpy(out_x, ox, (size_t)m * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(out_y, oy, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    if (out_index) CK(cudaMemcpy(out_index, oi, (size_t)m * 4, cudaMemcpyDeviceToHost));
+  }
+  *n_out = m;
+  return 0;
+}
+
 // ---- introspection ----------------------------------------------------------------------------------------------
 extern "C" int bevgen_set_profiling(bevgen_ctx* c, int on) {
   if (!c) return fail("null ctx");

@@ -1317,4 +1317,153 @@ __global__ void __launch_bounds__(256) k_cloud_manip(int64_t n, Xform xf, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// extractTopAndFlatten — TopPartRegistration.cpp:79-141 (same code in BatchTopPartRegistration.cpp:90):
+// non-ground points are binned into a 10 x 10 grid of 20 m cells (grid = round((p + 100.0f) / 20.0f), valid 0..9);
+// every cell with at least 20 points keeps its round(0.2f * count) highest points; the output lists them cell after
+// cell (x major), highest first, flattened to z = 0.  std::sort's order among equal heights is unspecified; here equal
+// heights keep their input order.
+// A segmented selection = one stable LSD radix sort of 40-bit keys (cell : 8 | ~orderable(z) : 32), values = point
+// indices in input order, 5 passes of 8 bits; each pass = per-tile digit histogram, scan of the [digit][tile] table,
+// stable scatter (rank inside a tile = rounds of 256 elements in thread order: match_any inside the warp + per-warp
+// digit counts).  Then per cell: bounds by binary search, quota, prefix over the 100 cells, gather.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TOP_GRID = 10, TOP_CELLS = TOP_GRID * TOP_GRID, TOP_MIN_PTS = 20;
+constexpr int RS_T = 256, RS_ITEMS = 8, RS_TILE = RS_T * RS_ITEMS;   // 2048 keys per tile
+constexpr uint64_t TOP_INVALID = 0xFFull << 32;                       // cell 255: sorts after every real cell
+
+__device__ __forceinline__ int top_axis(float p) {                    // round((p + 100.0f) / 20.0f) -> int (:104-105)
+  const float g = roundf(__fdiv_rn(__fadd_rn(p, 100.0f), 20.0f));
+  return (g > -2147483904.0f && g < 2147483648.0f) ? __float2int_rz(g) : INT32_MIN;
+}
+
+__global__ void __launch_bounds__(256) k_top_keys(int n, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
+                                                   const int16_t* __restrict__ label, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  uint64_t k = TOP_INVALID;
+  if (label[i] != 0) {                                                // :99-101
+    const int gx = top_axis(x[i]), gy = top_axis(y[i]);
+    if (gx >= 0 && gx < TOP_GRID && gy >= 0 && gy < TOP_GRID) {       // :107-109
+      float zz = z[i];
+      if (zz == 0.0f) zz = 0.0f;                                      // -0 and +0 compare equal in the reference's comparator
+      uint32_t u = __float_as_uint(zz);
+      u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);                 // order-preserving: larger float -> larger unsigned
+      k = ((uint64_t)(gx * TOP_GRID + gy) << 32) | (uint32_t)~u;      // descending height = ascending key
+    }
+  }
+  keys[i] = k; vals[i] = (uint32_t)i;
+}
+
+// digit histogram of every tile: hist[digit * n_tiles + tile].  grid n_tiles, block RS_T.
+__global__ void __launch_bounds__(RS_T) k_rs_hist(int n, int shift, const uint64_t* __restrict__ keys, uint32_t* __restrict__ hist, int n_tiles) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * RS_TILE;
+  for (int j = 0; j < RS_ITEMS; j++) {
+    const int i = base + j * RS_T + threadIdx.x;
+    if (i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of the whole table in place (digit-major, tile-minor = the order of a stable sort).  grid 1, block 1024.
+__global__ void __launch_bounds__(1024) k_rs_scan(int m, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int b = 0; b < m; b += 1024) {
+    const int i = b + tid;
+    const uint32_t v = i < m ? hist[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+    for (int w = 0; w < 32; w++) { const uint32_t c = s_warp[w]; if (w < wid) wbase += c; total += c; }
+    const uint32_t carry = s_carry;
+    if (i < m) hist[i] = carry + wbase + incl - v;
+    __syncthreads();
+    if (tid == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+}
+
+// stable scatter of one tile.  grid n_tiles, block RS_T.
+__global__ void __launch_bounds__(RS_T) k_rs_scatter(int n, int shift, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                      const uint32_t* __restrict__ hist, int n_tiles, uint64_t* __restrict__ keys_out,
+                                                      uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t s_run[256];              // elements of each digit placed by earlier rounds of this tile
+  __shared__ uint16_t s_wc[RS_T / 32][256];    // this round: per-warp count of each digit
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  s_run[tid] = hist[(size_t)tid * n_tiles + blockIdx.x];               // global position of the tile's first element of digit `tid`
+  const int base = blockIdx.x * RS_TILE;
+  for (int j = 0; j < RS_ITEMS; j++) {
+    for (int q = tid; q < (RS_T / 32) * 256; q += RS_T) (&s_wc[0][0])[q] = 0;
+    __syncthreads();
+    const int i = base + j * RS_T + tid;
+    const bool on = i < n;
+    uint64_t k = 0; uint32_t v = 0; unsigned d = 256u + lane;          // inactive lanes: private pseudo-digits
+    if (on) { k = keys[i]; v = vals[i]; d = (unsigned)(k >> shift) & 255u; }
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const unsigned below = __popc(peers & ((1u << lane) - 1u));
+    if (on && below == 0) s_wc[wid][d] = (uint16_t)__popc(peers);     // the group's lowest lane publishes the warp's count
+    __syncthreads();
+    if (on) {
+      uint32_t pos = s_run[d] + below;
+      for (int w = 0; w < wid; w++) pos += s_wc[w][d];
+      keys_out[pos] = k; vals_out[pos] = v;
+    }
+    __syncthreads();
+    {                                                                  // digit `tid`: advance by this round's total
+      uint32_t t = 0;
+#pragma unroll
+      for (int w = 0; w < RS_T / 32; w++) t += s_wc[w][tid];
+      s_run[tid] += t;
+    }
+    __syncthreads();
+  }
+}
+
+// per cell: [start, end) in the sorted keys, quota = round(0.2f * count) (0 below 20 points), output offsets.  grid 1, block 128.
+__global__ void __launch_bounds__(128) k_top_cells(int n, const uint64_t* __restrict__ keys, int* __restrict__ cell_start,
+                                                    int* __restrict__ cell_quota, int* __restrict__ cell_out, int* __restrict__ n_out) {
+  __shared__ int s_q[TOP_CELLS];
+  const int c = threadIdx.x;
+  if (c < TOP_CELLS) {
+    auto lower = [&](uint64_t key) { int lo = 0, hi = n; while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; } return lo; };
+    const int st = lower((uint64_t)c << 32), en = lower((uint64_t)(c + 1) << 32);
+    const int cnt = en - st;
+    int need = __float2int_rz(roundf(__fmul_rn(0.2f, (float)cnt)));     // :123 (computed before the size test)
+    if (cnt < TOP_MIN_PTS) need = 0;                                     // :124-126
+    cell_start[c] = st; cell_quota[c] = need; s_q[c] = need;
+  }
+  __syncthreads();
+  if (c == 0) {
+    int run = 0;
+    for (int k = 0; k < TOP_CELLS; k++) { cell_out[k] = run; run += s_q[k]; }   // cells in (grid_x, grid_y) order (:116-117)
+    *n_out = run;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_top_gather(int n, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                     const int* __restrict__ cell_start, const int* __restrict__ cell_quota,
+                                                     const int* __restrict__ cell_out, const float* __restrict__ x, const float* __restrict__ y,
+                                                     float* __restrict__ ox, float* __restrict__ oy, uint32_t* __restrict__ oidx) {
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= n) return;
+  const unsigned c = (unsigned)(keys[p] >> 32);
+  if (c >= (unsigned)TOP_CELLS) return;
+  const int j = p - cell_start[c];
+  if (j >= cell_quota[c]) return;
+  const uint32_t i = vals[p];
+  const int o = cell_out[c] + j;
+  ox[o] = x[i]; oy[o] = y[i]; oidx[o] = i;                               // flat_point.z = 0 (:135)
+}
+
 }  // namespace bevgen

@@ -410,3 +410,27 @@ def test_kitti_ring_detection_bit_exact(gens, synth, O, seed, kw):
     assert row[0] == 0xFFFF and placed.sum() > 1000 and col[placed].max() < 2083 and row[placed].max() < 64
     if kw.get("n_rings", 64) == 64 and not kw.get("start_negative"):
         assert row[placed].max() == 61          # 64 rings, two short ones merged into their successors
+
+
+def test_top_flatten_segmented_selection(gens, synth, O):
+    """extractTopAndFlatten on the GPU (stable radix sort by cell / height + per-cell quota) against the
+    oracle: a real ground-removed frame, a wide random cloud with many equal heights (ties keep input order), tiny inputs."""
+    g = gens("HDL_64E")
+    sp = O.sensor("HDL_64E")
+    f = synth.make_frame("HDL_64E", 77)
+    oc = O.order(sp, *[f[k] for k in FIELDS])
+    lab = O.mark_ground(sp, oc)[0]                                   # what non_ground_point_cloud/*.pcd holds
+    cases = [(oc["x"], oc["y"], oc["z"], lab)]
+    rng = np.random.default_rng(21)
+    n = 300_007
+    cases.append((rng.uniform(-130, 130, n).astype(np.float32), rng.uniform(-130, 130, n).astype(np.float32),
+                  (rng.integers(-8, 40, n) * 0.25).astype(np.float32), rng.integers(-2, 3, n).astype(np.int16)))   # quantised heights: ties
+    cases.append((np.zeros(25, np.float32), np.zeros(25, np.float32), np.r_[np.arange(24, dtype=np.float32), -0.0].astype(np.float32), np.ones(25, np.int16)))
+    cases.append((np.zeros(0, np.float32),) * 3 + (np.zeros(0, np.int16),))
+    for x, y, z, l in cases:
+        wx, wy, wi = O.top_flatten(x, y, z, l)
+        gx, gy, gi = g.top_flatten(x, y, z, l)
+        assert len(gi) == len(wi), (len(gi), len(wi))
+        assert np.array_equal(gi, wi), int((gi != wi).sum())
+        assert np.array_equal(gx.view(np.uint32), wx.view(np.uint32)) and np.array_equal(gy.view(np.uint32), wy.view(np.uint32))
+    assert len(O.top_flatten(*cases[0])[2]) > 1000 and len(O.top_flatten(*cases[1])[2]) > 10000

@@ -333,3 +333,26 @@ def test_kitti_ring_detection_rule(O):
     x, y = scan(5, 50, first_az=-10.0)        # starts below 0: nothing is placed before the first crossing, which is always taken
     row, _ = O.project_kitti(x, y)
     assert set(row[:6]) == {0xFFFF} and set(row[6:]) == {0}
+
+
+def test_top_flatten_quota_and_order(O):
+    """extractTopAndFlatten (TopPartRegistration.cpp:79-141): cell = round((p + 100) / 20), cells with < 20 points give
+    nothing, others their round(0.2f * count) highest points, highest first; label 0 skipped; cells in x-major order."""
+    # cell (5, 5): 30 points around the origin with heights 0..29 -> 6 highest = 29..24; five of them are label 0 -> 25 points -> 5
+    n = 30
+    x = np.full(n, 1.0, np.float32); y = np.full(n, -2.0, np.float32); z = np.arange(n, dtype=np.float32)
+    lab = np.full(n, -2, np.int16)
+    ox, oy, oi = O.top_flatten(x, y, z, lab)
+    assert oi.tolist() == [29, 28, 27, 26, 25, 24] and set(ox) == {1.0} and set(oy) == {-2.0}
+    lab[[29, 27, 0, 1, 2]] = 0
+    assert O.top_flatten(x, y, z, lab)[2].tolist() == [28, 26, 25, 24, 23]
+    # 19 points: below MIN_GRID_POINTS_SIZE
+    assert len(O.top_flatten(x[:19], y[:19], z[:19], np.full(19, 1, np.int16))[0]) == 0
+    # rounding of the cell index: x = -90.1 -> round(0.495) = 0, x = -89.9 -> round(0.505) = 1; x = 90 -> round(9.5) = 10: outside
+    xs = np.concatenate([np.full(20, -90.1), np.full(20, -89.9), np.full(20, 90.0)]).astype(np.float32)
+    ys = np.zeros(60, np.float32); zs = np.tile(np.arange(20, dtype=np.float32), 3); ls = np.ones(60, np.int16)
+    ox, oy, oi = O.top_flatten(xs, ys, zs, ls)
+    assert oi.tolist() == [19, 18, 17, 16, 39, 38, 37, 36]          # cell (0,5) then (1,5); the x = 90 points fall outside
+    # equal heights keep their input order (the stable choice among what std::sort may return)
+    zt = np.zeros(40, np.float32); zt[[7, 30]] = 5.0
+    assert O.top_flatten(np.zeros(40, np.float32), np.zeros(40, np.float32), zt, np.ones(40, np.int16))[2].tolist() == [7, 30, 0, 1, 2, 3, 4, 5]
