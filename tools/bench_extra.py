@@ -81,6 +81,13 @@ def main():
     t_m = wall(lambda: g.project(0, x, y), 5); t_o = wall(lambda: g.project(1, x, y, z), 5)
     print(json.dumps({"what": "bevgen_project, %d points (8 OS1-64 scans), host (pageable) arrays in/out, copies included" % n,
                       "Mpts_per_s": {"mulran": n / t_m / 1e6, "oxford": n / t_o / 1e6}}), flush=True)
+    # ---- 8(f)-4: extractTopAndFlatten on one ground-removed HDL_64E cloud (S slots), host arrays in/out -----------------
+    S = g.S
+    tx = rng.uniform(-100, 100, S).astype(np.float32); ty = rng.uniform(-100, 100, S).astype(np.float32)
+    tz = rng.uniform(-2, 10, S).astype(np.float32); tl = (rng.random(S) < 0.5).astype(np.int16)
+    t_t = wall(lambda: g.top_flatten(tx, ty, tz, tl), 5)
+    print(json.dumps({"what": "bevgen_top_flatten, %d slots (one HDL_64E cloud), host (pageable) arrays in/out, copies included" % S,
+                      "clouds_per_s": 1 / t_t, "Mpts_per_s": S / t_t / 1e6}), flush=True)
     # ---- configs[4]: cloud_manip, 2 M points ------------------------------------------------------------------------------
     n = 2_000_000
     hot = rng.random(n) < 0.6
