@@ -62,34 +62,60 @@ def tile_batch(distinct, F):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML (nvidia_ml_py) answers in
+    well under a millisecond, so a 75 ms timed region still yields a dozen samples; `nvidia-smi` (50-100 ms per call) is the
+    fallback when the module or the query is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, dev):
         super().__init__(daemon=True)
-        self.dev, self.rows, self.stop_ev = dev, [], threading.Event()
+        self.dev, self.rows, self.stop_ev = dev, [], threading.Event()   # rows: (sm_mhz, max_mhz, {reasons})
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[dev]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else dev
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _nvml_sample(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(self.h))
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        return sm, self.max_mhz, {n for n, b in names.items() if mask & b}
+
+    def _smi_sample(self):
+        o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                           capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [c.strip() for c in o.split(",")]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        return float(r[1]), float(r[2]), {n for n, v in zip(names, r[5:9]) if v.lower().startswith("active")}
 
     def run(self):
         while not self.stop_ev.is_set():
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([c.strip() for c in o.split(",")])
+                self.rows.append(self._nvml_sample() if self.nv else self._smi_sample())
             except Exception:
-                pass
-            self.stop_ev.wait(0.2)
+                if self.nv:
+                    self.nv = None      # fall back to nvidia-smi
+                    continue
+            self.stop_ev.wait(0.004 if self.nv else 0.2)
 
     def summary(self):
         self.stop_ev.set(); self.join(timeout=6)
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][2]) if self.rows[0][2].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"]}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted(set().union(*[r[2] for r in self.rows]))
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows),
+                "source": "nvml" if self.nv else "nvidia-smi"}
 
 
 def algorithmic_bytes(sensor_S, n_in_total, F):

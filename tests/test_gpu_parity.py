@@ -347,6 +347,15 @@ def test_packed_records_deinterleave_on_gpu(gens, synth, O, pkg, kind):
     out["owner"] = pkg.owner_from_winner(out["winner"], batch["offsets"], np.asarray(batch["row"], np.uint16), np.asarray(batch["col"], np.uint16),
                                          g.params.horizon_scan, g.S)
     assert_same(out, ref, "packed " + kind)
+    # ragged input: an empty frame in the middle and a one-point frame at the end
+    fr = lambda f: {k: batch[k][batch["offsets"][f]:batch["offsets"][f + 1]] for k in FIELDS}
+    empty = {k: batch[k][:0] for k in FIELDS}
+    one = {k: batch[k][5:6] for k in FIELDS}
+    rag = cat_frames([fr(0), empty, fr(1), one])
+    out = g.process_packed_host(_pack_records(rag, lay, rng), rag["offsets"], lay)
+    out["owner"] = pkg.owner_from_winner(out["winner"], rag["offsets"], np.asarray(rag["row"], np.uint16), np.asarray(rag["col"], np.uint16),
+                                         g.params.horizon_scan, g.S)
+    assert_same(out, oracle_batch(O, sensor, rag), "packed ragged " + kind)
     with pytest.raises(pkg.BevgenError, match="offset outside"):
         g.process_packed_host(rec, batch["offsets"], pkg.RecordLayout(lay.stride, lay.stride - 2, 4, 8, -1, 12, 14, -1))   # x (f32) overruns the record
 
