@@ -298,8 +298,8 @@ static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
   }
   mark(3);
   {
-    dim3 g((sp.H + 127) / 128, w.nf);
-    k_ground_mark<<<g, 128, 0, st>>>(sp, w.sc->rec, w.sc->gkey, w.sc->gz, w.sc->cnt, w.sc->gsum);
+    dim3 g((sp.H + GM_T - 1) / GM_T, w.nf);
+    k_ground_mark<<<g, GM_T, 0, st>>>(sp, w.sc->rec, w.sc->gkey, w.sc->gz, w.sc->cnt, w.sc->gsum);
   }
   mark(4);
   CK(cudaGetLastError());
