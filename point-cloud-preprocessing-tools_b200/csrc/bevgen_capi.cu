@@ -278,8 +278,8 @@ static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
     uint32_t *occ = w.sc->occ, *cont = occ + (size_t)w.sc->frames * W, *cpre = cont + (size_t)w.sc->frames * W;
     k_order_winners<<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, row, col, occ, cont, cpre, w.sc->cwin, w.qbase, w.sc->cpt);
     mark(2);
-    dim3 g((std::max<int>(w.max_n, (int)S) + 255) / 256, w.nf);
-    k_order_scatter<<<g, 256, 0, st>>>(sp, c->xf, w.offs_d, w.frame0, c->cw_stride, x, y, z, it, row, col, lab, occ, cont, cpre, w.sc->cwin,
+    dim3 g((std::max<int>(w.max_n, (int)S) + SCAT_T - 1) / SCAT_T, w.nf);
+    k_order_scatter<<<g, SCAT_T, 0, st>>>(sp, c->xf, w.offs_d, w.frame0, c->cw_stride, x, y, z, it, row, col, lab, occ, cont, cpre, w.sc->cwin,
                                        w.sc->rec, w.out.wbits, w.qbase, w.sc->cpt);
     c->launches += 2;
   } else {   // range image too large for shared memory: claim table in global memory (two kernels + the winner bits)

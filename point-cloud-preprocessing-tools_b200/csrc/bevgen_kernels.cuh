@@ -430,7 +430,10 @@ __global__ void __launch_bounds__(256) k_winner_bits(SensorDev sp, const int64_t
 // rejected: with ~300 frames in flight the half-written sectors of `rec` are evicted before their second half
 // arrives (DRAM traffic 13.5 MB per frame).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int ORD_T = 512;
+#ifndef ORD_THREADS
+#define ORD_THREADS 512   // measured: 0.275 / 0.251 / 0.261 us per frame for 256 / 512 / 1024 threads
+#endif
+constexpr int ORD_T = ORD_THREADS;
 __host__ __device__ inline size_t ord_smem_bytes(int S) { return (((size_t)S + 31) / 32) * 4 * 2 + 256; }
 
 // 8 consecutive u16 as one 128-bit load: block v8 of the 16-byte aligned pointer.
@@ -526,8 +529,11 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
   scan(visit2);
 }
 
-// grid (ceil(max(max_n, S)/256), F), block 256.
-__global__ void __launch_bounds__(256) k_order_scatter(SensorDev sp, Xform xf, const int64_t* __restrict__ offs, int frame0, int cw_stride,
+// grid (ceil(max(max_n, S)/SCAT_T), F), block SCAT_T.
+#ifndef SCAT_T
+#define SCAT_T 128   // measured: 1.21 / 1.205 / 1.264 / 1.35 us per frame for 64 / 128 / 256 / 512 threads
+#endif
+__global__ void __launch_bounds__(SCAT_T) k_order_scatter(SensorDev sp, Xform xf, const int64_t* __restrict__ offs, int frame0, int cw_stride,
                                                         const float* __restrict__ x, const float* __restrict__ y,
                                                         const float* __restrict__ z, const float* __restrict__ inten,
                                                         const uint16_t* __restrict__ row, const uint16_t* __restrict__ col,
@@ -539,7 +545,7 @@ __global__ void __launch_bounds__(256) k_order_scatter(SensorDev sp, Xform xf, c
   const int f = blockIdx.y;
   const int64_t o = offs[f];
   const int n = (int)(offs[f + 1] - o);
-  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int i = blockIdx.x * SCAT_T + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const size_t fb = (size_t)f * sp.S;
   const int W = (sp.S + 31) >> 5;
@@ -769,8 +775,14 @@ constexpr int SEG_CAP = 4096;
 constexpr int SEGT = 512;
 constexpr int SMEM_SEG = SEG_CAP * 4 * 2 + NSECT * 4 + SEGT * 8 + 320 + SEG_CAP * 2 * 3 + (NSECT + 2) * 2;   // 84,264 B
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-constexpr int FOLD_AHEAD = 6;           // segments prefetched ahead of the chain in k_seg_fold
-constexpr int FOLD_STEP = 32;           // heights per step of a chain in k_seg_fold
+#ifndef FOLD_AHEAD_N
+#define FOLD_AHEAD_N 6   // measured flat between 3 and 12
+#endif
+#ifndef FOLD_STEP_N
+#define FOLD_STEP_N 32   // 16 is 10 % slower
+#endif
+constexpr int FOLD_AHEAD = FOLD_AHEAD_N;           // segments prefetched ahead of the chain in k_seg_fold
+constexpr int FOLD_STEP = FOLD_STEP_N;           // heights per step of a chain in k_seg_fold
 constexpr int FOLD_PASSES = 12;         // warps per frame in k_seg_fold (32 sectors each; more sectors wrap around)
 
 __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const uint4* __restrict__ gsum,
