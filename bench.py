@@ -169,8 +169,16 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout; stdout carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout when the first communicator is built; stdout must carry exactly one
+        # JSON line, so fd 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
 
     pkg, synth = load_pkg(), load_synth()
     F, Fe = args.frames, args.e2e_frames
