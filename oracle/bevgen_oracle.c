@@ -14,6 +14,12 @@
  *     BatchMultiBevGen.cpp:575-636  getKeyFrameLabel
  *     src/Utility.cpp:72-124        parseSensorType / getSensorParams
  *     CloudManip.cpp:79-109,119-128 saveAsMat / rigid transform (pcl::transformPointCloud)
+ *   widened rows, same status ("parity unpinned": no reference tests exist for them either):
+ *     BatchCloudManip.cpp:201-226                saveAsMat with the label filter (oracle_bvm)
+ *     MulranPointCloudSelect.cpp:112-126         row / col projection (oracle_project_mulran)
+ *     OxfordPointCloudSelect.cpp:201-219         row / col projection (oracle_project_oxford)
+ *     KittiPointCloudSelect.cpp:188-243          ring detection + column (oracle_project_kitti)
+ *     TopPartRegistration.cpp:79-141             extractTopAndFlatten (oracle_top_flatten)
  *
  * PARITY PIN STATUS: the reference ships no tests, golden vectors or fixtures for this path and its
  * translation unit cannot be compiled here (needs PCL, OpenCV C++, Eigen, Boost, VTK — all absent), so
