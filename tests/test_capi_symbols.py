@@ -54,3 +54,23 @@ def test_product_does_not_touch_the_oracle():
 def test_cuda_sources_target_sm100a():
     mk = open(os.path.join(ROOT, "point-cloud-preprocessing-tools_b200", "Makefile")).read()
     assert "arch=compute_100a,code=sm_100a" in mk and "--fmad=false" in mk and "use_fast_math" not in mk
+
+
+def test_clis_are_built_print_usage_and_have_no_cpu_fallback(tmp_path, pkg):
+    """The three host CLIs exist, print the reference's usage text and exit 1 without arguments
+    (BatchMultiBevGen.cpp:666-689, BatchCloudManip.cpp:271-274); on a box without a CUDA device they refuse to run."""
+    import subprocess
+    for path, usage in ((pkg.CLI_PATH, "[keyframes_root_dir] [sensor_type]"), (pkg.BATCH_CLOUD_MANIP_PATH, "<keyframes_root_dir>"),
+                        (pkg.CLOUD_MANIP_PATH, "<cloud.pcd> <tx> <ty> <tz> <theta_deg>")):
+        assert os.path.exists(path), path
+        r = subprocess.run([path], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 1 and usage in (r.stdout + r.stderr)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        root = str(tmp_path / "kf"); os.makedirs(os.path.join(root, "keyframe_point_cloud"))
+        r = subprocess.run([pkg.CLI_PATH, root, "HDL_64E"], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 1 and "no CUDA device (there is no CPU fallback)" in r.stderr
