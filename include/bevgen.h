@@ -183,9 +183,11 @@ BEVGEN_API int bevgen_top_flatten(bevgen_ctx *ctx, int64_t n, const float *x, co
 
 /* ---- introspection for bench / tests (no reference counterpart) ---------------------------------------------- */
 #define BEVGEN_N_STAGES 8
-/* Stage order: 0 clear, 1 order (claim), 2 order_fill (large range images only), 3 ground_mark, 4 sector_mean,
- * 5 finalize_bin_scatter, 6..7 reserved.  When profiling is enabled, process_device brackets every stage with CUDA events on the compute
- * stream; stage_ms returns the accumulated milliseconds and launch counts since the last reset. */
+/* Stage order: 0 clear, 1 order_winners (k_order_winners, or k_order_claim for range images too large for shared memory),
+ * 2 order_scatter (k_order_scatter, or k_order_fill + k_winner_bits), 3 ground_mark, 4 sector_mean (k_seg_build + k_seg_fold +
+ * the k_sector_mean fallback), 5 finalize_bin_scatter (k_finalize_bin, + k_float_bev when bvm is requested), 6..7 reserved.
+ * When profiling is enabled, process_device runs its waves on one stream and brackets every stage with CUDA events;
+ * stage_ms returns the accumulated milliseconds and launch counts since the last reset. */
 BEVGEN_API int bevgen_set_profiling(bevgen_ctx *ctx, int enabled);
 BEVGEN_API int bevgen_stage_ms(bevgen_ctx *ctx, float *ms /*[BEVGEN_N_STAGES]*/, int64_t *launches /*[BEVGEN_N_STAGES]*/);
 BEVGEN_API int64_t bevgen_kernel_launches(bevgen_ctx *ctx); /* total kernels launched by this context so far */
