@@ -173,6 +173,7 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
     return fail("bevgen_create: invalid sensor params (need n_scan - ground_upper_scan >= 2)");
   if ((int64_t)p->n_scan * p->horizon_scan > (1 << 24)) return fail("bevgen_create: range image too large");
   if (max_pts <= 0 || max_frames <= 0) return fail("bevgen_create: max_points_per_frame / max_frames_per_batch must be > 0");
+  if (max_frames > 65535) return fail("bevgen_create: max_frames_per_batch must be <= 65535 (frames are the y dimension of the launch grids)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("bevgen_create: no CUDA device (there is no CPU fallback)");
   if (device < 0 || device >= ndev) return fail("bevgen_create: bad device index");
