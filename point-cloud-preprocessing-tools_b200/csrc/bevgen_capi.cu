@@ -317,7 +317,7 @@ static int wave_sweep(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
   else
     k_seg_fold<false><<<dim3(w.nf, FOLD_PASSES), 32, 0, st>>>(c->sp, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->slow, w.sc->seg_start, w.sc->seg_len,
                                                               w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->avg);
-  k_sector_mean<<<w.nf, 32, NSECT * sizeof(float), st>>>(c->sp, w.sc->gkey, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->avg, w.sc->slow);
+  k_sector_mean<<<w.nf, 32, 2 * NSECT * sizeof(float), st>>>(c->sp, w.sc->gkey, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->avg, w.sc->slow);
   if (prof) cudaEventRecord(c->pev[5], st);
   CK(cudaGetLastError());
   c->launches += 3;

@@ -10,7 +10,7 @@
 //   rec   [f][S]  f32x4 ordered cloud: x, y, z, w = {label:16 | I==-1:1 | owned:1} — scratch, written once
 //   gkey  [f][S]  u16   sector id (row*50+col) of slots with ground_mat == 1 after loop 1, else 0xFFFF — scratch
 //   gz    [f][S]  f32   z of those slots (0 elsewhere)                       — scratch
-//   cnt   [f][3750] u32 ground points per sector;  avg [f][3750] f32 sector mean heights — scratch
+//   cnt   [f][3750] u32 zero-height ground slots per sector (the others are counted by the fold);  avg [f][3750] f32 sector mean heights — scratch
 //   label [f][S] i16, single [f][224*224] u8, multi [f][24][224*224] u8      — outputs
 #pragma once
 #include <cuda_runtime.h>
@@ -633,17 +633,11 @@ __global__ void __launch_bounds__(GM_T) k_ground_mark(SensorDev sp, const float4
     unsigned key = NO_KEY;
     if (gm1) key = sector_of(p.x, p.y);
     if (act) { *gk = (uint16_t)key; *gzp = gm1 ? p.z : 0.0f; }
-    // loop 2's count (:205) is order-free: one atomicAdd per run of equal sectors along the row (neighbouring
-    // columns of a ring fall into the same 2 m sector for long stretches)
     const unsigned k2 = act ? key : NO_KEY;
-    const unsigned prev = __shfl_up_sync(0xffffffffu, k2, 1);
-    const bool head = lane == 0 || prev != k2;
-    const unsigned heads = __ballot_sync(0xffffffffu, head);
-    if (head && k2 != NO_KEY) {
-      const unsigned above = heads & ~((2u << lane) - 1u);            // heads strictly above this lane
-      const int nxt = above ? __ffs(above) - 1 : 32;
-      atomicAdd(&cntf[key], (uint32_t)(nxt - lane));
-    }
+    // loop 2's count (:205) is order-free and split in two: ground slots with a non-zero height are counted by the fold
+    // (they are exactly the non-zero entries of gz inside the sector's segments); the rare ground slots of height 0
+    // (pairs of empty slots, :173 atan2(0,0) = 0) take part in no segment and are counted here.
+    if (k2 != NO_KEY && !(p.z != 0.0f)) atomicAdd(&cntf[key], 1u);
     // Loop 2's float sums (:198) only change when a non-zero height is added, so the "participating" slots are the
     // ground slots with z != 0 (NaN participates).  pm = participating lanes, hm = lanes whose sector differs from the
     // previous participating lane of this group, fk / lk = sector of the first / last participating lane.
@@ -685,19 +679,20 @@ __global__ void __launch_bounds__(GM_T) k_ground_mark(SensorDev sp, const float4
 // ground_grid_avg_heights[sector] += z serially in row-major slot order: float addition is not associative, so the
 // per-sector order must be kept.  One warp sweeps one frame in slot order, 32 slots per step; inside a step each
 // sector group (match_any) is folded sequentially by its lowest lane from shared-memory accumulators.  Adding
-// +-0 never changes a (never -0) sum, so empty/zero-height ground slots are skipped; the count is order-free and
-// comes from K1.  num = 0.01f + 1 + 1 ... is a pure function of the count: cnt_lut[n].
-// grid F, block 32, dynamic smem NSECT*4.
+// +-0 never changes a (never -0) sum, so empty/zero-height ground slots are skipped; the count is order-free: K1
+// counted the zero-height ground slots, the others are counted here.  num = 0.01f + 1 + 1 ... is a pure function of the count: cnt_lut[n].
+// grid F, block 32, dynamic smem 2*NSECT*4.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t* __restrict__ gkey,
                                                      const float* __restrict__ gz, const uint32_t* __restrict__ cnt,
                                                      const float* __restrict__ cnt_lut, float* __restrict__ avg,
                                                      const uint32_t* __restrict__ slow_flag) {
-  extern __shared__ float ssum[];                 // [NSECT] running sums of this frame
+  extern __shared__ float ssum[];                 // [NSECT] running sums of this frame, then [NSECT] counts of non-zero heights
+  uint32_t* scnt = reinterpret_cast<uint32_t*>(ssum + NSECT);
   if (slow_flag && !slow_flag[blockIdx.x]) return; // the segment form (k_sector_mean_seg) already did this frame
   __shared__ __align__(16) float zb[2][32];       // the current step's 32 heights (double-buffered)
   const int f = blockIdx.x, lane = threadIdx.x;
-  for (int i = lane; i < NSECT; i += 32) ssum[i] = 0.0f;
+  for (int i = lane; i < NSECT; i += 32) { ssum[i] = 0.0f; scnt[i] = 0u; }
   __syncwarp();
   const size_t fb = (size_t)f * sp.S;
   const uint16_t* K = gkey + fb;
@@ -748,13 +743,14 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
         acc = __fadd_rn(acc, (mine & (1u << (4 * q + 2))) ? v[q].z : 0.0f);
         acc = __fadd_rn(acc, (mine & (1u << (4 * q + 3))) ? v[q].w : 0.0f);
       }
-      if (leader) ssum[k[u]] = acc;
+      const unsigned nzm = __ballot_sync(0xffffffffu, valid && zz[u] != 0.0f);
+      if (leader) { ssum[k[u]] = acc; scnt[k[u]] += (unsigned)__popc(peers & nzm); }
       buf ^= 1;
       __syncwarp();
     }
   }
   for (int i = lane; i < NSECT; i += 32)
-    avg[(size_t)f * NSECT + i] = __fdiv_rn(ssum[i], cnt_lut[cnt[(size_t)f * NSECT + i]]);   // :210 IEEE divide
+    avg[(size_t)f * NSECT + i] = __fdiv_rn(ssum[i], cnt_lut[cnt[(size_t)f * NSECT + i] + scnt[i]]);   // :210 IEEE divide
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -998,6 +994,7 @@ __global__ void __launch_bounds__(32) k_seg_fold(SensorDev sp, const float* __re
     const unsigned d = kdesc[(size_t)f * NSECT + k];
     unsigned cur = d >> 16; const unsigned endseg = cur + (d & 0xFFFFu);
     float acc = 0.0f;
+    unsigned nz = 0u;                                               // ground slots of this sector with a non-zero height (:205)
     unsigned j = SS[cur], hi = j + SL[cur];
     unsigned st2 = 0u, en2 = 0u;                                    // the following segment, fetched one segment ahead
     if (cur + 1 < endseg) { st2 = SS[cur + 1]; en2 = st2 + SL[cur + 1]; }
@@ -1022,7 +1019,7 @@ __global__ void __launch_bounds__(32) k_seg_fold(SensorDev sp, const float* __re
         for (int u = 0; u < FOLD_STEP; u++) { const unsigned q = j + u; v[u] = q <= hi ? Z[q] : 0.0f; }
       }
 #pragma unroll
-      for (int u = 0; u < FOLD_STEP; u++) acc = __fadd_rn(acc, v[u]);
+      for (int u = 0; u < FOLD_STEP; u++) { acc = __fadd_rn(acc, v[u]); nz += v[u] != 0.0f ? 1u : 0u; }
       j = jb + FOLD_STEP;
       if (j <= hi) { if (j + 3 * FOLD_STEP <= hi) prefetch_l1(Z + j + 3 * FOLD_STEP); continue; }
       cur++;
@@ -1031,7 +1028,7 @@ __global__ void __launch_bounds__(32) k_seg_fold(SensorDev sp, const float* __re
       if (cur + 1 < endseg) { st2 = SS[cur + 1]; en2 = st2 + SL[cur + 1]; }
       if (cur + FOLD_AHEAD < endseg) prefetch_l1(Z + SS[cur + FOLD_AHEAD]);   // the chain is latency bound: pull later segments in early
     }
-    avg[(size_t)f * NSECT + k] = __fdiv_rn(acc, cnt_lut[cnt[(size_t)f * NSECT + k]]);   // :210
+    avg[(size_t)f * NSECT + k] = __fdiv_rn(acc, cnt_lut[cnt[(size_t)f * NSECT + k] + nz]);   // :210
   }
 }
 
