@@ -234,3 +234,169 @@ def ref_knn(pts, q, k):
     idx = np.zeros(k, np.uint64); d = np.zeros(k, np.float32)
     r.ref_knn(_p(pts, C.c_float), C.c_int(len(pts)), _p(q, C.c_float), C.c_int(k), _p(idx, C.c_uint64), _p(d, C.c_float))
     return idx.astype(np.int64), d
+
+
+# ---- the reference's own translation unit, compiled against oracle/stub (oracle/_ref/libbevgen_ref*.so) -----------
+def ref_bevgen_lib(double_libm=False):
+    """oracle/_ref/libbevgen_ref.so (or _dbl: built with -DSTUB_NO_MATH_H so atan2/sqrt bind to the C double functions),
+    or None when it was never built (it is built here, where /root/reference exists, and travels to the GPU box)."""
+    key = "refbev_dbl" if double_libm else "refbev"
+    if key not in _libs:
+        p = os.path.join(_HERE, "_ref", "libbevgen_ref_dbl.so" if double_libm else "libbevgen_ref.so")
+        if not os.path.exists(p):
+            return None
+        L = C.CDLL(p)
+        L.ref_get_distance.restype = C.c_float
+        _libs[key] = L
+    return _libs[key]
+
+
+def ref_math_overloads(double_libm=False):
+    L = ref_bevgen_lib(double_libm)
+    a = [C.c_int() for _ in range(4)]
+    L.ref_math_overloads(*[C.byref(v) for v in a])
+    return dict(zip(("atan2", "sqrt", "abs", "round"), ["double" if v.value == 1 else "float" if v.value == 0 else "int" for v in a]))
+
+
+def ref_frame(sensor_name, x, y, z, intensity, row, col, label, t=None, double_libm=False, want_csv=False):
+    """One frame through getOrderedCloud -> markGroundPoints -> computeAndSaveMultiBev -> computeAndSaveSingleBev as the
+    reference's own source computes them.  Returns dict(x,y,z,intensity,row,col,t,label [S] = the ordered cloud,
+    ground_mat [N,H] i8, single, multi, bin_equal, csv)."""
+    L = ref_bevgen_lib(double_libm)
+    sp4 = (C.c_int32 * 4)()
+    if L.ref_set_sensor(sensor_name.encode(), sp4) != 0:
+        raise ValueError("Unknown sensor type: %s!" % sensor_name)
+    N, H = sp4[0], sp4[1]
+    S = N * H
+    x, px = _f(x); y, py = _f(y); z, pz = _f(z); it, pi = _f(intensity)
+    row = np.ascontiguousarray(row, np.uint16); col = np.ascontiguousarray(col, np.uint16)
+    label = np.ascontiguousarray(label, np.int16)
+    tt = None if t is None else np.ascontiguousarray(t, np.uint32)
+    o = dict(x=np.empty(S, np.float32), y=np.empty(S, np.float32), z=np.empty(S, np.float32), intensity=np.empty(S, np.float32),
+             row=np.empty(S, np.uint16), col=np.empty(S, np.uint16), t=np.empty(S, np.uint32), label=np.empty(S, np.int16),
+             ground_mat=np.empty(S, np.int8), single=np.empty(GRID * GRID, np.uint8), multi=np.empty(LAYERS * GRID * GRID, np.uint8))
+    beq = C.c_int(0); clen = C.c_int64(0)
+    cap = 400000 if want_csv else 0
+    cbuf = C.create_string_buffer(cap) if want_csv else None
+    rc = L.ref_frame(C.c_int64(len(x)), px, py, pz, pi, _p(row, C.c_uint16), _p(col, C.c_uint16),
+                     _p(tt, C.c_uint32) if tt is not None else None, _p(label, C.c_int16),
+                     _p(o["x"], C.c_float), _p(o["y"], C.c_float), _p(o["z"], C.c_float), _p(o["intensity"], C.c_float),
+                     _p(o["row"], C.c_uint16), _p(o["col"], C.c_uint16), _p(o["t"], C.c_uint32), _p(o["label"], C.c_int16),
+                     _p(o["ground_mat"], C.c_int8), _p(o["single"], C.c_uint8), _p(o["multi"], C.c_uint8),
+                     C.byref(beq), cbuf, C.c_int64(cap), C.byref(clen))
+    if rc != S:
+        raise RuntimeError("ref_frame returned %d (expected S=%d)" % (rc, S))
+    o["ground_mat"] = o["ground_mat"].reshape(N, H)
+    o["single"] = o["single"].reshape(GRID, GRID); o["multi"] = o["multi"].reshape(LAYERS, GRID, GRID)
+    o["bin_equal"] = bool(beq.value)
+    o["csv"] = cbuf.raw[:clen.value] if want_csv and clen.value > 0 else None
+    return o
+
+
+def ref_select_and_label(xyz, want_labels=True):
+    """selectMajorFrames + getKeyFrameLabel of the reference's own source -> (major_idx, labels [K,M] or None).
+    (The reference prints its progress lines to stdout.)"""
+    L = ref_bevgen_lib()
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    K = len(xyz)
+    mi = np.empty(max(K, 1), np.int32)
+    M = L.ref_labels(C.c_int(K), _p(xyz, C.c_float), _p(mi, C.c_int32), None)
+    if not want_labels:
+        return mi[:M].copy(), None
+    lab = np.empty((K, M), np.float32)
+    L.ref_labels(C.c_int(K), _p(xyz, C.c_float), _p(mi, C.c_int32), _p(lab, C.c_float))
+    return mi[:M].copy(), lab
+
+
+def ref_read_poses(path, cap=1 << 20):
+    L = ref_bevgen_lib()
+    xyz = np.zeros((cap, 3), np.float32)
+    n = L.ref_read_poses(path.encode(), _p(xyz, C.c_float), C.c_int(cap))
+    return xyz[:n].copy()
+
+
+def ref_list_pcd(d):
+    L = ref_bevgen_lib()
+    buf = C.create_string_buffer(1 << 22)
+    n = L.ref_list_pcd(d.encode(), buf, C.c_int64(len(buf)))
+    names = buf.value.decode().split("\n")[:-1]
+    assert len(names) == n
+    return names
+
+
+def ref_save_labels(labels, path):
+    L = ref_bevgen_lib()
+    labels = np.ascontiguousarray(labels, np.float32)
+    L.ref_save_labels(C.c_int(labels.shape[0]), C.c_int(labels.shape[1]), _p(labels, C.c_float), path.encode())
+
+
+def ref_belonging_grid(x, y):
+    L = ref_bevgen_lib()
+    a, b = C.c_int(), C.c_int()
+    L.ref_belonging_grid(C.c_float(x), C.c_float(y), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def ref_main(root, sensor, double_libm=False):
+    """The reference's whole main() on a keyframe folder, in a child process (it prints progress and may exit()).
+    Returns (returncode, stdout)."""
+    import sys
+    so = os.path.join(_HERE, "_ref", "libbevgen_ref_dbl.so" if double_libm else "libbevgen_ref.so")
+    code = ("import ctypes as C, sys; L = C.CDLL(%r); a = [b'batch_multi_bev_gen', sys.argv[1].encode(), sys.argv[2].encode()];"
+            "argv = (C.c_char_p * 4)(*a, None); rc = L.ref_bevgen_main(3, argv); sys.stdout.flush(); sys.exit(rc)" % so)
+    r = subprocess.run([sys.executable, "-c", code, root, sensor], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    return r.returncode, r.stdout.decode(errors="replace"), r.stderr.decode(errors="replace")
+
+
+def _ref_so(name):
+    if name not in _libs:
+        p = os.path.join(_HERE, "_ref", name)
+        if not os.path.exists(p):
+            return None
+        _libs[name] = C.CDLL(p)
+    return _libs[name]
+
+
+def ref_save_as_mat(x, y, z, csv_path, interval=1.0):
+    """saveAsMat of the reference's own CloudManip.cpp (:79-109) -> the 201x201 f32 grid handed to imwrite; writes csv_path."""
+    L = _ref_so("libcloudmanip_ref.so")
+    x, px = _f(x); y, py = _f(y); z, pz = _f(z)
+    m = np.empty(201 * 201, np.float32)
+    rc = L.ref_save_as_mat(C.c_int64(len(x)), px, py, pz, C.c_float(interval), _p(m, C.c_float), csv_path.encode())
+    if rc != 201:
+        raise RuntimeError("ref_save_as_mat -> %d" % rc)
+    return m.reshape(201, 201)
+
+
+def ref_cloud_manip_matrix(tx, ty, tz, theta_deg, x, y, z):
+    """(rt[12], x', y', z'): the Affine3f of CloudManip.cpp:119-126 and pcl::transformPointCloud, as oracle/stub restates Eigen / PCL."""
+    L = _ref_so("libcloudmanip_ref.so")
+    x, px = _f(x); y, py = _f(y); z, pz = _f(z)
+    rt = np.empty(12, np.float32); o = [np.empty(len(x), np.float32) for _ in range(3)]
+    L.ref_cloud_manip_matrix(C.c_float(tx), C.c_float(ty), C.c_float(tz), C.c_float(theta_deg), _p(rt, C.c_float), C.c_int64(len(x)),
+                             px, py, pz, *[_p(a, C.c_float) for a in o])
+    return rt, o
+
+
+def ref_cloud_manip_main(argv, cwd):
+    """The reference's cloud_manip main() in a child process run in `cwd` (it writes its outputs into the working directory)."""
+    import sys
+    so = os.path.join(_HERE, "_ref", "libcloudmanip_ref.so")
+    code = ("import ctypes as C, sys; L = C.CDLL(%r); a = [b'cloud_manip'] + [s.encode() for s in sys.argv[1:]];"
+            "argv = (C.c_char_p * (len(a) + 1))(*a, None); rc = L.ref_cloud_manip_main(len(a), argv); sys.stdout.flush(); sys.exit(rc)" % so)
+    r = subprocess.run([sys.executable, "-c", code] + list(argv), stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=cwd)
+    return r.returncode, r.stdout.decode(errors="replace"), r.stderr.decode(errors="replace")
+
+
+def ref_bcm_frame(x, y, z, intensity, row, col, label, out_prefix):
+    """One frame through the reference's own BatchCloudManip.cpp (HDL-64E constants): (labels [S], bvm [201,201] f32)."""
+    L = _ref_so("libbatchcloudmanip_ref.so")
+    x, px = _f(x); y, py = _f(y); z, pz = _f(z); it, pi = _f(intensity)
+    row = np.ascontiguousarray(row, np.uint16); col = np.ascontiguousarray(col, np.uint16); label = np.ascontiguousarray(label, np.int16)
+    S = 64 * 2083
+    lab = np.empty(S, np.int16); m = np.empty(201 * 201, np.float32)
+    rc = L.ref_bcm_frame(C.c_int64(len(x)), px, py, pz, pi, _p(row, C.c_uint16), _p(col, C.c_uint16), _p(label, C.c_int16),
+                         _p(lab, C.c_int16), _p(m, C.c_float), out_prefix.encode())
+    if rc != S:
+        raise RuntimeError("ref_bcm_frame -> %d" % rc)
+    return lab, m.reshape(201, 201)

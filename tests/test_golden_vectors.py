@@ -1,0 +1,76 @@
+"""Golden vectors generated from the reference's own source (tests/golden/make_bev_golden.py -> bev_golden.json,
+bev_golden_small.npz): the CPU test holds the oracle to them (no /root/reference needed), the GPU test holds the CUDA
+path to them — so on the GPU box the product is compared with reference-generated outputs, not only with our oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from conftest import FIELDS, cat_frames
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+META = json.load(open(os.path.join(HERE, "golden", "bev_golden.json")))
+SMALL = np.load(os.path.join(HERE, "golden", "bev_golden_small.npz"))
+
+
+def _check(cid, got, what):
+    g = META["frames"][cid]
+    for k in ("owner", "label", "single", "multi"):
+        if cases.digest(got[k]) != g[k]:
+            key = cid + ":" + k
+            where = ""
+            if key in SMALL.files:
+                bad = np.argwhere(np.asarray(got[k]).reshape(SMALL[key].shape) != SMALL[key])
+                where = " (%d mismatches, first at %s)" % (len(bad), bad[:1].tolist())
+            raise AssertionError("%s: %s of %s differs from the reference-generated golden vector%s" % (what, k, cid, where))
+
+
+def test_oracle_matches_reference_generated_vectors(O, synth):
+    frames = cases.golden_frame_list(synth, O)
+    assert sorted(c for c, _, _ in frames) == sorted(META["frames"])
+    for cid, sensor, f in frames:
+        o = O.frame(O.sensor(sensor), *[f[k] for k in FIELDS])
+        _check(cid, o, "oracle")
+        od = O.frame(O.sensor(sensor), *[f[k] for k in FIELDS], double_libm=True)
+        assert cases.digest(od["label"]) == META["frames"][cid]["label_double_libm"], cid
+    for K, seed, step in cases.GOLDEN_LABEL_SETS:
+        g = META["labels"]["K%d_s%d" % (K, seed)]
+        xyz = synth.make_poses(K, seed=seed, step=step)
+        mi, _ = O.select_major(xyz)
+        lab, _, _ = O.labels(xyz, mi)
+        assert len(mi) == g["M"] and cases.digest(mi) == g["major"] and cases.digest(lab) == g["labels"], (K, seed)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sensor", ["HDL_32E", "OS1_64", "HDL_64E"])
+def test_cuda_matches_reference_generated_vectors(pkg, synth, O, sensor):
+    frames = [(c, f) for c, s, f in cases.golden_frame_list(synth, O) if s == sensor]
+    sp = O.sensor(sensor)
+    g = pkg.BevGen(sensor, device=0, max_frames_per_batch=4, max_points_per_frame=sp.S * 2)
+    try:
+        out = g.process_host(cat_frames([f for _, f in frames]))
+        for i, (cid, _) in enumerate(frames):
+            _check(cid, {k: out[k][i] for k in ("owner", "label", "single", "multi")}, "CUDA")
+    finally:
+        g.close()
+
+
+@pytest.mark.gpu
+def test_cuda_labels_match_reference_generated_vectors(pkg, synth):
+    """K = 10 000 keyframes / M = 457 majors is BASELINE configs[2],[3]'s label stage at full size."""
+    g = pkg.BevGen("HDL_32E", device=0, max_frames_per_batch=2)
+    try:
+        for K, seed, step in cases.GOLDEN_LABEL_SETS:
+            gold = META["labels"]["K%d_s%d" % (K, seed)]
+            xyz = synth.make_poses(K, seed=seed, step=step)
+            mi, _ = g.select_major(xyz)
+            assert len(mi) == gold["M"] and cases.digest(mi) == gold["major"], (K, seed)
+            lab, _, _ = g.labels(xyz, mi)
+            assert cases.digest(lab) == gold["labels"], (K, seed)
+            h = K // 3                                                  # row split as the multi-GPU label stage does it
+            parts = [g.labels(xyz, mi, a, b)[0] for a, b in ((0, h), (h, 2 * h), (2 * h, K))]
+            assert cases.digest(np.concatenate(parts)) == gold["labels"], (K, seed)
+    finally:
+        g.close()

@@ -5,6 +5,8 @@ import numpy as np
 import pytest
 
 from conftest import FIELDS, assert_same, cat_frames, oracle_batch
+import cases
+from cases import rand_frame as _rand_frame
 
 pytestmark = pytest.mark.gpu
 
@@ -81,22 +83,12 @@ def test_kitti_quirk_all_intensity_minus_one(gens, synth, O):
     assert (ref["label"][ref["owner"] > 0] == -2).mean() > 0.95
 
 
-def _rand_frame(rng, N, H, n, spread=60.0, zlo=-3.0, zhi=6.0, p_neg1=0.05, col_over=True):
-    f = dict(x=rng.uniform(-spread, spread, n), y=rng.uniform(-spread, spread, n), z=rng.uniform(zlo, zhi, n),
-             intensity=np.where(rng.random(n) < p_neg1, -1.0, rng.random(n)),
-             row=rng.integers(0, N + (2 if col_over else 0), n), col=rng.integers(0, H + (3 if col_over else 0), n),
-             label=rng.integers(-3, 4, n))
-    return {k: np.asarray(v).astype(t) for (k, v), t in zip(f.items(), (np.float32,) * 4 + (np.uint16, np.uint16, np.int16))}
-
-
 @pytest.mark.parametrize("sensor", ["HDL_32E", "OS1_64", "HDL_64E"])
 def test_random_unstructured_frames(gens, O, sensor):
     """Uniform random points: heavy slot collisions (last writer wins), out-of-range row/col, mixed labels incl. 0,
     many -1 intensities (substitution chain incl. the negative (col-2)%H wrap), points outside the BEV range."""
     sp = O.sensor(sensor)
-    rng = np.random.default_rng(1234)
-    frames = [_rand_frame(rng, sp.n_scan, sp.horizon_scan, n) for n in (sp.S * 2, sp.S // 3, 1, 0, 5000)]
-    frames.append(_rand_frame(rng, sp.n_scan, sp.horizon_scan, sp.S, spread=130.0, zlo=-10, zhi=30, p_neg1=0.5))
+    frames = cases.random_unstructured_frames(sp)
     batch = cat_frames(frames)
     g = gens(sensor, max_frames_per_batch=4, max_points_per_frame=sp.S * 2)
     assert_same(g.process_host(batch), oracle_batch(O, sensor, batch), sensor)
@@ -107,34 +99,7 @@ def test_ground_plane_borderline_angles(gens, O):
     values (zero-length pairs, huge, inf, nan).  The decision must match glibc's float atan2f exactly."""
     sensor = "HDL_32E"
     sp = O.sensor(sensor)
-    N, H = sp.n_scan, sp.horizon_scan
-    rng = np.random.default_rng(7)
-    rows, cols = np.divmod(np.arange(N * H), H)
-    rng_h = rng.uniform(0.5, 40.0, N * H).astype(np.float32)
-    x = np.zeros(N * H, np.float32); y = np.zeros(N * H, np.float32); z = np.zeros(N * H, np.float32)
-    tan10 = np.tan(np.float64(0.17453292))
-    for r in range(N - 1, -1, -1):        # build columns bottom-up so that dz/h of (r-1, r) is ~tan(10 deg) * (1 + k ulp)
-        sel = rows == r
-        if r == N - 1:
-            x[sel] = rng.uniform(-30, 30, H); y[sel] = rng.uniform(-30, 30, H); z[sel] = -1.7
-        else:
-            below = rows == r + 1
-            h = rng_h[sel]
-            ang = rng.uniform(0, 2 * np.pi, H)
-            x[sel] = x[below] + (h * np.cos(ang)).astype(np.float32)
-            y[sel] = y[below] + (h * np.sin(ang)).astype(np.float32)
-            dx = x[sel] - x[below]; dy = y[sel] - y[below]
-            hh = np.sqrt((dx * dx + dy * dy).astype(np.float32)).astype(np.float64)
-            k = rng.integers(-40, 41, H)
-            sgn = np.where(rng.random(H) < 0.5, -1.0, 1.0)
-            z[sel] = z[below] + (sgn * hh * tan10 * (1.0 + k * 6e-8)).astype(np.float32)
-    f = dict(x=x, y=y, z=z, intensity=np.full(N * H, 0.5, np.float32), row=rows.astype(np.uint16),
-             col=cols.astype(np.uint16), label=np.full(N * H, -2, np.int16))
-    # special values sprinkled into a second copy
-    f2 = {k: v.copy() for k, v in f.items()}
-    idx = rng.choice(N * H, 600, replace=False)
-    f2["z"][idx[:100]] = np.inf; f2["x"][idx[100:200]] = np.nan; f2["x"][idx[200:300]] = 3e38
-    f2["z"][idx[300:400]] = -np.inf; f2["y"][idx[400:500]] = -3e38; f2["z"][idx[500:600]] = 1e-42
+    f, f2 = cases.borderline_frames(sp)
     batch = cat_frames([f, f2])
     g = gens(sensor, max_frames_per_batch=4, max_points_per_frame=sp.S * 2)
     ref = oracle_batch(O, sensor, batch)
@@ -173,17 +138,7 @@ def test_cell_index_boundaries(gens, O):
     """Cell / layer / height rounding at the boundaries listed in SURVEY §8a.1-B."""
     sensor = "HDL_32E"
     sp = O.sensor(sensor)
-    vs = np.array([-113.0, -112.99999, -112.5, -112.0, -111.99999, -111.5, -111.0, 0.0, -0.0, 0.49999997, 0.5, 110.99999,
-                   111.0, 111.00001, 110.5, 112.0, 1e9, -1e9, np.nan, np.inf], np.float32)
-    zs = np.array([-2.0, -1.26, -1.25, -1.24999, -1.0, -0.75, -0.7500001, 0.0, 10.74, 10.75, 10.76, 11.0, 61.7, 61.75, 70.0,
-                   -2.1, 5.3e8, 6e8, np.nan, -np.inf, np.inf, 1e-40], np.float32)
-    X, Y, Z = np.meshgrid(vs, vs, zs, indexing="ij")
-    n = X.size
-    assert n <= sp.S
-    slots = np.arange(n)
-    f = dict(x=X.ravel(), y=Y.ravel(), z=Z.ravel(), intensity=np.full(n, -1.0, np.float32),   # -1: nothing is ground
-             row=(slots // sp.horizon_scan).astype(np.uint16), col=(slots % sp.horizon_scan).astype(np.uint16),
-             label=np.where(slots % 7 == 0, 0, 5).astype(np.int16))
+    f = cases.boundary_frame(sp)
     batch = cat_frames([f])
     g = gens(sensor, max_frames_per_batch=4, max_points_per_frame=sp.S * 2)
     ref = oracle_batch(O, sensor, batch)
