@@ -110,6 +110,43 @@ BEVGEN_API int bevgen_process_device(bevgen_ctx *ctx, int n_frames, const int64_
                           const bevgen_outputs *out);
 BEVGEN_API int bevgen_sync(bevgen_ctx *ctx);
 
+/* ---- compact staging format: the host path with the fewest bytes over PCIe ----------------------------------------
+ * The loop body BatchMultiBevGen.cpp:735-747 needs, per input point, x / y / z, the slot row*Horizon_SCAN + col
+ * (:106-113), whether intensity == -1 (:146-165) and whether label != 0 (:285, :349) - 16 bytes instead of the 22 of
+ * the SoA form; and its results are, per frame, which slots became ground (:244-245, one bit per slot; every other
+ * slot keeps the label of the point that owns it, which the caller still holds), the winner bits, the single BEV and
+ * the multi BEV, whose 24 layers are 0/255 images, i.e. 24 bits per cell.  Same kernels, same results, 2.0 MB in /
+ * 0.23 MB out per HDL_64E frame instead of 2.6 MB / 1.5 MB.  The host-side packers / expanders below restate nothing of
+ * the algorithm: they only change the representation. */
+#define BEVGEN_META_INVALID 0x00FFFFFFu   /* slot field of a point getOrderedCloud drops (row >= N_SCAN or col >= Horizon_SCAN) */
+#define BEVGEN_META_NEG1 (1u << 24)       /* intensity == -1 */
+#define BEVGEN_META_LABELED (1u << 25)    /* label != 0 */
+typedef struct bevgen_points_compact {
+  const float *x, *y, *z;
+  const uint32_t *meta;                   /* bevgen_pack_meta() per point */
+} bevgen_points_compact;
+typedef struct bevgen_outputs_compact {
+  uint32_t *ground_bits;   /* [F][(S+31)/32]: bit s&31 of word s>>5 set iff slot s is ground after markGroundPoints (label -> 0) */
+  uint32_t *winner_bits;   /* as in bevgen_outputs */
+  uint8_t *single_bev;     /* [F][224][224] */
+  uint8_t *multi_planes;   /* [F][3][224][224]: bit (l & 7) of plane (l >> 3) set iff layer l of the cell is occupied (255) */
+} bevgen_outputs_compact;
+static inline uint32_t bevgen_pack_meta(const bevgen_params *p, uint16_t row, uint16_t col, float intensity, int16_t label) {
+  const uint32_t slot = (row < p->n_scan && col < p->horizon_scan) ? (uint32_t)row * (uint32_t)p->horizon_scan + col : BEVGEN_META_INVALID;
+  return slot | (intensity == -1.0f ? BEVGEN_META_NEG1 : 0u) | (label != 0 ? BEVGEN_META_LABELED : 0u);
+}
+/* multi_planes of one frame -> the 24 layers of the .bin payload (:307-314) */
+static inline void bevgen_expand_multi(const uint8_t *planes, uint8_t *multi_bev) {
+  for (int l = 0; l < BEVGEN_NUM_LAYERS; l++) {
+    const uint8_t *pl = planes + (size_t)(l >> 3) * BEVGEN_GRID_SIZE * BEVGEN_GRID_SIZE;
+    uint8_t *o = multi_bev + (size_t)l * BEVGEN_GRID_SIZE * BEVGEN_GRID_SIZE;
+    for (int i = 0; i < BEVGEN_GRID_SIZE * BEVGEN_GRID_SIZE; i++) o[i] = ((pl[i] >> (l & 7)) & 1) ? 255 : 0;
+  }
+}
+/* Same contract as bevgen_process_host (chunked H2D | kernels | D2H pipeline; pinned buffers make it fully async). */
+BEVGEN_API int bevgen_process_host_compact(bevgen_ctx *ctx, int n_frames, const int64_t *offsets,
+                                           const bevgen_points_compact *in, const bevgen_outputs_compact *out);
+
 /* SURVEY 8(f)-1 — packed-record staging: the frames arrive as the interleaved records of a binary PCD payload
  * (what pcl::io::loadPCDFile parses at BatchMultiBevGen.cpp:730 and savePCDFileBinary writes at :756) and the
  * de-interleave into SoA runs on the GPU, so host staging is one copy of the file payload into pinned memory.
@@ -131,7 +168,8 @@ BEVGEN_API int bevgen_process_packed_host(bevgen_ctx *ctx, int n_frames, const i
 
 /* Asynchronous single-frame form used by pipelined callers (one frame of the loop at :727-757):
  * submit copies the frame into the context's pinned ring and enqueues H2D + kernels + D2H; collect blocks on that
- * frame's event and copies the results out.  At most `max_frames_per_batch` frames may be in flight.     */
+ * frame's event and copies the results out.  At most `max_frames_per_batch` frames may be in flight (ring slots are
+ * built on demand).     */
 BEVGEN_API int bevgen_submit(bevgen_ctx *ctx, int frame_id, int n_in, const float *x, const float *y, const float *z,
                   const float *intensity, const uint16_t *row, const uint16_t *col, const int16_t *label);
 BEVGEN_API int bevgen_collect(bevgen_ctx *ctx, int frame_id, int16_t *label_out, uint32_t *winner_bits /* (n_in+31)/32 words */,
@@ -150,9 +188,15 @@ BEVGEN_API int bevgen_labels(bevgen_ctx *ctx, int K, const float *xyz, int M, co
 
 /* cloud_manip (CloudManip.cpp:111-141): rigid transform of n host points (rt as in bevgen_params) and the two
  * 201x201 float max-height grids of saveAsMat (:79-95) for the input and the transformed cloud.
- * Any output pointer may be NULL.  Works on any context (sensor params are not used). */
+ * Any output pointer may be NULL, each on its own; x / y / z may be NULL when n == 0 (the reference carries on with an empty
+ * cloud when loadPCDFile fails, CloudManip.cpp:117).  Works on any context (sensor params are not used). */
 BEVGEN_API int bevgen_cloud_manip(bevgen_ctx *ctx, int64_t n, const float *rt, const float *x, const float *y, const float *z,
                        float *tx, float *ty, float *tz, float *bev_in, float *bev_out);
+
+/* Device-resident form of bevgen_cloud_manip (BASELINE config #5 measured without PCIe): all pointers are device memory,
+ * tx/ty/tz given together or all NULL, grids of 201*201 floats are overwritten; enqueued on the compute stream. */
+BEVGEN_API int bevgen_cloud_manip_device(bevgen_ctx *ctx, int64_t n, const float *rt, const float *x, const float *y, const float *z,
+                              float *tx, float *ty, float *tz, float *bev_in, float *bev_out);
 
 /* SURVEY 8(f)-2 — the per-point projection of the keyframe extractors, i.e. the producer of the `row` / `col` fields:
  *   BEVGEN_PROJECT_MULRAN_OS1_64  (MulranPointCloudSelect.cpp:112-126): row = k % 64, col = round(azimuth / 360 * 1024)
@@ -193,6 +237,17 @@ BEVGEN_API int bevgen_stage_ms(bevgen_ctx *ctx, float *ms /*[BEVGEN_N_STAGES]*/,
 BEVGEN_API int64_t bevgen_kernel_launches(bevgen_ctx *ctx); /* total kernels launched by this context so far */
 BEVGEN_API void *bevgen_compute_stream(bevgen_ctx *ctx);    /* cudaStream_t of the compute stream */
 BEVGEN_API const char *bevgen_stage_name(int stage);
+/* Which C++ overload set the reference's unqualified `atan2(diffZ, sqrt(...))` (BatchMultiBevGen.cpp:173) binds to is
+ * decided by the reference's include tree (oracle/stub/README.md): 0 (default) = float atan2f / sqrtf, the build with
+ * <math.h> visible; 1 = the C double functions.  The two only differ for pairs within ~1 float ulp of the 10-degree
+ * threshold.  Applies to every later process_* / submit call of the context. */
+BEVGEN_API int bevgen_set_libm(bevgen_ctx *ctx, int use_double);
+/* Diagnostics of the ground criterion, accumulated over all frames processed while enabled (set_diag zeroes them):
+ * out[0] = vertical pairs whose slope fell inside the +-2e-5 guard band around tan(10 deg) and were decided by the exact
+ * libm evaluation, out[1] = pairs whose decision differs between the float and the double overload set,
+ * out[2..3] reserved.  Enabling costs a double atan2 per borderline / degenerate pair. */
+BEVGEN_API int bevgen_set_diag(bevgen_ctx *ctx, int enabled);
+BEVGEN_API int bevgen_get_diag(bevgen_ctx *ctx, uint64_t *out /*[4]*/);
 /* Device port of glibc's float atan2f used by the ground criterion, exposed for bit-exactness tests. */
 BEVGEN_API int bevgen_debug_atan2f(bevgen_ctx *ctx, int64_t n, const float *y, const float *x, float *out);
 

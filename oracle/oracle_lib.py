@@ -400,3 +400,35 @@ def ref_bcm_frame(x, y, z, intensity, row, col, label, out_prefix):
     if rc != S:
         raise RuntimeError("ref_bcm_frame -> %d" % rc)
     return lab, m.reshape(201, 201)
+
+
+def ref_bench(sensor_name, offsets, x, y, z, intensity, row, col, label, iters=1):
+    """Seconds the reference's own hot loop body (BatchMultiBevGen.cpp:735-747, PNG / CSV encoders stubbed out) spends on the
+    frames, single-threaded like the reference (its globals make it non-reentrant: run one process per core)."""
+    L = ref_bevgen_lib()
+    L.ref_bench.restype = C.c_double
+    if L.ref_set_sensor(sensor_name.encode(), None) != 0:
+        raise ValueError("Unknown sensor type: %s!" % sensor_name)
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    x, px = _f(x); y, py = _f(y); z, pz = _f(z); it, pi = _f(intensity)
+    row = np.ascontiguousarray(row, np.uint16); col = np.ascontiguousarray(col, np.uint16); label = np.ascontiguousarray(label, np.int16)
+    cs = C.c_uint64(0)
+    return float(L.ref_bench(C.c_int(len(offsets) - 1), _p(offsets, C.c_int64), px, py, pz, pi, _p(row, C.c_uint16), _p(col, C.c_uint16),
+                             _p(label, C.c_int16), C.c_int(iters), C.byref(cs)))
+
+
+def ref_bench_all_cores(sensor_name, npz_path, procs, seconds=8.0):
+    """frames/s of `procs` independent processes each looping ref_bench over the frames in npz_path (offsets + SoA) for about
+    `seconds`.  Child processes: the reference's file-scope globals rule out threads."""
+    import sys
+    code = ("import sys, time, numpy as np; sys.path.insert(0, %r); import oracle_lib as O; d = np.load(sys.argv[1]); n = len(d['offsets']) - 1;"
+            "a = [d[k] for k in ('x','y','z','intensity','row','col','label')]; O.ref_bench(sys.argv[2], d['offsets'], *a, iters=1);"
+            "t0 = time.perf_counter(); it = 0; busy = 0.0\n"
+            "while time.perf_counter() - t0 < float(sys.argv[3]): busy += O.ref_bench(sys.argv[2], d['offsets'], *a, iters=1); it += 1\n"
+            "print(n * it, busy, time.perf_counter() - t0)" % _HERE)
+    ps = [subprocess.Popen([sys.executable, "-c", code, npz_path, sensor_name, str(seconds)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL) for _ in range(procs)]
+    frames = busy = wall = 0.0
+    for p in ps:
+        o = p.communicate()[0].decode().split()
+        frames += float(o[0]); busy += float(o[1]); wall = max(wall, float(o[2]))
+    return dict(frames_per_s=frames / wall, procs=procs, frames=int(frames), wall_s=wall, ms_per_frame_single_core=busy / frames * 1e3)

@@ -131,6 +131,50 @@ REF_API int ref_frame(int64_t n, const float* x, const float* y, const float* z,
   return (int)S;
 }
 
+// Timing entry for bench.py's reference arm: the four calls of the reference's hot loop body (:735-747) over nf frames,
+// `iters` times, clouds built once outside the timed span.  The PNG / CSV encoders are stubbed out (imwrite hook that
+// does nothing, cv::format returning "") because the GPU arm it is compared with has no file encoders either; the
+// reference's own .bin write (:307-314) goes to a tmpfs directory.  Returns the seconds spent inside the four calls.
+REF_API double ref_bench(int nf, const int64_t* offs, const float* x, const float* y, const float* z, const float* intensity,
+                         const uint16_t* row, const uint16_t* col, const int16_t* label, int iters, uint64_t* checksum) {
+  ensure_neighbors();
+  std::vector<pcl::PointCloud<pcl::PointXYZIRCT>::Ptr> clouds(nf);
+  for (int f = 0; f < nf; f++) {
+    clouds[f].reset(new pcl::PointCloud<pcl::PointXYZIRCT>());
+    const int64_t o = offs[f], n = offs[f + 1] - o;
+    clouds[f]->points.resize(n);
+    for (int64_t i = 0; i < n; i++) {
+      pcl::PointXYZIRCT& p = clouds[f]->points[i];
+      p.x = x[o + i]; p.y = y[o + i]; p.z = z[o + i]; p.intensity = intensity[o + i]; p.row = row[o + i]; p.col = col[o + i]; p.label = label[o + i];
+    }
+  }
+  std::string dir = tmp_dir();
+  if (access("/dev/shm", W_OK) == 0) { char tpl[] = "/dev/shm/bevgen_ref_XXXXXX"; const char* d = mkdtemp(tpl); if (d) dir = std::string(d) + "/"; }
+  output_multi_bvm_bin_dir_ = dir; output_multi_bvm_img_dir_ = dir; output_single_bvm_img_dir_ = dir; output_single_bvm_csv_dir_ = dir;
+  ::mkdir((dir + "f").c_str(), 0777);
+  uint64_t sum = 0;
+  cv::stub::imwrite_hook() = [&sum](const std::string&, const cv::Mat& m) { sum += m.at<uint8_t>(112, 112); return true; };
+  cv::stub::format_enabled() = false;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int it = 0; it < iters; it++)
+    for (int f = 0; f < nf; f++) {
+      pcl::PointCloud<pcl::PointXYZIRCT>::Ptr cloud_ordered(new pcl::PointCloud<pcl::PointXYZIRCT>());
+      cv::Mat ground_mat;
+      getOrderedCloud(clouds[f], cloud_ordered);
+      markGroundPoints(cloud_ordered, ground_mat);
+      computeAndSaveMultiBev(cloud_ordered, "f", 1.0f);
+      computeAndSaveSingleBev(cloud_ordered, "f", 1.0f);
+      sum += (uint64_t)cloud_ordered->points[cloud_ordered->points.size() / 2].label & 0xFFFF;
+    }
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  cv::stub::imwrite_hook() = nullptr;
+  cv::stub::format_enabled() = true;
+  std::remove((dir + "f.bin").c_str()); std::remove((dir + "f.csv").c_str()); ::rmdir((dir + "f").c_str());
+  if (dir != tmp_dir()) ::rmdir(dir.c_str());
+  if (checksum) *checksum = sum;
+  return dt;
+}
+
 static std::vector<Pose6f> poses_from_xyz(int K, const float* xyz) {
   std::vector<Pose6f> v(K);
   for (int i = 0; i < K; i++) { v[i].x = xyz[3 * i]; v[i].y = xyz[3 * i + 1]; v[i].z = xyz[3 * i + 2]; v[i].roll = v[i].pitch = v[i].yaw = 0.f; }

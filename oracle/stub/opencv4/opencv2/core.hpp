@@ -116,6 +116,8 @@ class Formatted {
 };
 inline std::ostream& operator<<(std::ostream& os, const Ptr<Formatted>& f) { return os << f->text; }
 
+namespace stub { inline bool& format_enabled() { static bool on = true; return on; } }   // false: format() returns "" (timing runs)
+
 class Formatter {
  public:
   enum FormatType { FMT_DEFAULT = 0, FMT_MATLAB = 1, FMT_CSV = 2, FMT_PYTHON = 3, FMT_NUMPY = 4, FMT_C = 5 };
@@ -126,6 +128,7 @@ class Formatter {
   void setMultiline(bool = true) {}
   Ptr<Formatted> format(const Mat& m) const {
     Ptr<Formatted> out = std::make_shared<Formatted>();
+    if (!stub::format_enabled()) return out;
     std::string& s = out->text;
     char fl[16], buf[80];
     std::snprintf(fl, sizeof fl, "%%.%dg", m.type() == CV_64F ? prec64f_ : prec32f_);

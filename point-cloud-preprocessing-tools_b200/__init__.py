@@ -48,6 +48,45 @@ class RecordLayout(C.Structure):
                 ("off_intensity", C.c_int32), ("off_row", C.c_int32), ("off_col", C.c_int32), ("off_label", C.c_int32)]
 
 
+class PointsCompact(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p), ("meta", C.c_void_p)]
+
+
+class OutputsCompact(C.Structure):
+    _fields_ = [("ground_bits", C.c_void_p), ("winner_bits", C.c_void_p), ("single_bev", C.c_void_p), ("multi_planes", C.c_void_p)]
+
+
+META_INVALID, META_NEG1, META_LABELED = 0x00FFFFFF, 1 << 24, 1 << 25
+
+
+def pack_meta(params, row, col, intensity, label):
+    """bevgen_pack_meta (include/bevgen.h) over arrays: slot | intensity == -1 | label != 0 - a change of representation."""
+    row = np.asarray(row).astype(np.int64); col = np.asarray(col).astype(np.int64)
+    ok = (row < params.n_scan) & (col < params.horizon_scan)
+    slot = np.where(ok, row * params.horizon_scan + col, META_INVALID).astype(np.uint32)
+    return slot | np.where(np.asarray(intensity, np.float32) == np.float32(-1.0), np.uint32(META_NEG1), np.uint32(0)) \
+        | np.where(np.asarray(label) != 0, np.uint32(META_LABELED), np.uint32(0))
+
+
+def expand_multi(planes):
+    """bevgen_expand_multi over frames: [F][3][224][224] bit planes -> [F][24][224][224] 0/255 layers."""
+    planes = np.asarray(planes, np.uint8)
+    l = np.arange(LAYERS)
+    return (((planes[:, l >> 3] >> (l & 7)[None, :, None, None].astype(np.uint8)) & 1) * 255).astype(np.uint8)
+
+
+def labels_from_ground_bits(ground_bits, owner, label_in, offsets):
+    """[F][S] int16 labels of the ordered cloud from the compact outputs: 0 where the slot is ground (or empty), else the
+    label of the input point that owns the slot (BatchMultiBevGen.cpp:244-248 leaves it untouched)."""
+    F, S = owner.shape
+    g = np.unpackbits(np.asarray(ground_bits, np.uint32).reshape(F, -1).view(np.uint8), axis=1, bitorder="little")[:, :S].astype(bool)
+    lab = np.zeros((F, S), np.int16)
+    for f in range(F):
+        sel = (owner[f] > 0) & ~g[f]
+        lab[f, sel] = np.asarray(label_in)[int(offsets[f]) + owner[f][sel].astype(np.int64) - 1]
+    return lab
+
+
 def pcd_record_layout():
     """The 26-byte record of a PointXYZIRCT binary PCD (savePCDFileBinary, BatchMultiBevGen.cpp:756)."""
     lay = RecordLayout()
@@ -87,7 +126,8 @@ EXPORTS = ["bevgen_sensor_params", "bevgen_create", "bevgen_destroy", "bevgen_la
            "bevgen_host_free", "bevgen_process_host", "bevgen_process_device", "bevgen_sync", "bevgen_submit",
            "bevgen_collect", "bevgen_select_major", "bevgen_labels", "bevgen_cloud_manip", "bevgen_set_profiling",
            "bevgen_stage_ms", "bevgen_kernel_launches", "bevgen_compute_stream", "bevgen_stage_name",
-           "bevgen_debug_atan2f", "bevgen_pcd_record_layout", "bevgen_process_packed_host", "bevgen_project", "bevgen_top_flatten"]
+           "bevgen_debug_atan2f", "bevgen_pcd_record_layout", "bevgen_process_packed_host", "bevgen_project", "bevgen_top_flatten",
+           "bevgen_process_host_compact", "bevgen_cloud_manip_device", "bevgen_set_libm", "bevgen_set_diag", "bevgen_get_diag"]
 
 
 def build(verbose=False):
@@ -223,6 +263,33 @@ class BevGen:
             out["owner"] = owner_from_winner(out["winner"], offs, arrs[4], arrs[5], self.params.horizon_scan, self.S)
         return out
 
+    def alloc_outputs_compact(self, F, pinned=False, n_total=None):
+        mk = pinned_empty if pinned else np.empty
+        n_total = F * self.max_pts if n_total is None else n_total
+        out = dict(ground=mk((F, (self.S + 31) // 32), np.uint32), winner=mk((winner_words(n_total, F),), np.uint32),
+                   single=mk((F, GRID, GRID), np.uint8), planes=mk((F, 3, GRID, GRID), np.uint8))
+        out["winner"][...] = 0
+        return out
+
+    def process_host_compact(self, cbatch, out=None):
+        """cbatch: dict x, y, z (f32), meta (u32, pack_meta) + offsets of HOST arrays -> compact outputs (ground, winner, single, planes)."""
+        offs = np.ascontiguousarray(cbatch["offsets"], np.int64)
+        F = len(offs) - 1
+        out = out or self.alloc_outputs_compact(F, n_total=int(offs[-1]))
+        arrs = [_as(cbatch[k], t) for k, t in (("x", np.float32), ("y", np.float32), ("z", np.float32), ("meta", np.uint32))]
+        pts = PointsCompact(*[_ptr(a) for a in arrs])
+        o = OutputsCompact(_ptr(out["ground"]), _ptr(out["winner"]), _ptr(out["single"]), _ptr(out["planes"]))
+        _ck(lib().bevgen_process_host_compact(self._ctx, C.c_int(F), _ptr(offs), C.byref(pts), C.byref(o)))
+        return out
+
+    def compact_to_reference_layout(self, cout, batch):
+        """Expands compact outputs into the dict process_host returns (owner, label, single, multi), using the caller's
+        own row / col / label arrays - what the CLI's encode pool does before writing files."""
+        offs = np.asarray(batch["offsets"], np.int64)
+        owner = owner_from_winner(cout["winner"], offs, _as(batch["row"], np.uint16), _as(batch["col"], np.uint16), self.params.horizon_scan, self.S)
+        return dict(owner=owner, label=labels_from_ground_bits(cout["ground"], owner, batch["label"], offs), single=np.asarray(cout["single"]),
+                    multi=expand_multi(cout["planes"]))
+
     def process_packed_host(self, records, offsets, layout=None, out=None):
         """records: HOST uint8 array with the concatenated interleaved records of all frames (a binary PCD payload);
         layout: RecordLayout (default = the 26-byte PCD record).  The de-interleave runs on the GPU."""
@@ -295,6 +362,24 @@ class BevGen:
         _ck(lib().bevgen_cloud_manip(self._ctx, C.c_int64(n), _ptr(rt), _ptr(x), _ptr(y), _ptr(z), _ptr(t[0]), _ptr(t[1]),
                                      _ptr(t[2]), _ptr(bi), _ptr(bo)))
         return t, bi, bo
+
+    def cloud_manip_device(self, n, rt, dev):
+        """dev: dict of integer DEVICE pointers x, y, z, tx, ty, tz, bev_in, bev_out (outputs may be 0); async on the compute stream."""
+        rt = np.ascontiguousarray(rt, np.float32).reshape(12)
+        g = lambda k: C.c_void_p(int(dev[k])) if dev.get(k) else None
+        _ck(lib().bevgen_cloud_manip_device(self._ctx, C.c_int64(n), _ptr(rt), g("x"), g("y"), g("z"), g("tx"), g("ty"), g("tz"), g("bev_in"), g("bev_out")))
+
+    # ---- libm overload set / diagnostics of the ground criterion ------------------------------------------------
+    def set_libm(self, use_double):
+        _ck(lib().bevgen_set_libm(self._ctx, C.c_int(1 if use_double else 0)))
+
+    def set_diag(self, on):
+        _ck(lib().bevgen_set_diag(self._ctx, C.c_int(1 if on else 0)))
+
+    def get_diag(self):
+        out = (C.c_uint64 * 4)()
+        _ck(lib().bevgen_get_diag(self._ctx, out))
+        return dict(borderline_pairs=int(out[0]), float_double_disagree=int(out[1]))
 
     # ---- projection step of the keyframe extractors -----------------------------------------------------------
     def project(self, kind, x, y, z=None):

@@ -4,6 +4,8 @@
 #include "../../include/bevgen.h"
 #include "bevgen_kernels.cuh"
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -36,8 +38,9 @@ constexpr size_t BVM_CELLS = (size_t)MGRID * MGRID;
 static size_t wwords(size_t n_total, size_t frames) { return (n_total >> 5) + frames + 1; }
 
 struct Scratch {            // device scratch for one wave of up to `frames` frames
-  float4* rec = 0; uint16_t* gkey = 0; float* gz = 0; uint32_t* cnt = 0; float* avg = 0;
+  float4* rec = 0; float* gz = 0; uint32_t* cnt = 0; float* avg = 0;
   uint4* gsum = 0; uint32_t* slow = 0;   // per (row, 32-column group) summaries; per-frame "use the sweep kernel" flag
+  uint32_t* gmask = 0;                   // per (row, 32-column group): ground_mat == 1 after loop 1, one bit per slot
   uint32_t* seg_start = 0; uint16_t* seg_len = 0;   // [frames][SEG_CAP] segments bucketed by sector, slot order inside a bucket
   uint32_t* kdesc = 0; uint16_t* act = 0; uint32_t* n_act = 0;   // [frames][NSECT] bucket (base<<16|count), active sectors; [frames]
   uint32_t* owner = 0;                   // [frames][S] claim table, only for range images too large for k_order_winners' shared memory
@@ -74,6 +77,8 @@ struct bevgen_ctx {
   float* cnt_lut = 0;
   int cw_stride = 1;         // max_points_per_frame / 2 + 1
   int seg_cap = SEG_CAP;     // BEVGEN_SEG_CAP (tests): frames with more segments take the sweep kernel
+  int fold_wpb = 4;          // warps per CTA of k_seg_fold (BEVGEN_FOLD_WPB: 1, 2 or 4)
+  unsigned long long* diag_d = 0;   // device counters of bevgen_set_diag (borderline pairs, float/double libm disagreements)
   Scratch sc_dev;            // scratch of the device path (waves on the compute stream)
   static constexpr int MAX_AUX = 7;
   Scratch sc_aux[MAX_AUX];       // scratch sets of the auxiliary compute streams
@@ -133,19 +138,19 @@ static int alloc_scratch(Scratch& s, size_t frames, const SensorDev& sp, int max
     CK(cudaMalloc(&s.cpt, s.cpt_words * sizeof(uint32_t)));
   }
   CK(cudaMalloc(&s.gsum, frames * gsum_per_frame(sp) * sizeof(uint4)));
+  CK(cudaMalloc(&s.gmask, frames * gsum_per_frame(sp) * sizeof(uint32_t)));
   CK(cudaMalloc(&s.slow, frames * sizeof(uint32_t)));
   CK(cudaMalloc(&s.seg_start, frames * SEG_CAP * sizeof(uint32_t))); CK(cudaMalloc(&s.seg_len, frames * SEG_CAP * sizeof(uint16_t)));
   CK(cudaMalloc(&s.kdesc, frames * NSECT * sizeof(uint32_t))); CK(cudaMalloc(&s.act, frames * NSECT * sizeof(uint16_t)));
   CK(cudaMalloc(&s.n_act, frames * sizeof(uint32_t)));
   CK(cudaMalloc(&s.rec, frames * S * sizeof(float4)));
-  CK(cudaMalloc(&s.gkey, frames * S * sizeof(uint16_t)));
   CK(cudaMalloc(&s.gz, (frames * S + 64) * sizeof(float)));   // + slack: k_seg_fold's last aligned window may pass the end
   CK(cudaMalloc(&s.cnt, frames * NSECT * sizeof(uint32_t)));
   CK(cudaMalloc(&s.avg, frames * NSECT * sizeof(float)));
   return 0;
 }
 static void free_scratch(Scratch& s) {
-  cudaFree(s.rec); cudaFree(s.gkey); cudaFree(s.gz); cudaFree(s.cnt); cudaFree(s.avg); cudaFree(s.gsum); cudaFree(s.slow); cudaFree(s.seg_start); cudaFree(s.seg_len); cudaFree(s.kdesc); cudaFree(s.act); cudaFree(s.n_act); cudaFree(s.owner); cudaFree(s.occ); cudaFree(s.cwin); cudaFree(s.cpt);
+  cudaFree(s.rec); cudaFree(s.gmask); cudaFree(s.gz); cudaFree(s.cnt); cudaFree(s.avg); cudaFree(s.gsum); cudaFree(s.slow); cudaFree(s.seg_start); cudaFree(s.seg_len); cudaFree(s.kdesc); cudaFree(s.act); cudaFree(s.n_act); cudaFree(s.owner); cudaFree(s.occ); cudaFree(s.cwin); cudaFree(s.cpt);
   s = Scratch();
 }
 static int alloc_io(DevIn& in, DevOut& out, size_t frames, size_t pts, size_t S) {
@@ -163,8 +168,7 @@ static void free_io(DevIn& in, DevOut& out) {
 }
 
 // ---- create / destroy -----------------------------------------------------------------------------------------
-extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* p, int max_pts, int max_frames) {
-  if (!out || !p) return fail("bevgen_create: null argument");
+static int create_checks(int device, const bevgen_params* p, int max_pts, int max_frames) {
   if (p->grid_size != BEVGEN_GRID_SIZE || p->max_range != BEVGEN_MAX_RANGE || p->n_layers != BEVGEN_NUM_LAYERS ||
       p->lidar_to_ground != 2.0f)
     return fail("bevgen_create: grid_size/max_range/n_layers/lidar_to_ground must be 224/112/24/2.0 (BatchMultiBevGen.cpp:266-269)");
@@ -179,10 +183,14 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
   if (device < 0 || device >= ndev) return fail("bevgen_create: bad device index");
   CK(cudaSetDevice(device));
   cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, k_finalize_bin) != cudaSuccess)
+  if (cudaFuncGetAttributes(&fa, k_finalize_bin<false>) != cudaSuccess)
     return fail("bevgen_create: no sm_100a kernel image usable on this device (library is built for B200 only)");
+  return 0;
+}
 
-  bevgen_ctx* c = new bevgen_ctx();
+// Everything that can fail after the context object exists; on failure bevgen_create destroys the half-built context
+// (bevgen_destroy copes with any prefix of this sequence).
+static int create_fill(bevgen_ctx* c, int device, const bevgen_params* p, int max_pts, int max_frames) {
   c->device = device; c->p = *p; c->max_pts = max_pts; c->max_frames = max_frames; c->cw_stride = max_pts / 2 + 1;
   SensorDev& sp = c->sp;
   sp.N = p->n_scan; sp.H = p->horizon_scan; sp.G = p->ground_upper_scan; sp.S = sp.N * sp.H;
@@ -208,32 +216,70 @@ extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* 
   CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
   for (auto& e : c->pev) CK(cudaEventCreate(&e));
-  CK(cudaFuncSetAttribute(k_finalize_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BIN));
+  CK(cudaFuncSetAttribute(k_finalize_bin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BIN));
+  CK(cudaFuncSetAttribute(k_finalize_bin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BIN));
+  // records of up to 256 bytes (bevgen_process_packed_host): 256 of them + the alignment head per CTA
+  CK(cudaFuncSetAttribute(k_unpack_records<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256 + 32));
+  CK(cudaFuncSetAttribute(k_unpack_records<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256 + 32));
   CK(cudaFuncSetAttribute(k_seg_build, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SEG));
   CK(cudaFuncSetAttribute(k_float_bev, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BVM));
-  CK(cudaFuncSetAttribute(k_order_winners, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // function-wide: the largest any context may ask for
+  CK(cudaFuncSetAttribute(k_order_winners<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // function-wide: the largest any context may ask for
+  CK(cudaFuncSetAttribute(k_order_winners<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_seg_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   if (const char* e = getenv("BEVGEN_SEG_CAP")) c->seg_cap = std::max(0, std::min(SEG_CAP, atoi(e)));
+  if (const char* e = getenv("BEVGEN_FOLD_WPB")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->fold_wpb = v; }
+  CK(cudaMalloc(&c->diag_d, 4 * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(c->diag_d, 0, 4 * sizeof(unsigned long long), c->s_comp));
   // (measured: forcing the max-shared carveout on the ordering kernels makes k_order_fill 1.8x slower - it relies on L1)
   CK(cudaFuncSetAttribute(k_sector_mean, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_seg_fold<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
   CK(cudaFuncSetAttribute(k_seg_fold<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
-  CK(cudaFuncSetAttribute(k_finalize_bin, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_finalize_bin<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_finalize_bin<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaMalloc(&c->cnt_lut, ((size_t)sp.S + 1) * sizeof(float)));
   k_build_cnt_lut<<<1, 32, 0, c->s_comp>>>(sp.S, c->cnt_lut);
   CK(cudaGetLastError());
   c->launches++;
-  if (alloc_scratch(c->sc_dev, max_frames, sp, max_pts)) { delete c; return -1; }
+  if (alloc_scratch(c->sc_dev, max_frames, sp, max_pts)) return -1;
   if (const char* e = getenv("BEVGEN_STREAMS")) c->n_dev_streams = std::max(1, std::min(bevgen_ctx::MAX_AUX + 1, atoi(e)));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   for (int i = 0; i + 1 < c->n_dev_streams; i++) {
-    if (alloc_scratch(c->sc_aux[i], max_frames, sp, max_pts)) { delete c; return -1; }
+    if (alloc_scratch(c->sc_aux[i], max_frames, sp, max_pts)) return -1;
     CK(cudaStreamCreateWithFlags(&c->s_aux[i], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
   }
   CK(cudaStreamSynchronize(c->s_comp));
+  return 0;
+}
+
+extern "C" int bevgen_create(bevgen_ctx** out, int device, const bevgen_params* p, int max_pts, int max_frames) {
+  if (!out || !p) return fail("bevgen_create: null argument");
+  *out = nullptr;
+  if (create_checks(device, p, max_pts, max_frames)) return -1;
+  bevgen_ctx* c = new bevgen_ctx();
+  if (create_fill(c, device, p, max_pts, max_frames)) {
+    const std::string why = g_err;     // bevgen_destroy may overwrite the message
+    cudaGetLastError();                // clear a sticky allocation error so that the frees below run
+    bevgen_destroy(c);
+    g_err = why;
+    return -1;
+  }
   *out = c;
   return 0;
+}
+
+static void free_lanes(bevgen_ctx* c) {
+  for (auto& l : c->lanes) {
+    cudaFree(l.raw); cudaFree(l.bvm); free_scratch(l.sc); free_io(l.in, l.out);
+    if (l.ev_h2d) cudaEventDestroy(l.ev_h2d); if (l.ev_comp) cudaEventDestroy(l.ev_comp); if (l.ev_d2h) cudaEventDestroy(l.ev_d2h);
+    l = Lane();
+  }
+  c->lanes_ready = false;
+}
+static void free_slot(Slot& s) {
+  free_scratch(s.sc); free_io(s.in, s.out); cudaFreeHost(s.pin_in); cudaFreeHost(s.pin_out); cudaFree(s.offs_d);
+  if (s.st) cudaStreamDestroy(s.st); if (s.done) cudaEventDestroy(s.done);
+  s = Slot();
 }
 
 extern "C" void bevgen_destroy(bevgen_ctx* c) {
@@ -241,13 +287,17 @@ extern "C" void bevgen_destroy(bevgen_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_scratch(c->sc_dev);
-  for (int i = 0; i < bevgen_ctx::MAX_AUX; i++) if (c->s_aux[i]) { free_scratch(c->sc_aux[i]); cudaStreamDestroy(c->s_aux[i]); cudaEventDestroy(c->ev_join[i]); }
+  for (int i = 0; i < bevgen_ctx::MAX_AUX; i++) {
+    free_scratch(c->sc_aux[i]);
+    if (c->s_aux[i]) cudaStreamDestroy(c->s_aux[i]);
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+  }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-  if (c->lanes_ready) for (auto& l : c->lanes) { cudaFree(l.raw); cudaFree(l.bvm); free_scratch(l.sc); free_io(l.in, l.out); cudaEventDestroy(l.ev_h2d); cudaEventDestroy(l.ev_comp); cudaEventDestroy(l.ev_d2h); }
-  for (auto& s : c->slots) { free_scratch(s.sc); free_io(s.in, s.out); cudaFreeHost(s.pin_in); cudaFreeHost(s.pin_out); cudaFree(s.offs_d); cudaStreamDestroy(s.st); cudaEventDestroy(s.done); }
-  cudaFree(c->cnt_lut); cudaFree(c->offs_d); cudaFree(c->tmp);
-  for (auto& e : c->pev) cudaEventDestroy(e);
-  cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h);
+  free_lanes(c);
+  for (auto& s : c->slots) free_slot(s);
+  cudaFree(c->cnt_lut); cudaFree(c->offs_d); cudaFree(c->tmp); cudaFree(c->diag_d);
+  for (auto& e : c->pev) if (e) cudaEventDestroy(e);
+  if (c->s_copy) cudaStreamDestroy(c->s_copy); if (c->s_comp) cudaStreamDestroy(c->s_comp); if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   delete c;
 }
 
@@ -259,9 +309,13 @@ extern "C" void bevgen_destroy(bevgen_ctx* c) {
 //   sweep  = sector_mean                                          (MIO / latency bound, few warps per SM)
 //   back   = finalize_bin_scatter                                 (HBM + shared-memory bound)
 struct WaveArgs { const Scratch* sc; int nf; const int64_t* offs_d; int64_t base; int max_n; DevIn in; DevOut out; int frame0;
-                  int64_t qbase, n_pts; };   // qbase: 32-aligned caller offset of the wave's first point; n_pts: points of the wave (+ alignment slack)
+                  int64_t qbase, n_pts;   // qbase: 32-aligned caller offset of the wave's first point; n_pts: points of the wave (+ alignment slack)
+                  bool compact; };        // compact staging format in (in.inten = u32 meta), compact outputs (out.label = ground bits, out.multi = bit planes)
+
+struct NvtxRange { explicit NvtxRange(const char* n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } };
 
 static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {
+  NvtxRange nv("bevgen front: order + ground_mark");
   const SensorDev& sp = c->sp;
   const size_t S = sp.S;
   auto mark = [&](int i) { if (prof) cudaEventRecord(c->pev[i], st); };
@@ -277,13 +331,22 @@ static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
   if (fused_order(sp)) {
     const size_t W = (S + 31) / 32;
     uint32_t *occ = w.sc->occ, *cont = occ + (size_t)w.sc->frames * W, *cpre = cont + (size_t)w.sc->frames * W;
-    k_order_winners<<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, row, col, occ, cont, cpre, w.sc->cwin, w.qbase, w.sc->cpt);
-    mark(2);
     dim3 g((std::max<int>(w.max_n, (int)S) + SCAT_T - 1) / SCAT_T, w.nf);
-    k_order_scatter<<<g, SCAT_T, 0, st>>>(sp, c->xf, w.offs_d, w.frame0, c->cw_stride, x, y, z, it, row, col, lab, occ, cont, cpre, w.sc->cwin,
-                                       w.sc->rec, w.out.wbits, w.qbase, w.sc->cpt);
+    if (w.compact) {
+      const uint16_t* meta = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint32_t*>(w.in.inten) - w.base);
+      k_order_winners<true><<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, meta, nullptr, occ, cont, cpre, w.sc->cwin, w.qbase, w.sc->cpt);
+      mark(2);
+      k_order_scatter<true><<<g, SCAT_T, 0, st>>>(sp, c->xf, w.offs_d, w.frame0, c->cw_stride, x, y, z, it, nullptr, nullptr, nullptr, occ, cont, cpre, w.sc->cwin,
+                                                 w.sc->rec, w.out.wbits, w.qbase, w.sc->cpt);
+    } else {
+      k_order_winners<false><<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, row, col, occ, cont, cpre, w.sc->cwin, w.qbase, w.sc->cpt);
+      mark(2);
+      k_order_scatter<false><<<g, SCAT_T, 0, st>>>(sp, c->xf, w.offs_d, w.frame0, c->cw_stride, x, y, z, it, row, col, lab, occ, cont, cpre, w.sc->cwin,
+                                                  w.sc->rec, w.out.wbits, w.qbase, w.sc->cpt);
+    }
     c->launches += 2;
   } else {   // range image too large for shared memory: claim table in global memory (two kernels + the winner bits)
+    if (w.compact) return fail("compact staging format: range image too large (needs the shared-memory ordering kernels)");
     if (w.max_n > 0) {
       dim3 g((w.max_n + 511) / 512, w.nf);
       k_order_claim<<<g, 256, 0, st>>>(sp, w.offs_d, row, col, w.sc->owner);
@@ -300,7 +363,8 @@ static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
   mark(3);
   {
     dim3 g((sp.H + GM_T - 1) / GM_T, w.nf);
-    k_ground_mark<<<g, GM_T, 0, st>>>(sp, w.sc->rec, w.sc->gkey, w.sc->gz, w.sc->cnt, w.sc->gsum);
+    if (sp.libm_double || sp.diag) k_ground_mark<true><<<g, GM_T, 0, st>>>(sp, w.sc->rec, w.sc->gmask, w.sc->gz, w.sc->cnt, w.sc->gsum);
+    else k_ground_mark<false><<<g, GM_T, 0, st>>>(sp, w.sc->rec, w.sc->gmask, w.sc->gz, w.sc->cnt, w.sc->gsum);
   }
   mark(4);
   CK(cudaGetLastError());
@@ -308,23 +372,27 @@ static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
   return 0;
 }
 static int wave_sweep(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {
+  NvtxRange nv("bevgen sweep: sector means");
   // segment form first; frames it cannot hold (> seg_cap segments) raise slow[f] and are swept by k_sector_mean
-  k_seg_build<<<w.nf, SEGT, SMEM_SEG, st>>>(c->sp, c->seg_cap, w.sc->gsum, w.sc->gkey, w.sc->avg, w.sc->slow, w.sc->seg_start,
+  k_seg_build<<<w.nf, SEGT, SMEM_SEG, st>>>(c->sp, c->seg_cap, w.sc->gsum, w.sc->rec, w.sc->avg, w.sc->slow, w.sc->seg_start,
                                             w.sc->seg_len, w.sc->kdesc, w.sc->act, w.sc->n_act);
+  const dim3 fg(w.nf, FOLD_PASSES / c->fold_wpb), fb(32, c->fold_wpb);
   if ((c->sp.S & 3) == 0)   // every frame of gz starts on a 16-byte boundary: 128-bit loads
-    k_seg_fold<true><<<dim3(w.nf, FOLD_PASSES), 32, 0, st>>>(c->sp, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->slow, w.sc->seg_start, w.sc->seg_len,
-                                                             w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->avg);
+    k_seg_fold<true><<<fg, fb, 0, st>>>(c->sp, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->slow, w.sc->seg_start, w.sc->seg_len,
+                                        w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->avg);
   else
-    k_seg_fold<false><<<dim3(w.nf, FOLD_PASSES), 32, 0, st>>>(c->sp, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->slow, w.sc->seg_start, w.sc->seg_len,
-                                                              w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->avg);
-  k_sector_mean<<<w.nf, 32, 2 * NSECT * sizeof(float), st>>>(c->sp, w.sc->gkey, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->avg, w.sc->slow);
+    k_seg_fold<false><<<fg, fb, 0, st>>>(c->sp, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->slow, w.sc->seg_start, w.sc->seg_len,
+                                         w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->avg);
+  k_sector_mean<<<w.nf, 32, 2 * NSECT * sizeof(float), st>>>(c->sp, w.sc->rec, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->avg, w.sc->slow);
   if (prof) cudaEventRecord(c->pev[5], st);
   CK(cudaGetLastError());
   c->launches += 3;
   return 0;
 }
 static int wave_back(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {
-  k_finalize_bin<<<w.nf, 1024, SMEM_BIN, st>>>(c->sp, w.sc->rec, w.sc->gkey, w.sc->avg, w.out.label, w.out.single, w.out.multi);
+  NvtxRange nv("bevgen back: finalize + bin + scatter");
+  if (w.compact) k_finalize_bin<true><<<w.nf, 1024, SMEM_BIN, st>>>(c->sp, w.sc->rec, w.sc->gmask, w.sc->avg, w.out.label, w.out.single, w.out.multi);
+  else k_finalize_bin<false><<<w.nf, 1024, SMEM_BIN, st>>>(c->sp, w.sc->rec, w.sc->gmask, w.sc->avg, w.out.label, w.out.single, w.out.multi);
   if (prof) cudaEventRecord(c->pev[6], st);
   CK(cudaGetLastError());
   c->launches += 1;
@@ -345,9 +413,9 @@ static int wave_back(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pro
 }
 // all three stages back to back on one stream
 static int run_wave(bevgen_ctx* c, cudaStream_t st, const Scratch& sc, int nf, const int64_t* offs_d, int64_t base, int max_n,
-                    const DevIn& in, const DevOut& out, bool prof, int frame0, int64_t first_pt, int64_t end_pt) {
+                    const DevIn& in, const DevOut& out, bool prof, int frame0, int64_t first_pt, int64_t end_pt, bool compact = false) {
   const int64_t qbase = first_pt & ~(int64_t)31;
-  WaveArgs w{&sc, nf, offs_d, base, max_n, in, out, frame0, qbase, end_pt - qbase};
+  WaveArgs w{&sc, nf, offs_d, base, max_n, in, out, frame0, qbase, end_pt - qbase, compact};
   if (wave_front(c, st, w, prof)) return -1;
   if (wave_sweep(c, st, w, prof)) return -1;
   return wave_back(c, st, w, prof);
@@ -435,8 +503,7 @@ extern "C" int bevgen_sync(bevgen_ctx* c) {
 // D2H of chunk k-1 overlap (the device path uses max_frames_per_batch-sized waves instead).
 static int host_chunk(const bevgen_ctx* c) { return std::min(c->max_frames, 48); }
 
-static int ensure_lanes(bevgen_ctx* c) {
-  if (c->lanes_ready) return 0;
+static int alloc_lanes(bevgen_ctx* c) {
   for (auto& l : c->lanes) {
     if (alloc_scratch(l.sc, host_chunk(c), c->sp, c->max_pts)) return -1;
     if (alloc_io(l.in, l.out, host_chunk(c), c->max_pts, c->sp.S)) return -1;
@@ -444,13 +511,29 @@ static int ensure_lanes(bevgen_ctx* c) {
     CK(cudaEventCreateWithFlags(&l.ev_comp, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&l.ev_d2h, cudaEventDisableTiming));
   }
+  return 0;
+}
+static int ensure_lanes(bevgen_ctx* c) {
+  if (c->lanes_ready) return 0;
+  if (alloc_lanes(c)) {             // all or nothing: a later call starts from scratch instead of reusing half-built lanes
+    const std::string why = g_err;
+    cudaGetLastError();
+    free_lanes(c);
+    g_err = why;
+    return -1;
+  }
   c->lanes_ready = true;
   return 0;
 }
 
-// `in` (SoA) or `records` + `lay` (interleaved records, de-interleaved on the GPU by k_unpack_records) - exactly one is set.
+// `in` (SoA) or `records` + `lay` (interleaved records, de-interleaved on the GPU by k_unpack_records) or `cin` (compact
+// staging format) - exactly one is set; `out` (reference-layout outputs) or `cout` (compact outputs, only with `cin`).
 static int process_host_impl(bevgen_ctx* c, int nf, const int64_t* offsets, const bevgen_points* in, const uint8_t* records,
-                             const RecLayout* lay, const bevgen_outputs* out) {
+                             const RecLayout* lay, const bevgen_outputs* out, const bevgen_points_compact* cin = nullptr,
+                             const bevgen_outputs_compact* cout = nullptr) {
+  static const bevgen_outputs no_out = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  const bool compact = cin != nullptr;
+  if (compact) out = &no_out;
   CK(cudaSetDevice(c->device));
   if (ensure_lanes(c)) return -1;
   int max_n_all = 0;
@@ -479,8 +562,14 @@ static int process_host_impl(bevgen_ctx* c, int nf, const int64_t* offsets, cons
     for (int f = f0; f < f0 + n; f++) max_n = std::max<int64_t>(max_n, offsets[f + 1] - offsets[f]);
     // inputs of this lane may be overwritten once the kernels of its previous wave are done
     if (l.used) CK(cudaStreamWaitEvent(c->s_copy, l.ev_comp, 0));
+    nvtxRangePushA("bevgen H2D enqueue");
     if (records) {
       CK(cudaMemcpyAsync(l.raw, records + (size_t)base * lay->stride, np * lay->stride, cudaMemcpyHostToDevice, c->s_copy));
+    } else if (compact) {   // 16 bytes per point: x, y, z + (slot | flags); l.in.inten holds the meta words
+      CK(cudaMemcpyAsync(l.in.x, cin->x + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
+      CK(cudaMemcpyAsync(l.in.y, cin->y + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
+      CK(cudaMemcpyAsync(l.in.z, cin->z + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
+      CK(cudaMemcpyAsync(l.in.inten, cin->meta + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
     } else {
       CK(cudaMemcpyAsync(l.in.x, in->x + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
       CK(cudaMemcpyAsync(l.in.y, in->y + base, np * 4, cudaMemcpyHostToDevice, c->s_copy));
@@ -490,6 +579,7 @@ static int process_host_impl(bevgen_ctx* c, int nf, const int64_t* offsets, cons
       CK(cudaMemcpyAsync(l.in.col, in->col + base, np * 2, cudaMemcpyHostToDevice, c->s_copy));
       CK(cudaMemcpyAsync(l.in.label, in->label + base, np * 2, cudaMemcpyHostToDevice, c->s_copy));
     }
+    nvtxRangePop();
     CK(cudaEventRecord(l.ev_h2d, c->s_copy));
     CK(cudaStreamWaitEvent(c->s_comp, l.ev_h2d, 0));
     if (l.used) CK(cudaStreamWaitEvent(c->s_comp, l.ev_d2h, 0));   // outputs of the previous wave have left
@@ -506,14 +596,24 @@ static int process_host_impl(bevgen_ctx* c, int nf, const int64_t* offsets, cons
     // winner words of this chunk: [w0, w1) of the caller's array; the kernel indexes with absolute offsets / frame ids
     const size_t w0 = (size_t)(base >> 5) + (size_t)f0, w1 = (size_t)(offsets[f0 + n] >> 5) + (size_t)(f0 + n);
     DevOut lo = l.out; lo.wbits = l.out.wbits - w0; lo.bvm = out->bvm ? l.bvm : nullptr;
-    if (run_wave(c, c->s_comp, l.sc, n, c->offs_d + f0, base, max_n, l.in, lo, false, f0, offsets[f0], offsets[f0 + n])) return -1;
+    if (run_wave(c, c->s_comp, l.sc, n, c->offs_d + f0, base, max_n, l.in, lo, false, f0, offsets[f0], offsets[f0 + n], compact)) return -1;
     CK(cudaEventRecord(l.ev_comp, c->s_comp));
     CK(cudaStreamWaitEvent(c->s_d2h, l.ev_comp, 0));
-    CK(cudaMemcpyAsync(out->label + (size_t)f0 * S, l.out.label, (size_t)n * S * 2, cudaMemcpyDeviceToHost, c->s_d2h));
-    CK(cudaMemcpyAsync(out->winner_bits + w0, l.out.wbits, (w1 - w0) * 4, cudaMemcpyDeviceToHost, c->s_d2h));
-    CK(cudaMemcpyAsync(out->single_bev + (size_t)f0 * CELLS, l.out.single, (size_t)n * CELLS, cudaMemcpyDeviceToHost, c->s_d2h));
-    CK(cudaMemcpyAsync(out->multi_bev + (size_t)f0 * LAYERS * CELLS, l.out.multi, (size_t)n * LAYERS * CELLS, cudaMemcpyDeviceToHost, c->s_d2h));
-    if (out->bvm) CK(cudaMemcpyAsync(out->bvm + (size_t)f0 * BVM_CELLS, l.bvm, (size_t)n * BVM_CELLS * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
+    nvtxRangePushA("bevgen D2H enqueue");
+    if (compact) {   // ground bits (in the lane's label buffer), winner bits, single, the three occupancy bit planes
+      const size_t GW = (S + 31) / 32;
+      CK(cudaMemcpyAsync(cout->ground_bits + (size_t)f0 * GW, l.out.label, (size_t)n * GW * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+      CK(cudaMemcpyAsync(cout->winner_bits + w0, l.out.wbits, (w1 - w0) * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+      CK(cudaMemcpyAsync(cout->single_bev + (size_t)f0 * CELLS, l.out.single, (size_t)n * CELLS, cudaMemcpyDeviceToHost, c->s_d2h));
+      CK(cudaMemcpyAsync(cout->multi_planes + (size_t)f0 * 3 * CELLS, l.out.multi, (size_t)n * 3 * CELLS, cudaMemcpyDeviceToHost, c->s_d2h));
+    } else {
+      CK(cudaMemcpyAsync(out->label + (size_t)f0 * S, l.out.label, (size_t)n * S * 2, cudaMemcpyDeviceToHost, c->s_d2h));
+      CK(cudaMemcpyAsync(out->winner_bits + w0, l.out.wbits, (w1 - w0) * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+      CK(cudaMemcpyAsync(out->single_bev + (size_t)f0 * CELLS, l.out.single, (size_t)n * CELLS, cudaMemcpyDeviceToHost, c->s_d2h));
+      CK(cudaMemcpyAsync(out->multi_bev + (size_t)f0 * LAYERS * CELLS, l.out.multi, (size_t)n * LAYERS * CELLS, cudaMemcpyDeviceToHost, c->s_d2h));
+      if (out->bvm) CK(cudaMemcpyAsync(out->bvm + (size_t)f0 * BVM_CELLS, l.bvm, (size_t)n * BVM_CELLS * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+    nvtxRangePop();
     CK(cudaEventRecord(l.ev_d2h, c->s_d2h));
     l.used = true;
   }
@@ -527,6 +627,16 @@ extern "C" int bevgen_process_host(bevgen_ctx* c, int nf, const int64_t* offsets
   if (!c || !offsets || !in || !out) return fail("bevgen_process_host: null argument");
   if (nf <= 0) return 0;
   return process_host_impl(c, nf, offsets, in, nullptr, nullptr, out);
+}
+
+extern "C" int bevgen_process_host_compact(bevgen_ctx* c, int nf, const int64_t* offsets, const bevgen_points_compact* in,
+                                           const bevgen_outputs_compact* out) {
+  if (!c || !offsets || !in || !out) return fail("bevgen_process_host_compact: null argument");
+  if (!in->x || !in->y || !in->z || !in->meta || !out->ground_bits || !out->winner_bits || !out->single_bev || !out->multi_planes)
+    return fail("bevgen_process_host_compact: null array");
+  if ((unsigned)c->sp.S >= BEVGEN_META_INVALID) return fail("bevgen_process_host_compact: range image too large for a 24-bit slot index");
+  if (nf <= 0) return 0;
+  return process_host_impl(c, nf, offsets, nullptr, nullptr, nullptr, nullptr, in, out);
 }
 
 // The 26-byte record savePCDFileBinary writes for pcl::PointXYZIRCT (BatchMultiBevGen.h:56-66; `t` at byte 20 is skipped).
@@ -555,21 +665,32 @@ extern "C" int bevgen_process_packed_host(bevgen_ctx* c, int nf, const int64_t* 
 
 // ---- submit / collect (single frames in flight, one stream per ring slot) ---------------------------------------
 static size_t in_bytes(size_t n) { return n * 22; }
-static int ensure_slots(bevgen_ctx* c) {
-  if (!c->slots.empty()) return 0;
-  const int ns = std::min(c->max_frames, 8);
-  c->slots.resize(ns);
+// The ring holds up to max_frames_per_batch frames in flight (bevgen.h); a slot (one frame of scratch + staging + its own
+// stream) is only built when every existing one is busy.
+static int build_slot(bevgen_ctx* c, Slot& s) {
   const size_t S = c->sp.S;
-  for (auto& s : c->slots) {
-    if (alloc_scratch(s.sc, 1, c->sp, c->max_pts)) return -1;
-    if (alloc_io(s.in, s.out, 1, c->max_pts, S)) return -1;
-    CK(cudaHostAlloc((void**)&s.pin_in, in_bytes(c->max_pts) + 16, cudaHostAllocPortable));
-    CK(cudaHostAlloc((void**)&s.pin_out, ((size_t)c->max_pts / 32 + 4) * 4 + S * 2 + CELLS + (size_t)LAYERS * CELLS, cudaHostAllocPortable));
-    CK(cudaMalloc(&s.offs_d, 2 * sizeof(int64_t)));
-    CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-  }
+  if (alloc_scratch(s.sc, 1, c->sp, c->max_pts)) return -1;
+  if (alloc_io(s.in, s.out, 1, c->max_pts, S)) return -1;
+  CK(cudaHostAlloc((void**)&s.pin_in, in_bytes(c->max_pts) + 16, cudaHostAllocPortable));
+  CK(cudaHostAlloc((void**)&s.pin_out, ((size_t)c->max_pts / 32 + 4) * 4 + S * 2 + CELLS + (size_t)LAYERS * CELLS, cudaHostAllocPortable));
+  CK(cudaMalloc(&s.offs_d, 2 * sizeof(int64_t)));
+  CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
   return 0;
+}
+static Slot* free_ring_slot(bevgen_ctx* c) {
+  for (auto& t : c->slots) if (!t.busy) return &t;
+  if ((int)c->slots.size() >= c->max_frames) { fail("bevgen_submit: ring full — collect a frame first"); return nullptr; }
+  c->slots.emplace_back();
+  if (build_slot(c, c->slots.back())) {
+    const std::string why = g_err;
+    cudaGetLastError();
+    free_slot(c->slots.back());
+    c->slots.pop_back();
+    g_err = why;
+    return nullptr;
+  }
+  return &c->slots.back();
 }
 
 extern "C" int bevgen_submit(bevgen_ctx* c, int frame_id, int n_in, const float* x, const float* y, const float* z,
@@ -577,11 +698,9 @@ extern "C" int bevgen_submit(bevgen_ctx* c, int frame_id, int n_in, const float*
   if (!c) return fail("bevgen_submit: null ctx");
   if (n_in < 0 || n_in > c->max_pts) return fail("bevgen_submit: n_in exceeds max_points_per_frame");
   CK(cudaSetDevice(c->device));
-  if (ensure_slots(c)) return -1;
-  Slot* s = nullptr;
   for (auto& t : c->slots) { if (t.busy && t.frame_id == frame_id) return fail("bevgen_submit: frame_id already in flight"); }
-  for (auto& t : c->slots) if (!t.busy) { s = &t; break; }
-  if (!s) return fail("bevgen_submit: ring full — collect a frame first");
+  Slot* s = free_ring_slot(c);
+  if (!s) return -1;
   const size_t n = (size_t)n_in, S = c->sp.S;
   // pinned staging: [x|y|z|intensity|row|col|label] SoA, then the two offsets
   char* p = s->pin_in;
@@ -690,8 +809,9 @@ extern "C" int bevgen_labels(bevgen_ctx* c, int K, const float* xyz, int M, cons
 // ---- cloud_manip ------------------------------------------------------------------------------------------------
 extern "C" int bevgen_cloud_manip(bevgen_ctx* c, int64_t n, const float* rt, const float* x, const float* y, const float* z,
                                   float* tx, float* ty, float* tz, float* bev_in, float* bev_out) {
-  if (!c || !rt || !x || !y || !z) return fail("bevgen_cloud_manip: null argument");
+  if (!c || !rt) return fail("bevgen_cloud_manip: null argument");
   if (n < 0) return fail("bevgen_cloud_manip: n < 0");
+  if (n > 0 && (!x || !y || !z)) return fail("bevgen_cloud_manip: null point array");   // an empty cloud may come with NULL arrays
   CK(cudaSetDevice(c->device));
   const size_t np = (size_t)std::max<int64_t>(n, 1);
   if (tmp_reserve(c, 6 * Carver::pad(np * 4) + 2 * Carver::pad(MGRID * MGRID * 4))) return -1;
@@ -699,22 +819,40 @@ extern "C" int bevgen_cloud_manip(bevgen_ctx* c, int64_t n, const float* rt, con
   float* d[6]; int* g[2];
   for (int i = 0; i < 6; i++) d[i] = cv.take<float>(np);
   for (int i = 0; i < 2; i++) { g[i] = cv.take<int>(MGRID * MGRID); CK(cudaMemsetAsync(g[i], 0, MGRID * MGRID * 4, c->s_comp)); }
-  CK(cudaMemcpyAsync(d[0], x, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
-  CK(cudaMemcpyAsync(d[1], y, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
-  CK(cudaMemcpyAsync(d[2], z, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
   Xform xf; memcpy(xf.m, rt, sizeof xf.m); xf.on = 1;
   if (n > 0) {
+    CK(cudaMemcpyAsync(d[0], x, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
+    CK(cudaMemcpyAsync(d[1], y, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
+    CK(cudaMemcpyAsync(d[2], z, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
     int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
     k_cloud_manip<<<blocks, 256, 0, c->s_comp>>>(n, xf, d[0], d[1], d[2], d[3], d[4], d[5], bev_in ? g[0] : nullptr, bev_out ? g[1] : nullptr);
     CK(cudaGetLastError()); c->launches++;
   }
   CK(cudaStreamSynchronize(c->s_comp));
-  if (tx && ty && tz) {
-    CK(cudaMemcpy(tx, d[3], (size_t)n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(ty, d[4], (size_t)n * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(tz, d[5], (size_t)n * 4, cudaMemcpyDeviceToHost));
-  }
+  // every output is optional on its own
+  if (tx && n > 0) CK(cudaMemcpy(tx, d[3], (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (ty && n > 0) CK(cudaMemcpy(ty, d[4], (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (tz && n > 0) CK(cudaMemcpy(tz, d[5], (size_t)n * 4, cudaMemcpyDeviceToHost));
   if (bev_in) CK(cudaMemcpy(bev_in, g[0], MGRID * MGRID * 4, cudaMemcpyDeviceToHost));
   if (bev_out) CK(cudaMemcpy(bev_out, g[1], MGRID * MGRID * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// Device-resident form: every pointer is device memory on the context's device; the grids must hold 201*201 floats and
+// are overwritten.  Enqueued on the compute stream (bevgen_sync before reading).
+extern "C" int bevgen_cloud_manip_device(bevgen_ctx* c, int64_t n, const float* rt, const float* x, const float* y, const float* z,
+                                         float* tx, float* ty, float* tz, float* bev_in, float* bev_out) {
+  if (!c || !rt) return fail("bevgen_cloud_manip_device: null argument");
+  if (n < 0 || (n > 0 && (!x || !y || !z))) return fail("bevgen_cloud_manip_device: bad point arrays");
+  if ((tx || ty || tz) && !(tx && ty && tz)) return fail("bevgen_cloud_manip_device: tx, ty, tz must be given together");
+  CK(cudaSetDevice(c->device));
+  if (bev_in) CK(cudaMemsetAsync(bev_in, 0, MGRID * MGRID * 4, c->s_comp));
+  if (bev_out) CK(cudaMemsetAsync(bev_out, 0, MGRID * MGRID * 4, c->s_comp));
+  if (n == 0) return 0;
+  Xform xf; memcpy(xf.m, rt, sizeof xf.m); xf.on = 1;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  k_cloud_manip<<<blocks, 256, 0, c->s_comp>>>(n, xf, x, y, z, tx, ty, tz, reinterpret_cast<int*>(bev_in), reinterpret_cast<int*>(bev_out));
+  CK(cudaGetLastError()); c->launches++;
   return 0;
 }
 
@@ -829,14 +967,40 @@ extern "C" void* bevgen_compute_stream(bevgen_ctx* c) { return c ? (void*)c->s_c
 
 extern "C" int bevgen_debug_atan2f(bevgen_ctx* c, int64_t n, const float* y, const float* x, float* out) {
   if (!c || !y || !x || !out) return fail("bevgen_debug_atan2f: null argument");
+  if (n <= 0) return 0;
   CK(cudaSetDevice(c->device));
-  float *dy = 0, *dx = 0, *dout = 0;
-  CK(cudaMalloc(&dy, n * 4)); CK(cudaMalloc(&dx, n * 4)); CK(cudaMalloc(&dout, n * 4));
-  CK(cudaMemcpy(dy, y, n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice));
+  if (tmp_reserve(c, 3 * Carver::pad((size_t)n * 4))) return -1;
+  Carver cv{c->tmp};
+  float* dy = cv.take<float>((size_t)n); float* dx = cv.take<float>((size_t)n); float* dout = cv.take<float>((size_t)n);
+  CK(cudaMemcpyAsync(dy, y, n * 4, cudaMemcpyHostToDevice, c->s_comp)); CK(cudaMemcpyAsync(dx, x, n * 4, cudaMemcpyHostToDevice, c->s_comp));
   k_debug_atan2f<<<(unsigned)((n + 255) / 256), 256, 0, c->s_comp>>>(n, dy, dx, dout);
   CK(cudaGetLastError()); c->launches++;
+  CK(cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, c->s_comp));
   CK(cudaStreamSynchronize(c->s_comp));
-  CK(cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost));
-  cudaFree(dy); cudaFree(dx); cudaFree(dout);
+  return 0;
+}
+
+// ---- libm overload set of the ground criterion + diagnostics ------------------------------------------------------
+extern "C" int bevgen_set_libm(bevgen_ctx* c, int use_double) {
+  if (!c) return fail("bevgen_set_libm: null ctx");
+  c->sp.libm_double = use_double ? 1 : 0;
+  return 0;
+}
+extern "C" int bevgen_set_diag(bevgen_ctx* c, int enabled) {
+  if (!c) return fail("bevgen_set_diag: null ctx");
+  CK(cudaSetDevice(c->device));
+  if (bevgen_sync(c)) return -1;
+  CK(cudaMemset(c->diag_d, 0, 4 * sizeof(unsigned long long)));
+  c->sp.diag = enabled ? c->diag_d : nullptr;
+  return 0;
+}
+extern "C" int bevgen_get_diag(bevgen_ctx* c, uint64_t* out) {
+  if (!c || !out) return fail("bevgen_get_diag: null argument");
+  CK(cudaSetDevice(c->device));
+  if (bevgen_sync(c)) return -1;
+  for (auto& s : c->slots) if (s.st) CK(cudaStreamSynchronize(s.st));
+  unsigned long long h[4];
+  CK(cudaMemcpy(h, c->diag_d, sizeof h, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; i++) out[i] = h[i];
   return 0;
 }

@@ -8,7 +8,7 @@
 // HBM layout per frame f of a batch (S = N_SCAN * Horizon_SCAN slots):
 //   owner [f][S]  u32   1 + winning input index per slot (0 = empty)        — output
 //   rec   [f][S]  f32x4 ordered cloud: x, y, z, w = {label:16 | I==-1:1 | owned:1} — scratch, written once
-//   gkey  [f][S]  u16   sector id (row*50+col) of slots with ground_mat == 1 after loop 1, else 0xFFFF — scratch
+//   gmask [f][G+1][ceil(H/32)] u32  ground_mat == 1 after loop 1, one bit per slot of the band rows  — scratch
 //   gz    [f][S]  f32   z of those slots (0 elsewhere)                       — scratch
 //   cnt   [f][3750] u32 zero-height ground slots per sector (the others are counted by the fold);  avg [f][3750] f32 sector mean heights — scratch
 //   label [f][S] i16, single [f][224*224] u8, multi [f][24][224*224] u8      — outputs
@@ -36,6 +36,9 @@ struct SensorDev {
   // ground criterion constants (computed on the host at context creation, see bevgen_capi.cu)
   float t_star;         // largest float t with (float)((double)t*180.0/M_PI) <= 10.0f   (BatchMultiBevGen.cpp:173,179)
   float q_lo2, q_hi2;   // (tan(t_star)*(1 -/+ 1e-5))^2: outside this band of dz^2/(dx^2+dy^2) no atan2f is needed
+  int libm_double;      // 1: decide borderline pairs with the C double atan2 / sqrt (the other overload set)
+  unsigned long long* diag;   // NULL, or device counters: [0] pairs inside the guard band, [1] pairs where the float- and
+                              // the double-libm decision differ
 };
 
 struct Xform { float m[12]; int on; };
@@ -441,6 +444,9 @@ __device__ __forceinline__ uint4 ld8_u16(const uint16_t* aligned_base, int v8) {
   return __ldg(reinterpret_cast<const uint4*>(aligned_base) + v8);
 }
 
+// PACKED (bevgen_process_host_compact): `row` points at the u32 meta array instead (slot | flags, see bevgen.h), `col` is unused.
+constexpr unsigned META_SLOT = 0x00FFFFFFu, META_NEG1 = 1u << 24, META_LABELED = 1u << 25;
+template <bool PACKED>
 __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int64_t* __restrict__ offs, int cw_stride,
                                                           const uint16_t* __restrict__ row, const uint16_t* __restrict__ col,
                                                           uint32_t* __restrict__ occ_bits, uint32_t* __restrict__ cont_bits,
@@ -465,9 +471,9 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
   for (int i = tid; i < W; i += ORD_T) { occ[i] = 0u; cont[i] = 0u; }
   __syncthreads();
   // ---- scan 1: occupancy + contention bits ----
-  auto visit1 = [&](unsigned r, unsigned c, int i) {
-    if (i >= 0 && i < n && r < N && c < H) {                        // :106-109
-      const unsigned slot = r * H + c, bit = 1u << (slot & 31);
+  auto visit1 = [&](unsigned slot, bool ok) {
+    if (ok) {                                                       // :106-109
+      const unsigned bit = 1u << (slot & 31);
       if (atomicOr(&occ[slot >> 5], bit) & bit) atomicOr(&cont[slot >> 5], bit);
     }
   };
@@ -475,9 +481,9 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
   // point's slot is contended.  k_order_scatter reads it coalesced, so only the 0.5 % contended points pay the random
   // cont_bits / cont_pre / cwin lookups (ncu: those lookups were 0.76 L2 sector reads per point, a fifth of its L2 traffic).
   const int64_t q0 = o - qbase;
-  auto visit2 = [&](unsigned r, unsigned c, int i) {
-    if (i >= 0 && i < n && r < N && c < H) {
-      const unsigned slot = r * H + c, bit = 1u << (slot & 31), cw = cont[slot >> 5];
+  auto visit2 = [&](unsigned slot, bool ok, int i) {
+    if (ok) {
+      const unsigned bit = 1u << (slot & 31), cw = cont[slot >> 5];
       if (cw & bit) {
         atomicMax(&cwin[(size_t)f * cw_stride + occ[slot >> 5] + __popc(cw & (bit - 1u))], (uint32_t)i + 1u);
         const int64_t q = q0 + i;
@@ -485,25 +491,44 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
       }
     }
   };
+  // visit(slot, valid, input index) over the frame's points, 16 bytes per load where the alignment allows
   auto scan = [&](auto visit) {
+    if (PACKED) {
+      const uint32_t* M = reinterpret_cast<const uint32_t*>(row) + o;
+      const int mis4 = (int)((reinterpret_cast<uintptr_t>(M) >> 2) & 3);
+      const uint32_t* Ma = M - mis4;
+      const int n4 = (n + mis4 + 3) >> 2;
+      for (int v = tid; v < n4; v += ORD_T) {
+        const int i = v * 4 - mis4;
+        if (i < 0 || i + 4 > n) {
+          for (int k = max(i, 0); k < min(i + 4, n); k++) { const unsigned sl = M[k] & META_SLOT; visit(sl, sl < (unsigned)sp.S, k); }
+          continue;
+        }
+        const uint4 mm = __ldg(reinterpret_cast<const uint4*>(Ma) + v);
+        visit(mm.x & META_SLOT, (mm.x & META_SLOT) < (unsigned)sp.S, i);     visit(mm.y & META_SLOT, (mm.y & META_SLOT) < (unsigned)sp.S, i + 1);
+        visit(mm.z & META_SLOT, (mm.z & META_SLOT) < (unsigned)sp.S, i + 2); visit(mm.w & META_SLOT, (mm.w & META_SLOT) < (unsigned)sp.S, i + 3);
+      }
+      return;
+    }
+    auto rc = [&](unsigned r, unsigned c, int i) { visit(r * H + c, i >= 0 && i < n && r < N && c < H, i); };
     if (vec) {
       for (int v = tid; v < n8; v += ORD_T) {
         const int i = v * 8 - mis;
         if (i < 0 || i + 8 > n) {                                   // head / tail block: stay inside the frame's elements
-          for (int k = max(i, 0); k < min(i + 8, n); k++) visit(R[k], C[k], k);
+          for (int k = max(i, 0); k < min(i + 8, n); k++) rc(R[k], C[k], k);
           continue;
         }
         const uint4 rr = ld8_u16(Ra, v), cc = ld8_u16(Ca, v);
-        visit(rr.x & 0xFFFFu, cc.x & 0xFFFFu, i);     visit(rr.x >> 16, cc.x >> 16, i + 1);
-        visit(rr.y & 0xFFFFu, cc.y & 0xFFFFu, i + 2); visit(rr.y >> 16, cc.y >> 16, i + 3);
-        visit(rr.z & 0xFFFFu, cc.z & 0xFFFFu, i + 4); visit(rr.z >> 16, cc.z >> 16, i + 5);
-        visit(rr.w & 0xFFFFu, cc.w & 0xFFFFu, i + 6); visit(rr.w >> 16, cc.w >> 16, i + 7);
+        rc(rr.x & 0xFFFFu, cc.x & 0xFFFFu, i);     rc(rr.x >> 16, cc.x >> 16, i + 1);
+        rc(rr.y & 0xFFFFu, cc.y & 0xFFFFu, i + 2); rc(rr.y >> 16, cc.y >> 16, i + 3);
+        rc(rr.z & 0xFFFFu, cc.z & 0xFFFFu, i + 4); rc(rr.z >> 16, cc.z >> 16, i + 5);
+        rc(rr.w & 0xFFFFu, cc.w & 0xFFFFu, i + 6); rc(rr.w >> 16, cc.w >> 16, i + 7);
       }
     } else {
-      for (int i = tid; i < n; i += ORD_T) visit(R[i], C[i], i);
+      for (int i = tid; i < n; i += ORD_T) rc(R[i], C[i], i);
     }
   };
-  scan(visit1);
+  scan([&](unsigned slot, bool ok, int) { visit1(slot, ok); });
   __syncthreads();
   // ---- occupancy / contention bits out; dense ids of the contended slots (prefix popcount, kept in `occ`) ----
   for (int w = tid; w < W; w += ORD_T) { occ_bits[(size_t)f * W + w] = occ[w]; cont_bits[(size_t)f * W + w] = cont[w]; }
@@ -533,6 +558,7 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
 #ifndef SCAT_T
 #define SCAT_T 128   // measured: 1.21 / 1.205 / 1.264 / 1.35 us per frame for 64 / 128 / 256 / 512 threads
 #endif
+template <bool PACKED>   // PACKED: `inten` points at the u32 meta array (slot | flags); row / col / label are unused
 __global__ void __launch_bounds__(SCAT_T) k_order_scatter(SensorDev sp, Xform xf, const int64_t* __restrict__ offs, int frame0, int cw_stride,
                                                         const float* __restrict__ x, const float* __restrict__ y,
                                                         const float* __restrict__ z, const float* __restrict__ inten,
@@ -556,10 +582,21 @@ __global__ void __launch_bounds__(SCAT_T) k_order_scatter(SensorDev sp, Xform xf
     for (int64_t w = (n + 31) >> 5; w < ((o + n) >> 5) + 1 - (o >> 5); w++) wb[w] = 0u;
   if (i - lane >= n) return;                                        // whole warp past the end
   // every load of the point is issued before the winner test: 99.5 % of the points win
-  unsigned r = 0xFFFFu, c = 0xFFFFu; float px = 0.f, py = 0.f, pz = 0.f, pi = 0.f; int16_t lb = 0;
-  if (i < n) { r = row[o + i]; c = col[o + i]; px = __ldcs(x + o + i); py = __ldcs(y + o + i); pz = __ldcs(z + o + i); pi = __ldcs(inten + o + i); lb = __ldcs(label + o + i); }
-  const bool valid = r < (unsigned)sp.N && c < (unsigned)sp.H;      // :106-109
-  const unsigned slot = valid ? r * sp.H + c : 0u, bit = 1u << (slot & 31);
+  float px = 0.f, py = 0.f, pz = 0.f; unsigned lb16 = 0u; bool neg1 = false, valid = false; unsigned slot = 0u;
+  if (PACKED) {
+    unsigned m = META_SLOT;
+    if (i < n) { m = __ldcs(reinterpret_cast<const uint32_t*>(inten) + o + i); px = __ldcs(x + o + i); py = __ldcs(y + o + i); pz = __ldcs(z + o + i); }
+    slot = m & META_SLOT; valid = slot < (unsigned)sp.S;
+    neg1 = (m & META_NEG1) != 0u; lb16 = (m & META_LABELED) ? 1u : 0u;    // the device only ever tests label != 0
+    if (!valid) slot = 0u;
+  } else {
+    unsigned r = 0xFFFFu, c = 0xFFFFu; float pi = 0.f; int16_t lb = 0;
+    if (i < n) { r = row[o + i]; c = col[o + i]; px = __ldcs(x + o + i); py = __ldcs(y + o + i); pz = __ldcs(z + o + i); pi = __ldcs(inten + o + i); lb = __ldcs(label + o + i); }
+    valid = r < (unsigned)sp.N && c < (unsigned)sp.H;      // :106-109
+    slot = valid ? r * sp.H + c : 0u;
+    neg1 = pi == -1.0f; lb16 = (unsigned)(uint16_t)lb;
+  }
+  const unsigned bit = 1u << (slot & 31);
   bool win = valid;
   const int64_t q = o + i - qbase;
   if (valid && ((cpt_bits[q >> 5] >> (q & 31)) & 1u)) {   // contended slot (rare): the serial loop's last writer = largest index
@@ -575,7 +612,7 @@ __global__ void __launch_bounds__(SCAT_T) k_order_scatter(SensorDev sp, Xform xf
     const float oz = __fadd_rn(__fmul_rn(px, xf.m[8]), __fadd_rn(__fmul_rn(py, xf.m[9]), __fadd_rn(__fmul_rn(pz, xf.m[10]), xf.m[11])));
     px = ox; py = oy; pz = oz;
   }
-  const unsigned w = (unsigned)(uint16_t)lb | W_OWNED | (pi == -1.0f ? W_NEG1 : 0u);
+  const unsigned w = lb16 | W_OWNED | (neg1 ? W_NEG1 : 0u);
   rec[fb + slot] = make_float4(px, py, pz, __uint_as_float(w));
 }
 
@@ -584,11 +621,14 @@ __global__ void __launch_bounds__(SCAT_T) k_order_scatter(SensorDev sp, Xform xf
 // walking rows N-1 .. N-G like the reference; consecutive lanes = consecutive columns, so every record load is a
 // coalesced 512-byte warp access and the "upper" record is reused as the next "lower".
 // Closed form of the row-descending overwrite order:  gm[r] = -1 if invalid(r) else (ground(r) | ground(r+1)).
-// Emits gkey / gz for rows [N-G-1, N) and warp-aggregated per-sector counts (loop 2's `num`, :205).
+// Emits gz and the ground_mat bits for rows [N-G-1, N), the per-group segment summaries and the count of zero-height
+// ground slots per sector (loop 2's `num`, :205; the fold counts the others).
 // grid (ceil(H/GM_T), F), block GM_T.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool is_neg1(const float4& p) { return (__float_as_uint(p.w) & W_NEG1) != 0; }
 
+// DBL: also evaluate the double overload set (bevgen_set_libm / bevgen_set_diag); the default instantiation carries none of it.
+template <bool DBL>
 __device__ __forceinline__ bool ground_decision(const SensorDev& sp, const float4& up, const float4& lo) {
   const float dx = __fsub_rn(up.x, lo.x), dy = __fsub_rn(up.y, lo.y), dz = __fsub_rn(up.z, lo.z);      // :169-171
   const float hh = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
@@ -596,18 +636,31 @@ __device__ __forceinline__ bool ground_decision(const SensorDev& sp, const float
   // Pre-filter on squares (no sqrt, no division): tan^2 thresholds carry a 2e-5 relative guard band, the three
   // roundings involved are ~2e-7, and glibc's atan2f is accurate to < 1 ulp, so outside the band the sign of
   // |atan2f(dz, sqrtf(hh))| - t_star is decided.  Only taken when nothing can overflow / underflow.
-  if (hh > 1e-30f && hh < 1e30f && zz < 1e30f) {
+  const bool in_range = hh > 1e-30f && hh < 1e30f && zz < 1e30f;
+  if (in_range) {
     if (zz <= __fmul_rn(sp.q_lo2, hh)) return true;
     if (zz >= __fmul_rn(sp.q_hi2, hh)) return false;
   }
   const float hyp = __fsqrt_rn(hh);                                                                  // :173 sqrtf
   const float t = atan2f_glibc(dz, hyp);   // borderline / special values: the exact libm value decides
-  return fabsf(t) <= sp.t_star;            // <=> fabsf((float)((double)t*180.0/M_PI)) <= 10.0f  (:173,:179)
+  const bool gf = fabsf(t) <= sp.t_star;   // <=> fabsf((float)((double)t*180.0/M_PI)) <= 10.0f  (:173,:179)
+  if (!DBL) return gf;
+  // The other overload set (no <math.h> in the include tree): atan2(double, double), sqrt(double) of the float sum, the
+  // product rounded to float on assignment.  CUDA's double atan2 is within 2 ulp of glibc's; the float rounding of the
+  // angle absorbs that except within ~1e-15 relative of a rounding boundary.
+  const double ad = __ddiv_rn(__dmul_rn(atan2((double)dz, sqrt((double)hh)), 180.0), 3.14159265358979323846);
+  const bool gd = fabsf(__double2float_rn(ad)) <= 10.0f;
+  if (sp.diag != nullptr) {
+    if (in_range) atomicAdd(&sp.diag[0], 1ull);
+    if (gf != gd) atomicAdd(&sp.diag[1], 1ull);
+  }
+  return sp.libm_double ? gd : gf;
 }
 
 constexpr int GM_T = 64;   // columns per CTA: H = 2083 columns fill 33 CTAs of 64 to 98.6 % (17 of 128: 95.7 %)
+template <bool DBL>
 __global__ void __launch_bounds__(GM_T) k_ground_mark(SensorDev sp, const float4* __restrict__ rec,
-                                                      uint16_t* __restrict__ gkey, float* __restrict__ gz,
+                                                      uint32_t* __restrict__ gmask, float* __restrict__ gz,
                                                       uint32_t* __restrict__ cnt, uint4* __restrict__ gsum) {
   const int f = blockIdx.y;
   const int c0 = blockIdx.x * GM_T + threadIdx.x;
@@ -619,35 +672,37 @@ __global__ void __launch_bounds__(GM_T) k_ground_mark(SensorDev sp, const float4
   uint32_t* const cntf = cnt + (size_t)f * NSECT;
   // everything is addressed relative to the current row and walked upwards by -H per iteration
   const float4* pr = rec + fb + (size_t)(N - 1) * H + c;        // (row r, col c)
-  uint16_t* gk = gkey + fb + (size_t)(N - 1) * H + c;
   float* gzp = gz + fb + (size_t)(N - 1) * H + c;
   const int dplus = (c + 2 >= H ? c + 2 - H : c + 2) - c;       // (col+2) % H, relative to c           (:147)
   const int dminus = -2;                                        // (col-2) % H stays negative in C++ for col < 2 (:152)
 
-  // per (row, 32-column group) summary for the segment form of loop 2 (k_sector_mean_seg)
+  // per (row, 32-column group): summary for the segment form of loop 2 (k_seg_build) and the ground_mat == 1 bits
+  // loop 3 needs (k_finalize_bin)
   const int NG = (H + 31) >> 5;
-  uint4* gs = gsum + ((size_t)f * (sp.G + 1) + sp.G) * NG + (c0 >> 5);     // row N-1 first, walked upwards by -NG
+  const size_t g0 = ((size_t)f * (sp.G + 1) + sp.G) * NG + (c0 >> 5);     // row N-1 first, walked upwards by -NG
+  uint4* gs = gsum + g0;
+  uint32_t* gm = gmask + g0;
   const unsigned lt = (1u << lane) - 1u;
 
   auto emit = [&](const float4& p, bool gm1) {
-    unsigned key = NO_KEY;
-    if (gm1) key = sector_of(p.x, p.y);
-    if (act) { *gk = (uint16_t)key; *gzp = gm1 ? p.z : 0.0f; }
-    const unsigned k2 = act ? key : NO_KEY;
-    // loop 2's count (:205) is order-free and split in two: ground slots with a non-zero height are counted by the fold
-    // (they are exactly the non-zero entries of gz inside the sector's segments); the rare ground slots of height 0
-    // (pairs of empty slots, :173 atan2(0,0) = 0) take part in no segment and are counted here.
-    if (k2 != NO_KEY && !(p.z != 0.0f)) atomicAdd(&cntf[key], 1u);
+    const bool g1 = act && gm1;
+    if (act) *gzp = gm1 ? p.z : 0.0f;
     // Loop 2's float sums (:198) only change when a non-zero height is added, so the "participating" slots are the
     // ground slots with z != 0 (NaN participates).  pm = participating lanes, hm = lanes whose sector differs from the
     // previous participating lane of this group, fk / lk = sector of the first / last participating lane.
-    const bool part = k2 != NO_KEY && p.z != 0.0f;
+    const bool part = g1 && p.z != 0.0f;
+    const unsigned k2 = g1 ? sector_of(p.x, p.y) : NO_KEY;
+    // loop 2's count (:205) is order-free and split in two: ground slots with a non-zero height are counted by the fold
+    // (they are exactly the non-zero entries of gz inside the sector's segments); the rare ground slots of height 0
+    // (pairs of empty slots, :173 atan2(0,0) = 0) take part in no segment and are counted here.
+    if (g1 && !part) atomicAdd(&cntf[k2], 1u);
+    const unsigned gmm = __ballot_sync(0xffffffffu, g1);
     const unsigned pm = __ballot_sync(0xffffffffu, part);
     const unsigned below = pm & lt;
     const unsigned pk = __shfl_sync(0xffffffffu, k2, (31 - __clz(below)) & 31);
     const unsigned hm = __ballot_sync(0xffffffffu, part && below != 0u && pk != k2);
     if (c0 - lane < H) {                                         // the group exists (warp-uniform)
-      if (lane == 0) { gs->x = pm; gs->y = hm; }
+      if (lane == 0) { gs->x = pm; gs->y = hm; *gm = gmm; }
       uint16_t* fl = reinterpret_cast<uint16_t*>(&gs->z);
       if (part && below == 0u) fl[0] = (uint16_t)k2;
       if (part && (pm >> lane) == 1u) fl[1] = (uint16_t)k2;
@@ -665,11 +720,11 @@ __global__ void __launch_bounds__(GM_T) k_ground_mark(SensorDev sp, const float4
     if (is_neg1(up)) up = pr[-H + dminus];                        // :151-154
     if (is_neg1(up) && r >= 2) up = pr[-2 * H];                   // :157-160
     const bool invalid = is_neg1(lower) || is_neg1(up);           // :162
-    const bool ground = !invalid && ground_decision(sp, up, lower);
+    const bool ground = !invalid && ground_decision<DBL>(sp, up, lower);
     emit(lower, !invalid && (ground || ground_prev));
     ground_prev = ground;
     lower = direct;
-    pr -= H; gk -= H; gzp -= H; gs -= NG;
+    pr -= H; gzp -= H; gs -= NG; gm -= NG;
   }
   emit(lower, ground_prev);   // row above the band only receives gm[row-1] = 1 (:181)
 }
@@ -683,7 +738,7 @@ __global__ void __launch_bounds__(GM_T) k_ground_mark(SensorDev sp, const float4
 // counted the zero-height ground slots, the others are counted here.  num = 0.01f + 1 + 1 ... is a pure function of the count: cnt_lut[n].
 // grid F, block 32, dynamic smem 2*NSECT*4.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t* __restrict__ gkey,
+__global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const float4* __restrict__ rec,
                                                      const float* __restrict__ gz, const uint32_t* __restrict__ cnt,
                                                      const float* __restrict__ cnt_lut, float* __restrict__ avg,
                                                      const uint32_t* __restrict__ slow_flag) {
@@ -695,17 +750,20 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const uint16_t
   for (int i = lane; i < NSECT; i += 32) { ssum[i] = 0.0f; scnt[i] = 0u; }
   __syncwarp();
   const size_t fb = (size_t)f * sp.S;
-  const uint16_t* K = gkey + fb;
+  const float4* R = rec + fb;
   const float* Z = gz + fb;
   constexpr int U = 4;
   unsigned k[U], kn[U]; float zz[U], zn[U];
+  // gz is the slot's height where ground_mat == 1 and 0 elsewhere, so "participates in a sum" <=> gz != 0 (NaN included);
+  // the sector is recomputed from the record (this sweep is the rare fallback; the segment form never reads it)
   auto load = [&](int base, unsigned* kk, float* zv) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const int idx = base + u * 32 + lane;
       const bool in = idx < sp.S;
-      kk[u] = in ? (unsigned)K[idx] : NO_KEY;
       zv[u] = in ? Z[idx] : 0.0f;
+      kk[u] = NO_KEY;
+      if (in && zv[u] != 0.0f) { const float4 p = R[idx]; kk[u] = sector_of(p.x, p.y); }
     }
   };
   int base = sp.band_row0 * sp.H;
@@ -771,18 +829,14 @@ constexpr int SEG_CAP = 4096;
 constexpr int SEGT = 512;
 constexpr int SMEM_SEG = SEG_CAP * 4 * 2 + NSECT * 4 + SEGT * 8 + 320 + SEG_CAP * 2 * 3 + (NSECT + 2) * 2;   // 84,264 B
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-#ifndef FOLD_AHEAD_N
-#define FOLD_AHEAD_N 6   // measured flat between 3 and 12
-#endif
 #ifndef FOLD_STEP_N
 #define FOLD_STEP_N 32   // 16 is 10 % slower
 #endif
-constexpr int FOLD_AHEAD = FOLD_AHEAD_N;           // segments prefetched ahead of the chain in k_seg_fold
 constexpr int FOLD_STEP = FOLD_STEP_N;           // heights per step of a chain in k_seg_fold
 constexpr int FOLD_PASSES = 12;         // warps per frame in k_seg_fold (32 sectors each; more sectors wrap around)
 
 __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const uint4* __restrict__ gsum,
-                                                     const uint16_t* __restrict__ gkey, float* __restrict__ avg,
+                                                     const float4* __restrict__ rec, float* __restrict__ avg,
                                                      uint32_t* __restrict__ slow_flag, uint32_t* __restrict__ seg_start,
                                                      uint16_t* __restrict__ seg_len, uint32_t* __restrict__ kdesc,
                                                      uint16_t* __restrict__ act, uint32_t* __restrict__ n_act_out) {
@@ -806,7 +860,7 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
   const int gpt = (n_groups + SEGT - 1) / SEGT;                 // consecutive groups per thread
   const uint4* GS = gsum + (size_t)f * n_groups;
   const size_t fb = (size_t)f * sp.S;
-  const uint16_t* K = gkey + fb;
+  const float4* R = rec + fb;
   const int g0 = min(tid * gpt, n_groups), g1 = min(g0 + gpt, n_groups);
   auto slot_of = [&](int g, int l) { const int rb = g / NG, cg = g - rb * NG; return (sp.band_row0 + rb) * H + cg * 32 + l; };
   // exclusive block scan of one value per thread; returns the exclusive prefix, *total = sum over the block
@@ -895,7 +949,8 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
   __syncthreads();
   for (int e = tid; e < nseg; e += SEGT) {
     const unsigned st = s_start[e], d = s_endtmp[e] - st;
-    const unsigned k = K[st];                                     // sector of the segment (independent loads, all in flight)
+    const float4 p0 = R[st];                                      // a segment starts on a participating slot: its sector
+    const unsigned k = sector_of(p0.x, p0.y);                     // is the segment's (independent loads, all in flight)
     if (d > 0xFFFFu) s_misc[0] = 1u;                              // a segment longer than 65535 slots: sweep kernel
     s_len[e] = (uint16_t)d; s_key[e] = (uint16_t)k;
     atomicAdd(&s_kcnt[k], 1u);
@@ -970,63 +1025,106 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
 }
 
 // k_seg_fold — one LANE per active sector runs the sector's serial chain sum = fl(sum + z) (:198) over its segments in
-// slot order, straight from gz (each lane streams its own short contiguous pieces; the kernel uses no shared memory,
-// so the lines it touches live in L1).  The lane walks a flat sequence of steps of up to FOLD_STEP heights (padded
+// slot order, straight from gz.  The lane walks a flat sequence of windows of FOLD_STEP heights (16-byte aligned, padded
 // with +0, which never changes the sum), so the 32 chains of a warp stay in lockstep whatever their segment boundaries
 // are.  Then the IEEE divide (:210).
-// grid (F, FOLD_PASSES), block 32: warp p of a frame owns the active sectors p*32 + lane (+ 32*FOLD_PASSES ...).
+//
+// The chain is latency bound (round-1 ncu: 12 % warps active, one window = 8 dependent-free 128-bit loads that all miss
+// L1, then 32 dependent adds), so the address stream is decoupled from the adds: a position `pa` runs FOLD_DIST windows
+// ahead of the chain and only issues prefetches (the walk over segment descriptors does not depend on the sums); the
+// chain's own loads are issued one window ahead into a second register buffer and find their lines in L1.
+// grid (F, FOLD_PASSES / wpb), block (32, wpb): warp p of a frame owns the active sectors p*32 + lane (+ 32*FOLD_PASSES ...);
+// the list is sorted by cost, so a frame's pass 0 holds its 32 longest chains.
+#ifndef FOLD_DIST_N
+#define FOLD_DIST_N 3
+#endif
+constexpr int FOLD_DIST = FOLD_DIST_N;
+constexpr int FOLD_MAX_WPB = 4;
+
+struct FoldPos {            // a lane's position in its sector's window sequence
+  unsigned cur, end;        // current / one-past-last segment (indices into the frame's bucketed segment list)
+  unsigned j, hi;           // remaining slots [j, hi] of the current segment
+};
+__device__ __forceinline__ bool fold_valid(const FoldPos& p) { return p.cur < p.end; }
+__device__ __forceinline__ void fold_advance(FoldPos& p, const uint32_t* __restrict__ SS, const uint16_t* __restrict__ SL) {
+  const unsigned nj = (p.j & ~3u) + FOLD_STEP;
+  if (nj <= p.hi) { p.j = nj; return; }
+  p.cur++;
+  if (p.cur < p.end) { p.j = SS[p.cur]; p.hi = p.j + SL[p.cur]; }
+}
+
 template <bool VEC>
-__global__ void __launch_bounds__(32) k_seg_fold(SensorDev sp, const float* __restrict__ gz, const uint32_t* __restrict__ cnt,
+__global__ void __launch_bounds__(32 * FOLD_MAX_WPB) k_seg_fold(SensorDev sp, const float* __restrict__ gz, const uint32_t* __restrict__ cnt,
                                                   const float* __restrict__ cnt_lut, const uint32_t* __restrict__ slow_flag,
                                                   const uint32_t* __restrict__ seg_start, const uint16_t* __restrict__ seg_len,
                                                   const uint32_t* __restrict__ kdesc, const uint16_t* __restrict__ act,
                                                   const uint32_t* __restrict__ n_act_in, float* __restrict__ avg) {
-  // grid (F, FOLD_PASSES): CTAs are dispatched in linear order, so every frame's pass 0 (its 32 longest chains, the
-  // list is sorted by cost) starts before any short pass - longest-processing-time-first keeps the tail short.
   const int f = blockIdx.x;
   if (slow_flag[f]) return;                                       // the sweep kernel takes this frame
   const unsigned n_act = n_act_in[f];
   const float* Z = gz + (size_t)f * sp.S;
   const uint32_t* SS = seg_start + (size_t)f * SEG_CAP;
   const uint16_t* SL = seg_len + (size_t)f * SEG_CAP;
-  for (unsigned a = blockIdx.y * 32 + threadIdx.x; a < n_act; a += 32 * FOLD_PASSES) {
+  const unsigned pass = blockIdx.y * blockDim.y + threadIdx.y;
+  for (unsigned a = pass * 32 + threadIdx.x; a < n_act; a += 32 * FOLD_PASSES) {
     const unsigned k = act[(size_t)f * NSECT + a];
     const unsigned d = kdesc[(size_t)f * NSECT + k];
-    unsigned cur = d >> 16; const unsigned endseg = cur + (d & 0xFFFFu);
     float acc = 0.0f;
     unsigned nz = 0u;                                               // ground slots of this sector with a non-zero height (:205)
-    unsigned j = SS[cur], hi = j + SL[cur];
-    unsigned st2 = 0u, en2 = 0u;                                    // the following segment, fetched one segment ahead
-    if (cur + 1 < endseg) { st2 = SS[cur + 1]; en2 = st2 + SL[cur + 1]; }
+    if (VEC) {
+      FoldPos pc; pc.cur = d >> 16; pc.end = pc.cur + (d & 0xFFFFu); pc.j = SS[pc.cur]; pc.hi = pc.j + SL[pc.cur];
+      FoldPos pa = pc;
 #pragma unroll
-    for (int a2 = 1; a2 < FOLD_AHEAD; a2++) if (cur + a2 < endseg) prefetch_l1(Z + SS[cur + a2]);
-    // One step = a 16-byte aligned window of FOLD_STEP heights around the current position, fetched with 128-bit loads
-    // (every lane reads its own lines: the kernel is bound by L1 wavefronts, one per lane and load, so loads are wide)
-    // and all issued before the first add.  Heights outside [j, hi] are replaced by +0.
-    while (true) {
-      float v[FOLD_STEP];
-      const unsigned jb = VEC ? (j & ~3u) : j;
-      if (VEC) {
+      for (int q = 0; q < FOLD_DIST; q++) {
+        if (fold_valid(pa)) { prefetch_l1(Z + (pa.j & ~3u)); prefetch_l1(Z + (pa.j & ~3u) + FOLD_STEP - 1); fold_advance(pa, SS, SL); }
+      }
+      float4 w[FOLD_STEP / 4];
+      unsigned wj = pc.j, whi = pc.hi;                              // the window held in w
+      {
+        const float4* src = reinterpret_cast<const float4*>(Z + (pc.j & ~3u));   // gz is padded: the window may pass the frame's end
+#pragma unroll
+        for (int u = 0; u < FOLD_STEP / 4; u++) w[u] = __ldg(src + u);
+      }
+      while (true) {
+        FoldPos pn = pc; fold_advance(pn, SS, SL);
+        const bool more = fold_valid(pn);
+        float4 wn[FOLD_STEP / 4];
+        if (more) {
+          const float4* src = reinterpret_cast<const float4*>(Z + (pn.j & ~3u));
+#pragma unroll
+          for (int u = 0; u < FOLD_STEP / 4; u++) wn[u] = __ldg(src + u);
+        }
+        if (fold_valid(pa)) { prefetch_l1(Z + (pa.j & ~3u)); prefetch_l1(Z + (pa.j & ~3u) + FOLD_STEP - 1); fold_advance(pa, SS, SL); }
+        // heights outside [wj, whi] belong to other sectors (or to nobody): replaced by +0
+        const unsigned jb = wj & ~3u;
 #pragma unroll
         for (int u = 0; u < FOLD_STEP / 4; u++) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(Z + jb) + u);   // gz is padded: the window may pass the frame's end
-          v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
+          const unsigned q = jb + 4 * u;
+          const float v0 = (q >= wj && q <= whi) ? w[u].x : 0.0f, v1 = (q + 1 >= wj && q + 1 <= whi) ? w[u].y : 0.0f;
+          const float v2 = (q + 2 >= wj && q + 2 <= whi) ? w[u].z : 0.0f, v3 = (q + 3 >= wj && q + 3 <= whi) ? w[u].w : 0.0f;
+          acc = __fadd_rn(acc, v0); acc = __fadd_rn(acc, v1); acc = __fadd_rn(acc, v2); acc = __fadd_rn(acc, v3);
+          nz += (v0 != 0.0f ? 1u : 0u) + (v1 != 0.0f ? 1u : 0u) + (v2 != 0.0f ? 1u : 0u) + (v3 != 0.0f ? 1u : 0u);
         }
+        if (!more) break;
+        pc = pn; wj = pn.j; whi = pn.hi;
 #pragma unroll
-        for (int u = 0; u < FOLD_STEP; u++) { const unsigned q = jb + u; v[u] = (q >= j && q <= hi) ? v[u] : 0.0f; }
-      } else {
+        for (int u = 0; u < FOLD_STEP / 4; u++) w[u] = wn[u];
+      }
+    } else {
+      unsigned cur = d >> 16; const unsigned endseg = cur + (d & 0xFFFFu);
+      unsigned j = SS[cur], hi = j + SL[cur];
+      while (true) {
+        float v[FOLD_STEP];
 #pragma unroll
         for (int u = 0; u < FOLD_STEP; u++) { const unsigned q = j + u; v[u] = q <= hi ? Z[q] : 0.0f; }
-      }
 #pragma unroll
-      for (int u = 0; u < FOLD_STEP; u++) { acc = __fadd_rn(acc, v[u]); nz += v[u] != 0.0f ? 1u : 0u; }
-      j = jb + FOLD_STEP;
-      if (j <= hi) { if (j + 3 * FOLD_STEP <= hi) prefetch_l1(Z + j + 3 * FOLD_STEP); continue; }
-      cur++;
-      if (cur >= endseg) break;
-      j = st2; hi = en2;
-      if (cur + 1 < endseg) { st2 = SS[cur + 1]; en2 = st2 + SL[cur + 1]; }
-      if (cur + FOLD_AHEAD < endseg) prefetch_l1(Z + SS[cur + FOLD_AHEAD]);   // the chain is latency bound: pull later segments in early
+        for (int u = 0; u < FOLD_STEP; u++) { acc = __fadd_rn(acc, v[u]); nz += v[u] != 0.0f ? 1u : 0u; }
+        j += FOLD_STEP;
+        if (j <= hi) continue;
+        cur++;
+        if (cur >= endseg) break;
+        j = SS[cur]; hi = j + SL[cur];
+      }
     }
     avg[(size_t)f * NSECT + k] = __fdiv_rn(acc, cnt_lut[cnt[(size_t)f * NSECT + k] + nz]);   // :210
   }
@@ -1054,8 +1152,13 @@ __global__ void k_build_cnt_lut(int n_max, float* __restrict__ lut) {
 constexpr int SAVG_BYTES = 15008;                                   // 3750 floats, padded to 16
 constexpr int SMEM_BIN = SAVG_BYTES + 4 * CELLS;                    // 215,712 B
 
+// COMPACT (bevgen_process_host_compact): the outputs leave in the form that crosses PCIe cheapest and the host expands
+//   ground_bits  [F][ceil(S/32)] u32  bit = the slot is ground after loop 3 (its label becomes 0, :244-245) instead of label_out
+//   multi_planes [F][3][224*224] u8   the three occupancy bit planes as they sit in shared memory (bit l&7 of plane l>>3 =
+//                                     layer l occupied) instead of the 24 expanded 0/255 layers
+template <bool COMPACT>
 __global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const float4* __restrict__ rec,
-                                                           const uint16_t* __restrict__ gkey, const float* __restrict__ avg,
+                                                           const uint32_t* __restrict__ gmask, const float* __restrict__ avg,
                                                            int16_t* __restrict__ label_out, uint8_t* __restrict__ single,
                                                            uint8_t* __restrict__ multi) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -1070,48 +1173,61 @@ __global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const fl
   __syncthreads();
 
   const float4* R = rec + fb;
-  const uint16_t* K = gkey + fb;
-  const int first = sp.band_row0 * sp.H;
+  const int H = sp.H, NG = (H + 31) >> 5;
+  const uint32_t* GM = gmask + (size_t)f * (sp.G + 1) * NG;
+  const int first = sp.band_row0 * H;
+  const int W = (sp.S + 31) >> 5;
+  uint32_t* gbits = reinterpret_cast<uint32_t*>(label_out) + (size_t)f * W;   // COMPACT only
   // Register double buffer: the loads of batch k+1 are in flight while batch k goes through the shared-memory atomics
   // (ncu: the loop was load-batch -> wait -> process, the memory pipe idled during every process phase).
   constexpr int UB = 2;   // measured: 0.87 / 0.81 / 0.86 / 0.92 us per frame for 1 / 2 / 3 / 4 records per thread and batch
-  float4 nv[UB]; unsigned nk[UB];
+  float4 nv[UB]; bool ng[UB];
+  // (row, col) of the slot this thread fetches next, advanced by 1024 slots per record (no division in the loop)
+  int fr = tid / H, fc = tid - fr * H;
+  const int dr = 1024 / H, dc = 1024 - dr * H;
   auto fetch = [&](int s0) {
 #pragma unroll
     for (int u = 0; u < UB; u++) {
       const int sl = s0 + u * 1024;
       nv[u] = sl < sp.S ? __ldcs(R + sl) : make_float4(0.f, 0.f, 0.f, 0.f);       // read once: streaming (evict-first) loads
-      nk[u] = (sl < sp.S && sl >= first) ? (unsigned)__ldcs(K + sl) : NO_KEY;
+      // ground_mat == 1 after loop 1: one bit per slot of the band rows (k_ground_mark)
+      ng[u] = (sl < sp.S && sl >= first) ? ((__ldg(GM + (fr - sp.band_row0) * NG + (fc >> 5)) >> (fc & 31)) & 1u) != 0u : false;
+      fr += dr; fc += dc; if (fc >= H) { fc -= H; fr++; }
     }
   };
   fetch(tid);
-  for (int slot0 = tid; slot0 < sp.S; slot0 += 1024 * UB) {
-   float4 pv[UB]; unsigned kv[UB];
+  for (int slot0 = tid; slot0 - (tid & 31) < sp.S; slot0 += 1024 * UB) {   // warp-uniform trip count (the ballot below)
+   float4 pv[UB]; bool gv[UB];
 #pragma unroll
-   for (int u = 0; u < UB; u++) { pv[u] = nv[u]; kv[u] = nk[u]; }
+   for (int u = 0; u < UB; u++) { pv[u] = nv[u]; gv[u] = ng[u]; }
    if (slot0 + 1024 * UB < sp.S) fetch(slot0 + 1024 * UB);
 #pragma unroll
    for (int u = 0; u < UB; u++) {
     const int slot = slot0 + u * 1024;
-    if (slot >= sp.S) break;
+    if (slot - (tid & 31) >= sp.S) break;        // whole warp past the end (warp-uniform: the ballot below needs all lanes)
+    const bool in = slot < sp.S;
     const float4 p = pv[u];
     int16_t lab = (int16_t)(__float_as_uint(p.w) & 0xFFFFu);
-    {
-      const unsigned key = kv[u];
-      if (key != NO_KEY) {                       // ground_mat == 1 after loop 1
-        const int sr = key / SECT_C, sc = key - sr * SECT_C;
-        bool cleared = false;
-        // neighbour order (-1,0),(0,1),(0,-1),(1,0) (:73-84); (double)(z - avg) > 0.30  <=>  (z - avg) >= 0.3f
-        // because 0.3f is the smallest float above the double 0.30 (:236-237)
-        if (sr - 1 >= 0)      cleared = __fsub_rn(p.z, savg[key - SECT_C]) >= 0.3f;
-        if (!cleared && sc + 1 < SECT_C) cleared = __fsub_rn(p.z, savg[key + 1]) >= 0.3f;
-        if (!cleared && sc - 1 >= 0)     cleared = __fsub_rn(p.z, savg[key - 1]) >= 0.3f;
-        if (!cleared && sr + 1 < SECT_R) cleared = __fsub_rn(p.z, savg[key + SECT_C]) >= 0.3f;
-        if (!cleared) lab = 0;                   // :244-245
-      }
+    bool ground = false;
+    if (in && gv[u]) {                           // ground_mat == 1 after loop 1
+      const int key = (int)sector_of(p.x, p.y);
+      const int sr = key / SECT_C, sc = key - sr * SECT_C;
+      bool cleared = false;
+      // neighbour order (-1,0),(0,1),(0,-1),(1,0) (:73-84); (double)(z - avg) > 0.30  <=>  (z - avg) >= 0.3f
+      // because 0.3f is the smallest float above the double 0.30 (:236-237)
+      if (sr - 1 >= 0)      cleared = __fsub_rn(p.z, savg[key - SECT_C]) >= 0.3f;
+      if (!cleared && sc + 1 < SECT_C) cleared = __fsub_rn(p.z, savg[key + 1]) >= 0.3f;
+      if (!cleared && sc - 1 >= 0)     cleared = __fsub_rn(p.z, savg[key - 1]) >= 0.3f;
+      if (!cleared && sr + 1 < SECT_R) cleared = __fsub_rn(p.z, savg[key + SECT_C]) >= 0.3f;
+      if (!cleared) { lab = 0; ground = true; }  // :244-245
     }
-    __stcs(label_out + fb + slot, lab);     // outputs are never re-read on the device: streaming stores
-    if (lab == 0) continue;                      // :285 / :349
+    if (COMPACT) {
+      const unsigned gb = __ballot_sync(0xffffffffu, ground);   // lanes = 32 consecutive slots (slot & 31 == lane)
+      if ((tid & 31) == 0) __stcs(gbits + (slot >> 5), gb);
+    } else if (in) {
+      __stcs(label_out + fb + slot, lab);     // outputs are never re-read on the device: streaming stores
+    }
+    if (!in || lab == 0) continue;               // :285 / :349
     const float vx = __fadd_rn(p.x, 112.0f), vy = __fadd_rn(p.y, 112.0f);   // (pi.x + MAX_RANGE) / 1.0f
     // x = round(v + 0.5) in double, valid 0..223  <=>  -1 < v < 223 and then x = floor(v) + 1   (:279-284)
     if (!(vx > -1.0f && vx < 223.0f && vy > -1.0f && vy < 223.0f)) continue;
@@ -1146,6 +1262,11 @@ __global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const fl
 
   uint4* so = reinterpret_cast<uint4*>(single + (size_t)f * CELLS);
   for (int i = tid; i < CELL_WORDS / 4; i += 1024) __stcs(so + i, reinterpret_cast<const uint4*>(hgt)[i]);
+  if (COMPACT) {   // the three bit planes as they are: 150 528 bytes instead of 1 204 224
+    uint4* mo = reinterpret_cast<uint4*>(multi + (size_t)f * 3 * CELLS);
+    for (int i = tid; i < 3 * CELL_WORDS / 4; i += 1024) __stcs(mo + i, reinterpret_cast<const uint4*>(occ)[i]);
+    return;
+  }
   uint4* mo = reinterpret_cast<uint4*>(multi + (size_t)f * LAYERS * CELLS);
   constexpr int Q = CELL_WORDS / 4;   // uint4 per layer = 3136
   for (int i = tid; i < LAYERS * Q; i += 1024) {
@@ -1252,7 +1373,7 @@ __global__ void __launch_bounds__(128) k_labels(int K, const float* __restrict__
 // cloud_manip (BASELINE config #5): rigid transform (CloudManip.cpp:128) + saveAsMat max grid (:79-95) of the input
 // and of the transformed cloud.  Cells start at 0 and only strictly larger values are stored, so stored values are
 // positive floats and an int atomicMax on the bit pattern is an exact, order-free float max.  Lanes that hit the
-// same cell are folded first (match_any + shuffle max) so hot cells cost one atomic per warp.
+// same cell are folded first (match_any + redux max) so hot cells cost at most one atomic per warp.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int MGRID = 201;
 
@@ -1263,15 +1384,9 @@ __device__ __forceinline__ void manip_scatter(float px, float py, float pz, bool
   const int lane = threadIdx.x & 31;
   const int cell = in ? (__float2int_rd(vx) + 1) * MGRID + (__float2int_rd(vy) + 1) : -1 - lane;
   const unsigned peers = __match_any_sync(0xffffffffu, cell);
-  int m = __float_as_int(v);
-  // fold the group's max into its lowest lane: positive floats order like their int patterns
-  int best = m;
-  unsigned p = peers & ~(1u << lane);
-  while (__any_sync(0xffffffffu, p != 0)) {
-    const int j = p ? __ffs(p) - 1 : lane;
-    const int o = __shfl_sync(0xffffffffu, m, j);
-    if (p) { best = max(best, o); p &= p - 1; }
-  }
+  // the group's max in one REDUX: positive floats order like their int patterns (a warp whose 32 lanes all hit one cell
+  // costs the same as a warp that hits 32 cells; the round-1 form looped once per peer)
+  const int best = __reduce_max_sync(peers, __float_as_int(v));
   if (in && lane == __ffs(peers) - 1) {
     if (*reinterpret_cast<volatile int*>(&grid[cell]) < best) atomicMax(&grid[cell], best);
   }

@@ -45,6 +45,8 @@ int main(int argc, char** argv) {
   const size_t n = in.size();
   pcdio::Cloud out = in;
   std::vector<float> gi(BEVGEN_MANIP_GRID * BEVGEN_MANIP_GRID), go(gi.size());
+  // an empty / unreadable cloud (the reference ignores loadPCDFile's status, :117) still yields the two zero grids and
+  // the empty csv / png / pcd files: the library accepts NULL point arrays when n == 0
   if (bevgen_cloud_manip(ctx, (int64_t)n, rt, in.x.data(), in.y.data(), in.z.data(), out.x.data(), out.y.data(), out.z.data(), gi.data(), go.data()) != 0) {
     std::cerr << "bevgen_cloud_manip: " << bevgen_last_error() << std::endl; return 1;
   }

@@ -64,9 +64,9 @@ inline bool write_png_gray8(const std::string& path, const uint8_t* pix, int w, 
 }
 
 inline std::string format_csv_u8(const uint8_t* m, int rows, int cols) {
-  static char lut[256][4];
-  static bool init = false;
-  if (!init) { for (int i = 0; i < 256; i++) snprintf(lut[i], 4, "%3d", i); init = true; }
+  struct Lut { char t[256][4]; Lut() { for (int i = 0; i < 256; i++) snprintf(t[i], 4, "%3d", i); } };
+  static const Lut L;                     // magic static: initialised once, thread-safe (called from the encode pool)
+  const char (*lut)[4] = L.t;
   std::string s;
   s.reserve((size_t)rows * cols * 5 + 2);
   for (int r = 0; r < rows; r++) {

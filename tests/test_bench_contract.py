@@ -1,4 +1,4 @@
-"""bench.py contract checks that need no GPU: the reference arm (the CPU oracle port timed on the host cores) prints
+"""bench.py contract checks that need no GPU: the reference arm (the reference source of oracle/_ref, or the CPU oracle port, timed on the host cores) prints
 exactly one JSON line with the agreed keys, and the product arm refuses to run without a CUDA device."""
 import json
 import os
@@ -20,7 +20,11 @@ def test_reference_arm_prints_one_json_line():
     assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1 and d["ms_per_step"] > 0 and d["gpu_launches"] == 0
     assert d["config"]["workload"] and d["config"]["frames_per_step"] == 4
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert cb["port_frames_per_s"] > 0
+    if cb["kind"] == "reference":      # oracle/_ref present: the line's value is the reference's own source, one process per core
+        rs = cb["reference_source"]
+        assert rs["procs"] == cb["cores"] and rs["frames"] > 0 and abs(rs["frames_per_s"] - d["value"]) < 1e-9
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

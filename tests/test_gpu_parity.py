@@ -398,3 +398,144 @@ def test_top_flatten_segmented_selection(gens, synth, O):
         assert np.array_equal(gi, wi), int((gi != wi).sum())
         assert np.array_equal(gx.view(np.uint32), wx.view(np.uint32)) and np.array_equal(gy.view(np.uint32), wy.view(np.uint32))
     assert len(O.top_flatten(*cases[0])[2]) > 1000 and len(O.top_flatten(*cases[1])[2]) > 10000
+
+
+# ---- round 2: compact staging format, libm overload switch, diagnostics, leak / ring fixes -------------------------
+def _compact(pkg, g, batch):
+    return dict(x=batch["x"], y=batch["y"], z=batch["z"], offsets=batch["offsets"],
+                meta=pkg.pack_meta(g.params, batch["row"], batch["col"], batch["intensity"], batch["label"]))
+
+
+@pytest.mark.parametrize("sensor", ["HDL_32E", "OS1_64", "HDL_64E"])
+def test_compact_host_path_bit_exact_after_expand(gens, pkg, synth, O, sensor):
+    """bevgen_process_host_compact: 16 B/point in, ground bits + bit planes out; after the host-side expansion (a change of
+    representation only) every output equals the oracle's - synthetic frames (chunked: 7 > 3) and the random frames."""
+    sp = O.sensor(sensor)
+    g = gens(sensor, max_frames_per_batch=3, max_points_per_frame=sp.S * 2)
+    for batch in (synth.make_batch(sensor, 7, first=400), cat_frames(cases.random_unstructured_frames(sp) + [cases.hot_cell_frame(sp)])):
+        cout = g.process_host_compact(_compact(pkg, g, batch))
+        assert cout["planes"].shape[1:] == (3, 224, 224) and cout["ground"].shape[1] == (sp.S + 31) // 32
+        assert_same(g.compact_to_reference_layout(cout, batch), oracle_batch(O, sensor, batch), "compact " + sensor)
+    # pinned buffers (the fully asynchronous route) give the same bytes
+    batch = synth.make_batch(sensor, 4, first=410)
+    cb = _compact(pkg, g, batch)
+    pin = {k: pkg.pinned_empty(np.asarray(cb[k]).shape, np.asarray(cb[k]).dtype) for k in ("x", "y", "z", "meta")}
+    for k in pin:
+        pin[k][...] = cb[k]
+    pin["offsets"] = cb["offsets"]
+    out = g.alloc_outputs_compact(4, pinned=True, n_total=int(batch["offsets"][-1]))
+    g.process_host_compact(pin, out=out)
+    assert_same(g.compact_to_reference_layout(out, batch), oracle_batch(O, sensor, batch), "compact pinned " + sensor)
+    for a in list(pin.values())[:4] + list(out.values()):
+        pkg.pinned_free(a)
+
+
+def test_libm_double_switch_and_diag(pkg, O):
+    """bevgen_set_libm(1): the C double atan2 / sqrt overload set (the reference built without <math.h> in its include
+    tree); bevgen_set_diag counts the borderline pairs and the pairs on which the two overload sets disagree."""
+    sensor = "HDL_32E"
+    sp = O.sensor(sensor)
+    batch = cat_frames(cases.borderline_frames(sp))
+    ref_f = oracle_batch(O, sensor, batch); ref_d = oracle_batch(O, sensor, batch, double_libm=True)
+    assert (ref_f["label"] != ref_d["label"]).any()
+    g = pkg.BevGen(sensor, device=0, max_frames_per_batch=2, max_points_per_frame=sp.S * 2)
+    try:
+        g.set_diag(True)
+        assert_same(g.process_host(batch), ref_f, "float libm + diag")
+        d = g.get_diag()
+        assert d["borderline_pairs"] > 1000 and d["float_double_disagree"] > 0, d
+        g.set_libm(True)
+        assert_same(g.process_host(batch), ref_d, "double libm")
+        g.set_diag(False)
+        assert_same(g.process_host(batch), ref_d, "double libm, diag off")
+        assert g.get_diag() == dict(borderline_pairs=0, float_double_disagree=0)
+        g.set_libm(False)
+        assert_same(g.process_host(batch), ref_f, "back to float")
+    finally:
+        g.close()
+
+
+def test_packed_records_stride_256(gens, synth, O, pkg):
+    """records of 192..256 bytes need more than 48 KB of dynamic shared memory in k_unpack_records."""
+    sensor = "HDL_32E"
+    batch = synth.make_batch(sensor, 3, first=310)
+    g = gens(sensor, max_frames_per_batch=3)
+    rng = np.random.default_rng(6)
+    for lay in (pkg.RecordLayout(256, 100, 8, 248, 200, 2, 252, 0), pkg.RecordLayout(193, 1, 5, 9, 13, 17, 19, 21)):
+        out = g.process_packed_host(_pack_records(batch, lay, rng), batch["offsets"], lay)
+        out["owner"] = pkg.owner_from_winner(out["winner"], batch["offsets"], np.asarray(batch["row"], np.uint16), np.asarray(batch["col"], np.uint16),
+                                             g.params.horizon_scan, g.S)
+        assert_same(out, oracle_batch(O, sensor, batch), "stride %d" % lay.stride)
+
+
+def test_create_failure_releases_everything(pkg):
+    """a bevgen_create that fails part-way (device memory exhausted) must free what it had allocated."""
+    import torch
+    torch.cuda.init()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    for _ in range(40):
+        with pytest.raises(pkg.BevgenError):
+            pkg.BevGen("HDL_64E", device=0, max_frames_per_batch=65535, max_points_per_frame=4_000_000)
+    free1 = torch.cuda.mem_get_info(0)[0]
+    assert free0 - free1 < 64 << 20, (free0, free1)
+    g = pkg.BevGen("HDL_32E", device=0, max_frames_per_batch=2)      # the device is still usable
+    g.close()
+
+
+def test_ring_holds_max_frames_per_batch(pkg, synth, O):
+    """the submit / collect ring holds max_frames_per_batch frames (it used to stop at 8)."""
+    sensor = "HDL_32E"
+    batch = synth.make_batch(sensor, 11, first=60)
+    ref = oracle_batch(O, sensor, batch)
+    offs = batch["offsets"]
+    fr = lambda f: {k: batch[k][offs[f]:offs[f + 1]] for k in FIELDS}
+    g = pkg.BevGen(sensor, device=0, max_frames_per_batch=11)
+    try:
+        for f in range(11):
+            g.submit(f, fr(f))
+        with pytest.raises(pkg.BevgenError, match="ring full"):
+            g.submit(11, fr(0))
+        for f in (10, 0, 5, 1, 2, 3, 4, 6, 7, 8, 9):
+            o = g.collect(f, fr(f))
+            assert_same({k: v[None] for k, v in o.items() if k != "winner"}, {k: v[f:f + 1] for k, v in ref.items()}, "ring %d" % f)
+    finally:
+        g.close()
+
+
+def test_cloud_manip_2m_points_device_resident(gens, O):
+    """BASELINE config #5 at its stated size: 2 M points, 60 % in a 3 m blob around the origin; the device-resident entry
+    point, the independent optional outputs and the empty cloud."""
+    import torch
+    g = gens("HDL_32E", max_frames_per_batch=4, max_points_per_frame=33792 * 2)
+    rng = np.random.default_rng(55)
+    n = 2_000_000
+    hot = rng.random(n) < 0.6
+    x = np.where(hot, rng.normal(0, 3, n), rng.uniform(-100, 100, n)).astype(np.float32)
+    y = np.where(hot, rng.normal(0, 3, n), rng.uniform(-100, 100, n)).astype(np.float32)
+    z = rng.uniform(-2, 10, n).astype(np.float32)
+    th = np.float32(np.float32(37.0) / np.float32(180.0) * np.pi)
+    c, s = np.float32(np.cos(th)), np.float32(np.sin(th))
+    rt = np.array([c, -s, 0, 3.5, s, c, 0, -1.25, 0, 0, 1, 0.2], np.float32)
+    otx, oty, otz = O.transform(rt, x, y, z)
+    want_i = O.save_as_mat(x, y, z); want_o = O.save_as_mat(otx, oty, otz)
+    dev = torch.device("cuda:0")
+    d = {k: torch.from_numpy(v).to(dev) for k, v in (("x", x), ("y", y), ("z", z))}
+    for k in ("tx", "ty", "tz"):
+        d[k] = torch.empty(n, dtype=torch.float32, device=dev)
+    d["bev_in"] = torch.full((201, 201), 7.0, dtype=torch.float32, device=dev); d["bev_out"] = torch.full((201, 201), 7.0, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    g.cloud_manip_device(n, rt, {k: v.data_ptr() for k, v in d.items()})
+    g.sync()
+    for a, b in (("tx", otx), ("ty", oty), ("tz", otz)):
+        assert np.array_equal(d[a].cpu().numpy().view(np.uint32), b.view(np.uint32)), a
+    assert np.array_equal(d["bev_in"].cpu().numpy(), want_i) and np.array_equal(d["bev_out"].cpu().numpy(), want_o)
+    # host form: each output optional on its own; an empty cloud (NULL arrays) gives zero grids
+    import ctypes as C
+    L = pkg_lib = __import__("pcpt_b200").lib()
+    bo = np.empty((201, 201), np.float32); ty = np.empty(n, np.float32)
+    rc = L.bevgen_cloud_manip(g._ctx, C.c_int64(n), rt.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
+                              z.ctypes.data_as(C.c_void_p), None, ty.ctypes.data_as(C.c_void_p), None, None, bo.ctypes.data_as(C.c_void_p))
+    assert rc == 0 and np.array_equal(ty.view(np.uint32), oty.view(np.uint32)) and np.array_equal(bo, want_o)
+    bi = np.full((201, 201), 3.0, np.float32)
+    rc = L.bevgen_cloud_manip(g._ctx, C.c_int64(0), rt.ctypes.data_as(C.c_void_p), None, None, None, None, None, None, bi.ctypes.data_as(C.c_void_p), None)
+    assert rc == 0 and not bi.any()

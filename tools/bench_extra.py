@@ -22,8 +22,144 @@ def wall(fn, reps):
     return (time.perf_counter() - t0) / reps
 
 
+def device_rate(pkg, torch, dev, sensor, distinct, F, wave, device=0, steps=5):
+    """frames resident in HBM through bevgen_process_device, CUDA events on the compute stream -> (ms per step, n_total, S)."""
+    g = pkg.BevGen(sensor, device=device, max_frames_per_batch=wave, max_points_per_frame=max(int(np.diff(distinct["offsets"]).max()), 1) + 64)
+    batch = tile_batch(distinct, F)
+    n_total = int(batch["offsets"][-1])
+    din = {k: torch.from_numpy(batch[k]).to(dev) for k in FIELDS}
+    dout = dict(label=torch.empty((F, g.S), dtype=torch.int16, device=dev), winner=torch.zeros(pkg.winner_words(n_total, F), dtype=torch.int32, device=dev),
+                single=torch.empty((F, 224 * 224), dtype=torch.uint8, device=dev), multi=torch.empty((F, 24 * 224 * 224), dtype=torch.uint8, device=dev))
+    pin, pout = {k: v.data_ptr() for k, v in din.items()}, {k: v.data_ptr() for k, v in dout.items()}
+    stream = torch.cuda.ExternalStream(g.compute_stream(), device=dev)
+    step = lambda: g.process_device(F, batch["offsets"], pin, pout)
+    for _ in range(3):
+        step()
+    g.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream); g.sync(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    g.set_profiling(True); step(); g.sync(); st = g.stage_ms(); g.set_profiling(False)
+    S = g.S
+    g.close(); del din, dout; torch.cuda.empty_cache()
+    return ms, n_total, S, {k: round(v[0] / F * 1e3, 3) for k, v in st.items() if v[1] > 0}
+
+
+def sharded():
+    """BASELINE configs[2], [3] under torchrun: a 10 000-keyframe OS1_64 / HDL_32E batch sharded by frame index over the
+    ranks (one process per GPU, no data-path collective), and the label stage at K = 10 000 with its rows split per rank
+    and gathered on the host (here: all_gather of the per-rank row digests)."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev); dist.barrier(); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    pkg, synth = load_pkg(), load_synth()
+    K = 10000
+    lo, hi = K * rank // world, K * (rank + 1) // world
+    for sensor in ("OS1_64", "HDL_32E"):
+        distinct = synth.make_batch(sensor, 32, first=1000 * rank)
+        ms, n_total, S, st = device_rate(pkg, torch, dev, sensor, distinct, hi - lo, min(hi - lo, 4096 if sensor == "OS1_64" else 8192), device=local)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({"what": "%s: 10 000 synthetic keyframes sharded over %d GPU(s), device path (32 distinct frames per rank, tiled)" % (sensor, world),
+                              "frames_per_s": K / (float(t[0]) * 1e-3), "ms_for_the_batch": float(t[0]), "n_gpus": world, "stage_us_per_frame_rank0": st}), flush=True)
+    # label stage: greedy major-frame scan once per rank (serial chain), rows [lo, hi) of the K x M table per rank
+    xyz = synth.make_poses(K, seed=11, step=2.0)
+    g = pkg.BevGen("OS1_64", device=local, max_frames_per_batch=2)
+    t0 = time.perf_counter(); mi, _ = g.select_major(xyz); t_sel = time.perf_counter() - t0
+    t0 = time.perf_counter(); lab, _, _ = g.labels(xyz, mi, lo, hi); t_lab = time.perf_counter() - t0
+    g.close()
+    h = hashlib.sha256(np.ascontiguousarray(lab).tobytes()).digest()
+    parts = [None] * world
+    if world > 1:
+        dist.all_gather_object(parts, (lo, hi, lab if K * len(mi) < 8_000_000 else None, h))
+    else:
+        parts = [(lo, hi, lab, h)]
+    if rank == 0:
+        meta = json.load(open(os.path.join(ROOT, "tests", "golden", "bev_golden.json")))["labels"]["K10000_s11"]
+        full = np.concatenate([p[2] for p in parts]) if all(p[2] is not None for p in parts) else None
+        ok = None
+        if full is not None:
+            sys.path.insert(0, os.path.join(ROOT, "tests")); import cases
+            ok = cases.digest(full) == meta["labels"] and len(mi) == meta["M"]
+        print(json.dumps({"what": "label stage K = 10 000, M = %d, rows split over %d rank(s)" % (len(mi), world), "select_major_s": t_sel, "labels_rows_s_rank0": t_lab,
+                          "equals_reference_generated_golden": ok}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def contention(pkg, torch, dev, synth, peak):
+    """does a heavily contended cell need a sort-by-cell fallback?  (a) every point of a full HDL_64E frame in
+    ONE BEV cell vs the synthetic frames, device path; (b) cloud_manip on 2 M device-resident points: uniform, the
+    config #5 blob (60 % of the points within ~3 m), and all points in one cell."""
+    sys.path.insert(0, os.path.join(ROOT, "tests")); import cases
+    sensor = "HDL_64E"
+    sp = pkg.sensor_params(sensor)
+    class SP: n_scan, horizon_scan, S = sp.n_scan, sp.horizon_scan, sp.S
+    hot = cat = None
+    frames = [cases.hot_cell_frame(SP, seed=s) for s in range(8)]
+    offs = np.zeros(9, np.int64); offs[1:] = np.cumsum([len(f["x"]) for f in frames])
+    hot = {k: np.concatenate([f[k] for f in frames]) for k in FIELDS}; hot["offsets"] = offs
+    uni = synth.make_batch(sensor, 8)
+    res = {}
+    for name, d in (("synthetic", uni), ("one_cell", hot)):
+        ms, n_total, S, st = device_rate(pkg, torch, dev, sensor, d, 2220, 2220)
+        res[name] = {"us_per_frame": ms * 1e3 / 2220, "pts_per_frame": n_total / 2220, "stage_us_per_frame": st}
+    res["finalize_ratio_one_cell_vs_synthetic"] = res["one_cell"]["stage_us_per_frame"]["finalize_bin_scatter"] / res["synthetic"]["stage_us_per_frame"]["finalize_bin_scatter"]
+    print(json.dumps({"what": "contention: all %d points of a frame in one BEV cell vs synthetic frames (device path, HDL_64E)" % SP.S, **res}), flush=True)
+    g = pkg.BevGen("HDL_32E", device=0, max_frames_per_batch=2)
+    rng = np.random.default_rng(3)
+    n = 2_000_000
+    th = np.float32(np.deg2rad(37.0)); c, s = np.float32(np.cos(th)), np.float32(np.sin(th))
+    rt = np.array([c, -s, 0, 3.5, s, c, 0, -1.25, 0, 0, 1, 0.2], np.float32)
+    blob = rng.random(n) < 0.6
+    clouds = {"uniform": (rng.uniform(-100, 100, n), rng.uniform(-100, 100, n)),
+              "config5_blob": (np.where(blob, rng.normal(0, 3, n), rng.uniform(-100, 100, n)), np.where(blob, rng.normal(0, 3, n), rng.uniform(-100, 100, n))),
+              "one_cell": (rng.uniform(10.1, 10.9, n), rng.uniform(-7.9, -7.1, n))}
+    stream = torch.cuda.ExternalStream(g.compute_stream(), device=dev)
+    out = {}
+    for name, (cx, cy) in clouds.items():
+        d = {"x": torch.from_numpy(cx.astype(np.float32)).to(dev), "y": torch.from_numpy(cy.astype(np.float32)).to(dev),
+             "z": torch.from_numpy(rng.uniform(-2, 10, n).astype(np.float32)).to(dev)}
+        for k in ("tx", "ty", "tz"):
+            d[k] = torch.empty(n, dtype=torch.float32, device=dev)
+        d["bev_in"] = torch.empty((201, 201), dtype=torch.float32, device=dev); d["bev_out"] = torch.empty((201, 201), dtype=torch.float32, device=dev)
+        ptr = {k: v.data_ptr() for k, v in d.items()}
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ts = []
+        for it in range(8):
+            flush.zero_()                               # 24 MB of points fit the L2: flush it between iterations
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); g.cloud_manip_device(n, rt, ptr); e1.record(stream); g.sync(); torch.cuda.synchronize()
+            if it >= 3:
+                ts.append(e0.elapsed_time(e1))
+        ms = float(np.median(ts))
+        out[name] = {"us_per_call": ms * 1e3, "calls_per_s": 1e3 / ms, "algorithmic_GBps": 48323208 / (ms * 1e-3) / 1e9, "frac_of_measured_hbm_peak": 48323208 / (ms * 1e-3) / 1e9 / peak}
+        del d, flush
+    out["ratio_one_cell_vs_uniform"] = out["one_cell"]["us_per_call"] / out["uniform"]["us_per_call"]
+    out["ratio_blob_vs_uniform"] = out["config5_blob"]["us_per_call"] / out["uniform"]["us_per_call"]
+    print(json.dumps({"what": "cloud_manip (config #5), 2 M points resident in HBM, L2 flushed between calls, 48 323 208 algorithmic bytes per call (incl. the two memsets + kernel)", **out}), flush=True)
+    g.close()
+
+
 def main():
     import torch
+    if "--sharded" in sys.argv:
+        return sharded()
     pkg, synth = load_pkg(), load_synth()
     dev = torch.device("cuda", 0)
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -52,6 +188,7 @@ def main():
         print(json.dumps({"what": "device path, %s" % sensor, "frames_per_s": F / (ms * 1e-3), "us_per_frame": ms * 1e3 / F, "frames_per_step": F,
                           "pts_per_frame": n_total / F, "algorithmic_GBps": alg / (ms * 1e-3) / 1e9, "frac_of_measured_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak}), flush=True)
         g.close(); del din, dout; torch.cuda.empty_cache()
+    contention(pkg, torch, dev, synth, peak)
     # ---- 8(f)-1 / 8(f)-3: host-buffer paths through the C-ABI (PCIe inside the timed region), HDL_64E ------------------
     sensor, Fe = "HDL_64E", 256
     distinct = synth.make_batch(sensor, 32)

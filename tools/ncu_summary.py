@@ -18,7 +18,7 @@ with open(sys.argv[2], "w", newline="") as f:
         w.writerow([r[i] for i in idx])
 print(open(sys.argv[2]).read())
 
-# optional 3rd/4th argument: frames per launch of the captured command and the JSON bench.py reads for roofline.traffic
+# optional 3rd/4th (5th: commit the capture was taken at) argument: frames per launch of the captured command and the JSON bench.py reads for roofline.traffic
 # (dram__bytes_read.sum + dram__bytes_write.sum of each kernel, per frame, averaged over its captured launches)
 if len(sys.argv) >= 5:
     import json, re
@@ -40,6 +40,7 @@ if len(sys.argv) >= 5:
     per_stage = {}
     for k, b in acc.items():   # kernels of one stage add up (one launch of each per wave)
         per_stage[stage[k]] = per_stage.get(stage[k], 0.0) + b / cnt[k] / frames
-    json.dump({"source": "ncu --set full, %s, %d frames per launch" % (sys.argv[1], frames),
-               "dram_bytes_per_frame": per_stage}, open(out, "w"), indent=1)
+    commit = sys.argv[5] if len(sys.argv) >= 6 else subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    json.dump({"source": "ncu --set full, %s, %d frames per launch" % (sys.argv[1], frames), "commit": commit,
+               "dram_bytes_per_frame": per_stage, "total_dram_bytes_per_frame": sum(per_stage.values())}, open(out, "w"), indent=1)
     print(open(out).read())
