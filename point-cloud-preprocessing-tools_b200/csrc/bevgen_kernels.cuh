@@ -8,7 +8,7 @@
 // HBM layout per frame f of a batch (S = N_SCAN * Horizon_SCAN slots):
 //   owner [f][S]  u32   1 + winning input index per slot (0 = empty)        — output
 //   rec   [f][S]  f32x4 ordered cloud: x, y, z, w = {label:16 | I==-1:1 | owned:1} — scratch, written once
-//   gmask [f][G+1][ceil(H/32)] u32  ground_mat == 1 after loop 1, one bit per slot of the band rows  — scratch
+//   gmask [f][ceil(S/32)] u32  ground_mat == 1 after loop 1, bit (s & 31) of word (s >> 5) for slot s  — scratch
 //   gz    [f][S]  f32   z of those slots (0 elsewhere)                       — scratch
 //   cnt   [f][3750] u32 zero-height ground slots per sector (the others are counted by the fold);  avg [f][3750] f32 sector mean heights — scratch
 //   label [f][S] i16, single [f][224*224] u8, multi [f][24][224*224] u8      — outputs
@@ -636,6 +636,10 @@ __device__ __forceinline__ bool ground_decision(const SensorDev& sp, const float
   // Pre-filter on squares (no sqrt, no division): tan^2 thresholds carry a 2e-5 relative guard band, the three
   // roundings involved are ~2e-7, and glibc's atan2f is accurate to < 1 ulp, so outside the band the sign of
   // |atan2f(dz, sqrtf(hh))| - t_star is decided.  Only taken when nothing can overflow / underflow.
+  // Two vertically adjacent empty slots (all-zero records, :98) are the common degenerate pair - one in a hundred pairs,
+  // i.e. a quarter of all warps hold one: sqrtf(0) = 0 and atan2f(dz, +0) is +-0 for dz = +-0 (ground, :173 atan2(0,0) = 0)
+  // and +-pi/2 for any other dz, NaN excluded by the comparison.  (hh is exactly 0 only if both products are +-0.)
+  if (hh == 0.0f) return dz == 0.0f;
   const bool in_range = hh > 1e-30f && hh < 1e30f && zz < 1e30f;
   if (in_range) {
     if (zz <= __fmul_rn(sp.q_lo2, hh)) return true;
@@ -660,7 +664,7 @@ __device__ __forceinline__ bool ground_decision(const SensorDev& sp, const float
 constexpr int GM_T = 64;   // columns per CTA: H = 2083 columns fill 33 CTAs of 64 to 98.6 % (17 of 128: 95.7 %)
 template <bool DBL>
 __global__ void __launch_bounds__(GM_T) k_ground_mark(SensorDev sp, const float4* __restrict__ rec,
-                                                      uint32_t* __restrict__ gmask, float* __restrict__ gz,
+                                                      uint32_t* __restrict__ gmrow, float* __restrict__ gz,
                                                       uint32_t* __restrict__ cnt, uint4* __restrict__ gsum) {
   const int f = blockIdx.y;
   const int c0 = blockIdx.x * GM_T + threadIdx.x;
@@ -681,7 +685,7 @@ __global__ void __launch_bounds__(GM_T) k_ground_mark(SensorDev sp, const float4
   const int NG = (H + 31) >> 5;
   const size_t g0 = ((size_t)f * (sp.G + 1) + sp.G) * NG + (c0 >> 5);     // row N-1 first, walked upwards by -NG
   uint4* gs = gsum + g0;
-  uint32_t* gm = gmask + g0;
+  uint32_t* gm = gmrow + g0;                                              // ground_mat == 1 bits of the group (k_seg_build re-packs them slot-linear)
   const unsigned lt = (1u << lane) - 1u;
 
   auto emit = [&](const float4& p, bool gm1) {
@@ -827,7 +831,7 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const float4* 
 // ------------------------------------------------------------------------------------------------------------
 constexpr int SEG_CAP = 4096;
 constexpr int SEGT = 512;
-constexpr int SMEM_SEG = SEG_CAP * 4 * 2 + NSECT * 4 + SEGT * 8 + 320 + SEG_CAP * 2 * 3 + (NSECT + 2) * 2;   // 84,264 B
+constexpr int SMEM_SEG = SEG_CAP * 4 * 2 + NSECT * 4 + SEGT * 8 + 320 + SEG_CAP * 2 * 3 + (NSECT + 2) * 2 + 8 + SEG_CAP * 2;   // 92,464 B (two CTAs per SM)
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #ifndef FOLD_STEP_N
 #define FOLD_STEP_N 32   // 16 is 10 % slower
@@ -839,7 +843,9 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
                                                      const float4* __restrict__ rec, float* __restrict__ avg,
                                                      uint32_t* __restrict__ slow_flag, uint32_t* __restrict__ seg_start,
                                                      uint16_t* __restrict__ seg_len, uint32_t* __restrict__ kdesc,
-                                                     uint16_t* __restrict__ act, uint32_t* __restrict__ n_act_out) {
+                                                     uint16_t* __restrict__ act, uint32_t* __restrict__ n_act_out,
+                                                     const uint32_t* __restrict__ gmrow, uint32_t* __restrict__ gmask,
+                                                     uint32_t* __restrict__ cnt) {
   extern __shared__ __align__(16) unsigned char seg_smem[];
   uint32_t* s_start = reinterpret_cast<uint32_t*>(seg_smem);   // [SEG_CAP] first slot of the segment
   uint32_t* s_endtmp = s_start + SEG_CAP;                       // [SEG_CAP] last participating slot of the segment
@@ -853,6 +859,8 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
   uint16_t* s_key = s_len + SEG_CAP;                            // [SEG_CAP] sector of the segment
   uint16_t* s_order = s_key + SEG_CAP;                          // [SEG_CAP] segment ids bucketed by sector, slot order kept
   uint16_t* s_kbase = s_order + SEG_CAP;                        // [NSECT + 2] bucket base, later bucket end
+  // [SEG_CAP / 2] participating slots (ground, z != 0) of every segment, two 16-bit counts per word (smem atomics are 32-bit)
+  uint32_t* s_np = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(s_kbase + NSECT + 2 + 3) & ~(uintptr_t)7);
 
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int H = sp.H, NG = (H + 31) >> 5;
@@ -879,7 +887,33 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
   };
 
   for (int i = tid; i < NSECT; i += SEGT) s_kcnt[i] = 0;
+  for (int i = tid; i < SEG_CAP / 2; i += SEGT) s_np[i] = 0u;
   if (tid == 0) s_misc[0] = 0;
+  // ---- the ground_mat == 1 bits, re-packed from k_ground_mark's (row, 32-column group) words into one bit per slot in
+  // slot order (bit s & 31 of word s >> 5): k_finalize_bin walks the frame 32 consecutive slots per warp and then needs a
+  // single broadcast word.  Rows are H columns wide and H is not a multiple of 32, so a word is pieced together from up to
+  // four source words.  Independent of everything below; its loads overlap the summary loads of pass 1.
+  {
+    const int W = (sp.S + 31) >> 5;
+    const uint32_t* GR = gmrow + (size_t)f * n_groups;
+    uint32_t* GB = gmask + (size_t)f * W;
+    for (int w = tid; w < W; w += SEGT) {
+      uint32_t out = 0u;
+      int b = 0, slot = w * 32;
+      int r = slot / H, c = slot - r * H;
+      while (b < 32 && slot < sp.S) {
+        const int n = min(32 - b, min(32 - (c & 31), H - c));       // bits this source word supplies
+        const int rb = r - sp.band_row0;
+        if (rb >= 0) {
+          const uint32_t src = GR[rb * NG + (c >> 5)] >> (c & 31);
+          out |= (n == 32 ? src : (src & ((1u << n) - 1u))) << b;
+        }
+        b += n; slot += n; c += n;
+        if (c >= H) { c = 0; r++; }
+      }
+      GB[w] = out;
+    }
+  }
   // ---- pass 1: last participating slot / sector of this thread's groups ----
   // the thread's group summaries: the first 8 live in registers (one round trip), further ones are re-read
   uint4 gv[8];
@@ -930,14 +964,19 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
       unsigned hm = v.y;
       if ((v.z & 0xFFFFu) != k) hm |= pm & (0u - pm);             // the first participating lane opens a segment
       const int base = slot_of(g, 0);
+      unsigned rest = pm;                                           // participating lanes not yet credited to a segment
+      auto credit = [&](unsigned seg, unsigned lanes) { if (lanes) atomicAdd(&s_np[seg >> 1], (unsigned)__popc(lanes) << ((seg & 1u) * 16u)); };
       while (hm) {
         const int l = __ffs(hm) - 1; hm &= hm - 1;
         const unsigned below = pm & ((1u << l) - 1u);
         const int prev_end = below ? base + 31 - __clz(below) : lastp;
+        credit(e - 1u, rest & ((1u << l) - 1u));                    // lanes below a head belong to the segment before it
+        rest &= ~((1u << l) - 1u);
         s_start[e] = (uint32_t)(base + l);
         if (e > 0) s_endtmp[e - 1] = (uint32_t)prev_end;
         e++;
       }
+      credit(e - 1u, rest);
       k = v.z >> 16; lastp = base + 31 - __clz(pm);
     }
   }
@@ -951,7 +990,7 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
     const unsigned st = s_start[e], d = s_endtmp[e] - st;
     const float4 p0 = R[st];                                      // a segment starts on a participating slot: its sector
     const unsigned k = sector_of(p0.x, p0.y);                     // is the segment's (independent loads, all in flight)
-    if (d > 0xFFFFu) s_misc[0] = 1u;                              // a segment longer than 65535 slots: sweep kernel
+    if (d >= 0xFFFFu) s_misc[0] = 1u;                             // a segment of 65535 slots or more: sweep kernel (16-bit length and count)
     s_len[e] = (uint16_t)d; s_key[e] = (uint16_t)k;
     atomicAdd(&s_kcnt[k], 1u);
   }
@@ -999,14 +1038,20 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
   __syncthreads();
   // ---- the bucketed list goes to global memory: entry `pos` of the frame = (first slot, length - 1) ----
   uint32_t* s_span = s_endtmp;                                    // [NSECT] slots a sector's chain walks over (its cost)
-  for (int k = tid; k < NSECT; k += SEGT) s_span[k] = 0u;
+  uint32_t* s_knp = s_kcnt;                                       // [NSECT] participating slots of the sector (s_kcnt is dead: kdesc holds the counts)
+  for (int k = tid; k < NSECT; k += SEGT) { s_span[k] = 0u; s_knp[k] = 0u; }
   __syncthreads();
   for (int e = tid; e < nseg; e += SEGT) {
     const unsigned pos = s_order[e];
     seg_start[(size_t)f * SEG_CAP + pos] = s_start[e];
     seg_len[(size_t)f * SEG_CAP + pos] = s_len[e];
     atomicAdd(&s_span[s_key[e]], (unsigned)s_len[e] + 1u);
+    atomicAdd(&s_knp[s_key[e]], (s_np[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
   }
+  __syncthreads();
+  // loop 2's count (:205) is order-free: ground slots of height 0 were counted by k_ground_mark, the participating ones
+  // (exactly the non-zero heights the fold adds up) are known from the summaries - the fold itself counts nothing
+  for (int k = tid; k < NSECT; k += SEGT) { const unsigned c = s_knp[k]; if (c) cnt[(size_t)f * NSECT + k] += c; }
   __syncthreads();
   // ---- active sectors sorted by chain cost, longest first: k_seg_fold gives 32 consecutive entries to one warp, and a
   // warp runs as long as its longest chain ----
@@ -1041,13 +1086,23 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
 constexpr int FOLD_DIST = FOLD_DIST_N;
 constexpr int FOLD_MAX_WPB = 4;
 
+// 8 consecutive floats as one 256-bit load (sm_100: LDG.E.256; the address must be 32-byte aligned).  The fold is bound by
+// L1 wavefronts - every lane reads its own line - so the wider the load, the fewer wavefronts per height.
+struct __align__(32) F8 { float v[8]; };
+__device__ __forceinline__ F8 ldg_f8(const float* p) {
+  F8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
+  return r;
+}
+
 struct FoldPos {            // a lane's position in its sector's window sequence
   unsigned cur, end;        // current / one-past-last segment (indices into the frame's bucketed segment list)
   unsigned j, hi;           // remaining slots [j, hi] of the current segment
 };
 __device__ __forceinline__ bool fold_valid(const FoldPos& p) { return p.cur < p.end; }
 __device__ __forceinline__ void fold_advance(FoldPos& p, const uint32_t* __restrict__ SS, const uint16_t* __restrict__ SL) {
-  const unsigned nj = (p.j & ~3u) + FOLD_STEP;
+  const unsigned nj = (p.j & ~7u) + FOLD_STEP;
   if (nj <= p.hi) { p.j = nj; return; }
   p.cur++;
   if (p.cur < p.end) { p.j = SS[p.cur]; p.hi = p.j + SL[p.cur]; }
@@ -1070,45 +1125,45 @@ __global__ void __launch_bounds__(32 * FOLD_MAX_WPB) k_seg_fold(SensorDev sp, co
     const unsigned k = act[(size_t)f * NSECT + a];
     const unsigned d = kdesc[(size_t)f * NSECT + k];
     float acc = 0.0f;
-    unsigned nz = 0u;                                               // ground slots of this sector with a non-zero height (:205)
     if (VEC) {
+      static_assert(FOLD_STEP == 32, "the window mask of the 256-bit form is one 32-bit word");
       FoldPos pc; pc.cur = d >> 16; pc.end = pc.cur + (d & 0xFFFFu); pc.j = SS[pc.cur]; pc.hi = pc.j + SL[pc.cur];
       FoldPos pa = pc;
 #pragma unroll
       for (int q = 0; q < FOLD_DIST; q++) {
-        if (fold_valid(pa)) { prefetch_l1(Z + (pa.j & ~3u)); prefetch_l1(Z + (pa.j & ~3u) + FOLD_STEP - 1); fold_advance(pa, SS, SL); }
+        if (fold_valid(pa)) { prefetch_l1(Z + (pa.j & ~7u)); prefetch_l1(Z + (pa.j & ~7u) + FOLD_STEP - 1); fold_advance(pa, SS, SL); }
       }
-      float4 w[FOLD_STEP / 4];
+      F8 w[FOLD_STEP / 8];
       unsigned wj = pc.j, whi = pc.hi;                              // the window held in w
       {
-        const float4* src = reinterpret_cast<const float4*>(Z + (pc.j & ~3u));   // gz is padded: the window may pass the frame's end
+        const float* src = Z + (pc.j & ~7u);                        // gz is padded: the window may pass the frame's end
 #pragma unroll
-        for (int u = 0; u < FOLD_STEP / 4; u++) w[u] = __ldg(src + u);
+        for (int u = 0; u < FOLD_STEP / 8; u++) w[u] = ldg_f8(src + 8 * u);
       }
       while (true) {
         FoldPos pn = pc; fold_advance(pn, SS, SL);
         const bool more = fold_valid(pn);
-        float4 wn[FOLD_STEP / 4];
+        F8 wn[FOLD_STEP / 8];
         if (more) {
-          const float4* src = reinterpret_cast<const float4*>(Z + (pn.j & ~3u));
+          const float* src = Z + (pn.j & ~7u);
 #pragma unroll
-          for (int u = 0; u < FOLD_STEP / 4; u++) wn[u] = __ldg(src + u);
+          for (int u = 0; u < FOLD_STEP / 8; u++) wn[u] = ldg_f8(src + 8 * u);
         }
-        if (fold_valid(pa)) { prefetch_l1(Z + (pa.j & ~3u)); prefetch_l1(Z + (pa.j & ~3u) + FOLD_STEP - 1); fold_advance(pa, SS, SL); }
-        // heights outside [wj, whi] belong to other sectors (or to nobody): replaced by +0
-        const unsigned jb = wj & ~3u;
+        if (fold_valid(pa)) { prefetch_l1(Z + (pa.j & ~7u)); prefetch_l1(Z + (pa.j & ~7u) + FOLD_STEP - 1); fold_advance(pa, SS, SL); }
+        // heights outside [wj, whi] belong to other sectors (or to nobody) and are skipped: one predicated add per height
+        // (skipping equals adding +0: the sum starts at +0 and can never become -0)
+        const unsigned jb = wj & ~7u;
+        const unsigned m = (0xFFFFFFFFu << (wj - jb)) & (0xFFFFFFFFu >> (31u - min(whi - jb, 31u)));
 #pragma unroll
-        for (int u = 0; u < FOLD_STEP / 4; u++) {
-          const unsigned q = jb + 4 * u;
-          const float v0 = (q >= wj && q <= whi) ? w[u].x : 0.0f, v1 = (q + 1 >= wj && q + 1 <= whi) ? w[u].y : 0.0f;
-          const float v2 = (q + 2 >= wj && q + 2 <= whi) ? w[u].z : 0.0f, v3 = (q + 3 >= wj && q + 3 <= whi) ? w[u].w : 0.0f;
-          acc = __fadd_rn(acc, v0); acc = __fadd_rn(acc, v1); acc = __fadd_rn(acc, v2); acc = __fadd_rn(acc, v3);
-          nz += (v0 != 0.0f ? 1u : 0u) + (v1 != 0.0f ? 1u : 0u) + (v2 != 0.0f ? 1u : 0u) + (v3 != 0.0f ? 1u : 0u);
+        for (int u = 0; u < FOLD_STEP / 8; u++) {
+#pragma unroll
+          for (int e = 0; e < 8; e++)
+            if (m & (1u << (8 * u + e))) acc = __fadd_rn(acc, w[u].v[e]);
         }
         if (!more) break;
         pc = pn; wj = pn.j; whi = pn.hi;
 #pragma unroll
-        for (int u = 0; u < FOLD_STEP / 4; u++) w[u] = wn[u];
+        for (int u = 0; u < FOLD_STEP / 8; u++) w[u] = wn[u];
       }
     } else {
       unsigned cur = d >> 16; const unsigned endseg = cur + (d & 0xFFFFu);
@@ -1118,7 +1173,7 @@ __global__ void __launch_bounds__(32 * FOLD_MAX_WPB) k_seg_fold(SensorDev sp, co
 #pragma unroll
         for (int u = 0; u < FOLD_STEP; u++) { const unsigned q = j + u; v[u] = q <= hi ? Z[q] : 0.0f; }
 #pragma unroll
-        for (int u = 0; u < FOLD_STEP; u++) { acc = __fadd_rn(acc, v[u]); nz += v[u] != 0.0f ? 1u : 0u; }
+        for (int u = 0; u < FOLD_STEP; u++) acc = __fadd_rn(acc, v[u]);
         j += FOLD_STEP;
         if (j <= hi) continue;
         cur++;
@@ -1126,7 +1181,7 @@ __global__ void __launch_bounds__(32 * FOLD_MAX_WPB) k_seg_fold(SensorDev sp, co
         j = SS[cur]; hi = j + SL[cur];
       }
     }
-    avg[(size_t)f * NSECT + k] = __fdiv_rn(acc, cnt_lut[cnt[(size_t)f * NSECT + k] + nz]);   // :210
+    avg[(size_t)f * NSECT + k] = __fdiv_rn(acc, cnt_lut[cnt[(size_t)f * NSECT + k]]);   // :210; cnt = all ground slots of the sector (k_ground_mark + k_seg_build)
   }
 }
 
@@ -1173,31 +1228,26 @@ __global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const fl
   __syncthreads();
 
   const float4* R = rec + fb;
-  const int H = sp.H, NG = (H + 31) >> 5;
-  const uint32_t* GM = gmask + (size_t)f * (sp.G + 1) * NG;
-  const int first = sp.band_row0 * H;
   const int W = (sp.S + 31) >> 5;
+  const uint32_t* GM = gmask + (size_t)f * W;                       // ground_mat == 1 after loop 1, one bit per slot (k_ground_mark)
   uint32_t* gbits = reinterpret_cast<uint32_t*>(label_out) + (size_t)f * W;   // COMPACT only
   // Register double buffer: the loads of batch k+1 are in flight while batch k goes through the shared-memory atomics
   // (ncu: the loop was load-batch -> wait -> process, the memory pipe idled during every process phase).
   constexpr int UB = 2;   // measured: 0.87 / 0.81 / 0.86 / 0.92 us per frame for 1 / 2 / 3 / 4 records per thread and batch
-  float4 nv[UB]; bool ng[UB];
-  // (row, col) of the slot this thread fetches next, advanced by 1024 slots per record (no division in the loop)
-  int fr = tid / H, fc = tid - fr * H;
-  const int dr = 1024 / H, dc = 1024 - dr * H;
+  float4 nv[UB]; unsigned ng[UB];
+  const int lane = tid & 31;
   auto fetch = [&](int s0) {
 #pragma unroll
     for (int u = 0; u < UB; u++) {
       const int sl = s0 + u * 1024;
       nv[u] = sl < sp.S ? __ldcs(R + sl) : make_float4(0.f, 0.f, 0.f, 0.f);       // read once: streaming (evict-first) loads
-      // ground_mat == 1 after loop 1: one bit per slot of the band rows (k_ground_mark)
-      ng[u] = (sl < sp.S && sl >= first) ? ((__ldg(GM + (fr - sp.band_row0) * NG + (fc >> 5)) >> (fc & 31)) & 1u) != 0u : false;
-      fr += dr; fc += dc; if (fc >= H) { fc -= H; fr++; }
+      // the warp's 32 slots are one aligned word of the ground bits: a single broadcast load
+      ng[u] = sl - lane < sp.S ? __ldg(GM + (sl >> 5)) : 0u;
     }
   };
   fetch(tid);
   for (int slot0 = tid; slot0 - (tid & 31) < sp.S; slot0 += 1024 * UB) {   // warp-uniform trip count (the ballot below)
-   float4 pv[UB]; bool gv[UB];
+   float4 pv[UB]; unsigned gv[UB];
 #pragma unroll
    for (int u = 0; u < UB; u++) { pv[u] = nv[u]; gv[u] = ng[u]; }
    if (slot0 + 1024 * UB < sp.S) fetch(slot0 + 1024 * UB);
@@ -1209,7 +1259,7 @@ __global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const fl
     const float4 p = pv[u];
     int16_t lab = (int16_t)(__float_as_uint(p.w) & 0xFFFFu);
     bool ground = false;
-    if (in && gv[u]) {                           // ground_mat == 1 after loop 1
+    if (in && ((gv[u] >> lane) & 1u)) {          // ground_mat == 1 after loop 1
       const int key = (int)sector_of(p.x, p.y);
       const int sr = key / SECT_C, sc = key - sr * SECT_C;
       bool cleared = false;

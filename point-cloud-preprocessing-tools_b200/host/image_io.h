@@ -41,9 +41,16 @@ inline bool encode_png_gray8(const uint8_t* pix, int w, int h, std::vector<uint8
   png_chunk(out, "IHDR", ihdr.data(), ihdr.size());
   std::vector<uint8_t> raw((size_t)h * (w + 1));
   for (int y = 0; y < h; y++) { raw[(size_t)y * (w + 1)] = 0; memcpy(&raw[(size_t)y * (w + 1) + 1], pix + (size_t)y * w, w); }
-  uLongf cap = compressBound((uLong)raw.size());
-  std::vector<uint8_t> z(cap);
-  if (compress2(z.data(), &cap, raw.data(), (uLong)raw.size(), level) != Z_OK) return false;
+  // Z_RLE: match distance 1 only - what OpenCV's PNG writer asks of libpng by default (IMWRITE_PNG_STRATEGY_RLE) and far
+  // cheaper than hash chains on occupancy layers that are mostly runs of 0
+  z_stream zs; memset(&zs, 0, sizeof zs);
+  if (deflateInit2(&zs, level, Z_DEFLATED, 15, 8, Z_RLE) != Z_OK) return false;
+  std::vector<uint8_t> z(deflateBound(&zs, (uLong)raw.size()));
+  zs.next_in = raw.data(); zs.avail_in = (uInt)raw.size(); zs.next_out = z.data(); zs.avail_out = (uInt)z.size();
+  const int rc = deflate(&zs, Z_FINISH);
+  const size_t cap = zs.total_out;
+  deflateEnd(&zs);
+  if (rc != Z_STREAM_END) return false;
   png_chunk(out, "IDAT", z.data(), cap);
   png_chunk(out, "IEND", nullptr, 0);
   return true;
