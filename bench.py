@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true", help="skip the CLI / reference main() folder runs (rank 0, N=1)")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--wc", action="store_true", help="e2e input staging buffers write-combined (bevgen_host_alloc_wc)")
     return ap.parse_args()
 
 
@@ -382,8 +383,8 @@ def main():
     hb = tile_batch(distinct, Fe)
     e_offs = hb["offsets"]
 
-    def pin_copy(a):
-        p = pkg.pinned_empty(a.shape, a.dtype); p[...] = a
+    def pin_copy(a):      # input staging: written once by the host, then only read by the copy engine
+        p = pkg.pinned_empty(a.shape, a.dtype, write_combined=args.wc); p[...] = a
         return p
     # (a) compact staging format (bevgen_process_host_compact): x, y, z + (slot | flags) in; ground bits, winner bits,
     #     single and the 3 occupancy bit planes out.  The meta word is what a PCD parser writes instead of four SoA fields.
@@ -495,6 +496,7 @@ def main():
                            "parallelism": "frames sharded by index, %d process(es), no collective" % world},
                 "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "frames_per_step_per_gpu": Fe, "ms_per_step": e_wall / args.steps, "api": "bevgen_process_host_compact",
+                        "input_staging": "pinned, write-combined" if args.wc else "pinned",
                         "full_layout": {"value": e2e_full_v, "api": "bevgen_process_host", "h2d_bytes_per_step": h2d_full,
                                         "d2h_bytes_per_step": d2h_full, "ms_per_step": f_wall / args.steps},
                         "pcie_alone": {"ms_per_step": p_wall / args.steps, "h2d_GBps": lim, "frames_per_s_if_copy_bound": world * Fe / (p_wall / args.steps * 1e-3)},

@@ -97,6 +97,10 @@ BEVGEN_API const char *bevgen_last_error(void);
 /* Pinned host memory for staging (cudaHostAlloc); process_host/submit run fully async only on such buffers. */
 BEVGEN_API void *bevgen_host_alloc(size_t bytes);
 BEVGEN_API void bevgen_host_free(void *p);
+/* The same, write-combined (cudaHostAllocWriteCombined): for INPUT staging the host only ever writes sequentially and the
+ * copy engine reads - the PCIe reads are not snooped against the CPU caches, which matters when the GPUs of a box
+ * stage at once.  Never read such a buffer on the host (uncached reads); free with bevgen_host_free. */
+BEVGEN_API void *bevgen_host_alloc_wc(size_t bytes);
 
 /* The serial hot loop body BatchMultiBevGen.cpp:735-747 (getOrderedCloud + markGroundPoints + both BEVs, without
  * the file encoders) for n_frames frames.

@@ -127,7 +127,8 @@ EXPORTS = ["bevgen_sensor_params", "bevgen_create", "bevgen_destroy", "bevgen_la
            "bevgen_collect", "bevgen_select_major", "bevgen_labels", "bevgen_cloud_manip", "bevgen_set_profiling",
            "bevgen_stage_ms", "bevgen_kernel_launches", "bevgen_compute_stream", "bevgen_stage_name",
            "bevgen_debug_atan2f", "bevgen_pcd_record_layout", "bevgen_process_packed_host", "bevgen_project", "bevgen_top_flatten",
-           "bevgen_process_host_compact", "bevgen_cloud_manip_device", "bevgen_set_libm", "bevgen_set_diag", "bevgen_get_diag"]
+           "bevgen_process_host_compact", "bevgen_cloud_manip_device", "bevgen_set_libm", "bevgen_set_diag", "bevgen_get_diag",
+           "bevgen_host_alloc_wc"]
 
 
 def build(verbose=False):
@@ -150,6 +151,8 @@ def lib():
         L.bevgen_stage_name.restype = C.c_char_p
         L.bevgen_host_alloc.restype = C.c_void_p
         L.bevgen_host_alloc.argtypes = [C.c_size_t]
+        L.bevgen_host_alloc_wc.restype = C.c_void_p
+        L.bevgen_host_alloc_wc.argtypes = [C.c_size_t]
         L.bevgen_host_free.argtypes = [C.c_void_p]
         L.bevgen_kernel_launches.restype = C.c_int64
         L.bevgen_kernel_launches.argtypes = [C.c_void_p]
@@ -188,11 +191,12 @@ def _ptr(a):
     return C.c_void_p(a.ctypes.data)
 
 
-def pinned_empty(shape, dtype):
-    """numpy array backed by cudaHostAlloc memory (freed when the array's base capsule dies)."""
+def pinned_empty(shape, dtype, write_combined=False):
+    """numpy array backed by cudaHostAlloc memory (release with pinned_free).  write_combined: input staging only - the host
+    must never read such an array."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
-    p = lib().bevgen_host_alloc(max(n, 1))
+    p = (lib().bevgen_host_alloc_wc if write_combined else lib().bevgen_host_alloc)(max(n, 1))
     if not p:
         raise BevgenError(lib().bevgen_last_error().decode())
     buf = (C.c_char * max(n, 1)).from_address(p)

@@ -123,6 +123,11 @@ extern "C" void* bevgen_host_alloc(size_t bytes) {
   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
   return p;
 }
+extern "C" void* bevgen_host_alloc_wc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocWriteCombined) != cudaSuccess) { g_err = "cudaHostAlloc (write-combined) failed"; return nullptr; }
+  return p;
+}
 extern "C" void bevgen_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ---- allocation helpers ---------------------------------------------------------------------------------------
@@ -809,6 +814,25 @@ extern "C" int bevgen_labels(bevgen_ctx* c, int K, const float* xyz, int M, cons
 }
 
 // ---- cloud_manip ------------------------------------------------------------------------------------------------
+// Kernel + merge on the compute stream.  x .. tz, g_in, g_out are device pointers (g_in / g_out: the final 201 x 201 grids,
+// either may be NULL); `rep` = scratch for 2 * n_rep replicated grids.
+static int manip_replicas(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(MANIP_MAX_REP, n / 65536)); }
+static int launch_cloud_manip(bevgen_ctx* c, int64_t n, const Xform& xf, const float* x, const float* y, const float* z, float* tx, float* ty,
+                              float* tz, float* g_in, float* g_out, int* rep, int n_rep) {
+  const size_t cells = (size_t)MGRID * MGRID;
+  int* rep_in = g_in ? rep : nullptr;
+  int* rep_out = g_out ? rep + (size_t)n_rep * cells : nullptr;
+  CK(cudaMemsetAsync(rep, 0, 2 * (size_t)n_rep * cells * sizeof(int), c->s_comp));
+  if (n > 0) {
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    k_cloud_manip<<<blocks, 256, 0, c->s_comp>>>(n, xf, x, y, z, tx, ty, tz, rep_in, rep_out, n_rep);
+    c->launches++;
+  }
+  k_manip_merge<<<dim3((unsigned)((cells + 255) / 256), 2), 256, 0, c->s_comp>>>(rep_in, rep_out, n_rep, g_in, g_out);
+  CK(cudaGetLastError()); c->launches++;
+  return 0;
+}
+
 extern "C" int bevgen_cloud_manip(bevgen_ctx* c, int64_t n, const float* rt, const float* x, const float* y, const float* z,
                                   float* tx, float* ty, float* tz, float* bev_in, float* bev_out) {
   if (!c || !rt) return fail("bevgen_cloud_manip: null argument");
@@ -816,20 +840,20 @@ extern "C" int bevgen_cloud_manip(bevgen_ctx* c, int64_t n, const float* rt, con
   if (n > 0 && (!x || !y || !z)) return fail("bevgen_cloud_manip: null point array");   // an empty cloud may come with NULL arrays
   CK(cudaSetDevice(c->device));
   const size_t np = (size_t)std::max<int64_t>(n, 1);
-  if (tmp_reserve(c, 6 * Carver::pad(np * 4) + 2 * Carver::pad(MGRID * MGRID * 4))) return -1;
+  const int n_rep = manip_replicas(n);
+  if (tmp_reserve(c, 6 * Carver::pad(np * 4) + 2 * Carver::pad(MGRID * MGRID * 4) + Carver::pad(2 * (size_t)n_rep * MGRID * MGRID * 4))) return -1;
   Carver cv{c->tmp};
-  float* d[6]; int* g[2];
+  float* d[6]; float* g[2];
   for (int i = 0; i < 6; i++) d[i] = cv.take<float>(np);
-  for (int i = 0; i < 2; i++) { g[i] = cv.take<int>(MGRID * MGRID); CK(cudaMemsetAsync(g[i], 0, MGRID * MGRID * 4, c->s_comp)); }
+  for (int i = 0; i < 2; i++) g[i] = cv.take<float>(MGRID * MGRID);
+  int* rep = cv.take<int>(2 * (size_t)n_rep * MGRID * MGRID);
   Xform xf; memcpy(xf.m, rt, sizeof xf.m); xf.on = 1;
   if (n > 0) {
     CK(cudaMemcpyAsync(d[0], x, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
     CK(cudaMemcpyAsync(d[1], y, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
     CK(cudaMemcpyAsync(d[2], z, (size_t)n * 4, cudaMemcpyHostToDevice, c->s_comp));
-    int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-    k_cloud_manip<<<blocks, 256, 0, c->s_comp>>>(n, xf, d[0], d[1], d[2], d[3], d[4], d[5], bev_in ? g[0] : nullptr, bev_out ? g[1] : nullptr);
-    CK(cudaGetLastError()); c->launches++;
   }
+  if (launch_cloud_manip(c, n, xf, d[0], d[1], d[2], d[3], d[4], d[5], bev_in ? g[0] : nullptr, bev_out ? g[1] : nullptr, rep, n_rep)) return -1;
   CK(cudaStreamSynchronize(c->s_comp));
   // every output is optional on its own
   if (tx && n > 0) CK(cudaMemcpy(tx, d[3], (size_t)n * 4, cudaMemcpyDeviceToHost));
@@ -848,14 +872,10 @@ extern "C" int bevgen_cloud_manip_device(bevgen_ctx* c, int64_t n, const float* 
   if (n < 0 || (n > 0 && (!x || !y || !z))) return fail("bevgen_cloud_manip_device: bad point arrays");
   if ((tx || ty || tz) && !(tx && ty && tz)) return fail("bevgen_cloud_manip_device: tx, ty, tz must be given together");
   CK(cudaSetDevice(c->device));
-  if (bev_in) CK(cudaMemsetAsync(bev_in, 0, MGRID * MGRID * 4, c->s_comp));
-  if (bev_out) CK(cudaMemsetAsync(bev_out, 0, MGRID * MGRID * 4, c->s_comp));
-  if (n == 0) return 0;
+  const int n_rep = manip_replicas(n);
+  if (tmp_reserve(c, Carver::pad(2 * (size_t)n_rep * MGRID * MGRID * 4))) return -1;   // grow-only: no allocation after the first call of this size
   Xform xf; memcpy(xf.m, rt, sizeof xf.m); xf.on = 1;
-  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-  k_cloud_manip<<<blocks, 256, 0, c->s_comp>>>(n, xf, x, y, z, tx, ty, tz, reinterpret_cast<int*>(bev_in), reinterpret_cast<int*>(bev_out));
-  CK(cudaGetLastError()); c->launches++;
-  return 0;
+  return launch_cloud_manip(c, n, xf, x, y, z, tx, ty, tz, bev_in, bev_out, reinterpret_cast<int*>(c->tmp), n_rep);
 }
 
 // ---- projection step of the keyframe extractors ---------------------------------------------------

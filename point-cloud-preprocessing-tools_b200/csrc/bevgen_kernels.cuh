@@ -1474,22 +1474,43 @@ __global__ void __launch_bounds__(512) k_float_bev(SensorDev sp, const float4* _
   for (int i = tid; i < MGRID * MGRID; i += 512) o[i] = __int_as_float(bvm_s[i]);
 }
 
+// The max grids are REPLICATED: CTA b scatters into replica b % n_rep of each grid and k_manip_merge takes the cell-wise
+// max of the replicas.  A 201 x 201 grid is only 1263 lines of 128 bytes and the L2 serialises atomics that hit one line, so
+// 2 M points into ONE copy of the grid ran at the L2's same-line atomic rate (ncu / bench_extra: 133 us per call whatever
+// the kernel did around the atomics); sixteen copies spread the same atomics over sixteen times as many lines.
+constexpr int MANIP_MAX_REP = 16;
 __global__ void __launch_bounds__(256) k_cloud_manip(int64_t n, Xform xf, const float* __restrict__ x, const float* __restrict__ y,
                                                       const float* __restrict__ z, float* __restrict__ tx, float* __restrict__ ty,
-                                                      float* __restrict__ tz, int* __restrict__ bev_in, int* __restrict__ bev_out) {
+                                                      float* __restrict__ tz, int* __restrict__ rep_in, int* __restrict__ rep_out, int n_rep) {
   const int64_t stride = (int64_t)gridDim.x * 256;
   const int64_t n_pad = (n + 31) & ~(int64_t)31;
+  const size_t roff = (size_t)(blockIdx.x % n_rep) * (MGRID * MGRID);
+  int* const bev_in = rep_in ? rep_in + roff : nullptr;
+  int* const bev_out = rep_out ? rep_out + roff : nullptr;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_pad; i += stride) {
     const bool valid = i < n;
     float px = 0, py = 0, pz = 0;
-    if (valid) { px = x[i]; py = y[i]; pz = z[i]; }
+    if (valid) { px = __ldcs(x + i); py = __ldcs(y + i); pz = __ldcs(z + i); }
     const float ox = __fadd_rn(__fmul_rn(px, xf.m[0]), __fadd_rn(__fmul_rn(py, xf.m[1]), __fadd_rn(__fmul_rn(pz, xf.m[2]), xf.m[3])));
     const float oy = __fadd_rn(__fmul_rn(px, xf.m[4]), __fadd_rn(__fmul_rn(py, xf.m[5]), __fadd_rn(__fmul_rn(pz, xf.m[6]), xf.m[7])));
     const float oz = __fadd_rn(__fmul_rn(px, xf.m[8]), __fadd_rn(__fmul_rn(py, xf.m[9]), __fadd_rn(__fmul_rn(pz, xf.m[10]), xf.m[11])));
-    if (valid && tx) { tx[i] = ox; ty[i] = oy; tz[i] = oz; }
+    if (valid && tx) { __stcs(tx + i, ox); __stcs(ty + i, oy); __stcs(tz + i, oz); }
     if (bev_in) manip_scatter(px, py, pz, valid, bev_in);
     if (bev_out) manip_scatter(ox, oy, oz, valid, bev_out);
   }
+}
+
+// cell-wise max of the replicas (non-negative float patterns order like ints) -> the two 201 x 201 float grids.
+__global__ void __launch_bounds__(256) k_manip_merge(const int* __restrict__ rep_in, const int* __restrict__ rep_out, int n_rep,
+                                                      float* __restrict__ bev_in, float* __restrict__ bev_out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= MGRID * MGRID) return;
+  const int* rep = blockIdx.y == 0 ? rep_in : rep_out;
+  float* out = blockIdx.y == 0 ? bev_in : bev_out;
+  if (!rep || !out) return;
+  int m = 0;
+  for (int r = 0; r < n_rep; r++) m = max(m, rep[(size_t)r * (MGRID * MGRID) + i]);
+  out[i] = __int_as_float(m);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -163,6 +163,8 @@ def main():
     pkg, synth = load_pkg(), load_synth()
     dev = torch.device("cuda", 0)
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    if "--contention" in sys.argv:
+        return contention(pkg, torch, dev, synth, peak)
     # ---- configs[2], [3]: OS1_64 / HDL_32E frames resident in HBM (device path), CUDA events ---------------------------
     for sensor, F, wave in (("OS1_64", 8192, 4096), ("HDL_32E", 16384, 8192)):
         distinct = synth.make_batch(sensor, 32)
