@@ -1427,18 +1427,38 @@ __global__ void __launch_bounds__(128) k_labels(int K, const float* __restrict__
 // ------------------------------------------------------------------------------------------------------------
 constexpr int MGRID = 201;
 
-__device__ __forceinline__ void manip_scatter(float px, float py, float pz, bool valid, int* __restrict__ grid) {
+// One point's update of one max grid, split in two so that the kernel can have the reads of both grids in flight together:
+//   manip_probe : cell + value; when every lane of the warp sits in ONE cell (a heavily contended cell, BASELINE config #5's
+//                 stress) the warp's max is taken first (one REDUX) and only lane 0 goes on; then the check-first read - a
+//                 cell's max settles after a few arrivals, later points only read it (lanes of one cell read one address)
+//   manip_commit: lanes that still have to raise their cell.  A few of them: plain atomics (duplicates among them are rare).
+//                 Many: fold the lanes of a cell first (match_any); a reduce with a per-group mask is executed once per
+//                 DISTINCT mask of the warp (ncu, round 2: 32 serialised CREDUX per warp on scattered points, 40 % of the
+//                 kernel's samples), so lanes alone in their cell skip it.
+struct ManipProbe { int cell, vb; bool need; };
+__device__ __forceinline__ ManipProbe manip_probe(float px, float py, float pz, bool valid, const int* __restrict__ grid) {
   const float vx = __fadd_rn(px, 100.0f), vy = __fadd_rn(py, 100.0f);
   const float v = __fadd_rn(pz, 2.0f);
-  const bool in = valid && vx > -1.0f && vx < 200.0f && vy > -1.0f && vy < 200.0f && v > 0.0f;
+  bool in = valid && vx > -1.0f && vx < 200.0f && vy > -1.0f && vy < 200.0f && v > 0.0f;
   const int lane = threadIdx.x & 31;
-  const int cell = in ? (__float2int_rd(vx) + 1) * MGRID + (__float2int_rd(vy) + 1) : -1 - lane;
-  const unsigned peers = __match_any_sync(0xffffffffu, cell);
-  // the group's max in one REDUX: positive floats order like their int patterns (a warp whose 32 lanes all hit one cell
-  // costs the same as a warp that hits 32 cells; the round-1 form looped once per peer)
-  const int best = __reduce_max_sync(peers, __float_as_int(v));
-  if (in && lane == __ffs(peers) - 1) {
-    if (*reinterpret_cast<volatile int*>(&grid[cell]) < best) atomicMax(&grid[cell], best);
+  ManipProbe r;
+  r.cell = in ? (__float2int_rd(vx) + 1) * MGRID + (__float2int_rd(vy) + 1) : -1 - lane;
+  r.vb = __float_as_int(v);                          // positive floats order like their int patterns
+  const int c0 = __shfl_sync(0xffffffffu, r.cell, 0);
+  if (__all_sync(0xffffffffu, r.cell == c0)) { r.vb = __reduce_max_sync(0xffffffffu, r.vb); in = in && lane == 0; }
+  r.need = in && *reinterpret_cast<const volatile int*>(&grid[in ? r.cell : 0]) < r.vb;
+  return r;
+}
+__device__ __forceinline__ void manip_commit(const ManipProbe& r, int* __restrict__ grid) {
+  const unsigned nm = __ballot_sync(0xffffffffu, r.need);
+  if (nm == 0u) return;
+  if (__popc(nm) <= 8) { if (r.need) atomicMax(&grid[r.cell], r.vb); return; }
+  if (r.need) {
+    const int lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(nm, r.cell);
+    int best = r.vb;
+    if (peers != (1u << lane)) best = __reduce_max_sync(peers, best);
+    if (lane == __ffs(peers) - 1) atomicMax(&grid[r.cell], best);
   }
 }
 
@@ -1487,16 +1507,25 @@ __global__ void __launch_bounds__(256) k_cloud_manip(int64_t n, Xform xf, const 
   const size_t roff = (size_t)(blockIdx.x % n_rep) * (MGRID * MGRID);
   int* const bev_in = rep_in ? rep_in + roff : nullptr;
   int* const bev_out = rep_out ? rep_out + roff : nullptr;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_pad; i += stride) {
+  // the next point's loads are in flight while this one goes through the check-first reads (the loop is a chain of
+  // dependent memory round trips: point -> probe reads -> atomics; the probes of the two grids are issued together)
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  float nx = 0, ny = 0, nz = 0;
+  if (i < n) { nx = __ldcs(x + i); ny = __ldcs(y + i); nz = __ldcs(z + i); }
+  for (; i < n_pad; i += stride) {
     const bool valid = i < n;
-    float px = 0, py = 0, pz = 0;
-    if (valid) { px = __ldcs(x + i); py = __ldcs(y + i); pz = __ldcs(z + i); }
+    const float px = nx, py = ny, pz = nz;
+    const int64_t j = i + stride;
+    if (j < n) { nx = __ldcs(x + j); ny = __ldcs(y + j); nz = __ldcs(z + j); }
     const float ox = __fadd_rn(__fmul_rn(px, xf.m[0]), __fadd_rn(__fmul_rn(py, xf.m[1]), __fadd_rn(__fmul_rn(pz, xf.m[2]), xf.m[3])));
     const float oy = __fadd_rn(__fmul_rn(px, xf.m[4]), __fadd_rn(__fmul_rn(py, xf.m[5]), __fadd_rn(__fmul_rn(pz, xf.m[6]), xf.m[7])));
     const float oz = __fadd_rn(__fmul_rn(px, xf.m[8]), __fadd_rn(__fmul_rn(py, xf.m[9]), __fadd_rn(__fmul_rn(pz, xf.m[10]), xf.m[11])));
     if (valid && tx) { __stcs(tx + i, ox); __stcs(ty + i, oy); __stcs(tz + i, oz); }
-    if (bev_in) manip_scatter(px, py, pz, valid, bev_in);
-    if (bev_out) manip_scatter(ox, oy, oz, valid, bev_out);
+    ManipProbe a, b;
+    if (bev_in) a = manip_probe(px, py, pz, valid, bev_in);
+    if (bev_out) b = manip_probe(ox, oy, oz, valid, bev_out);
+    if (bev_in) manip_commit(a, bev_in);
+    if (bev_out) manip_commit(b, bev_out);
   }
 }
 
