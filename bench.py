@@ -80,6 +80,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, dev):
         super().__init__(daemon=True)
         self.dev, self.rows, self.stop_ev = dev, [], threading.Event()   # rows: (sm_mhz, max_mhz, {reasons})
+        self.mem, self.power = [], []
         self.nv = None
         try:
             import pynvml
@@ -95,6 +96,11 @@ class ClockSampler(threading.Thread):
     def _nvml_sample(self):
         nv = self.nv
         sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            self.mem.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM)))
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+        except Exception:
+            pass
         get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
         mask = int(get(self.h))
         names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
@@ -123,8 +129,13 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"]}
         sm = sorted(r[0] for r in self.rows)
         reasons = sorted(set().union(*[r[2] for r in self.rows]))
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows),
-                "source": "nvml" if self.nv else "nvidia-smi"}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows),
+               "source": "nvml" if self.nv else "nvidia-smi"}
+        if self.mem:
+            out["mem_mhz"] = sorted(self.mem)[len(self.mem) // 2]
+        if self.power:
+            out["power_w"] = sorted(self.power)[len(self.power) // 2]
+        return out
 
 
 def algorithmic_bytes(sensor_S, n_in_total, F):
@@ -441,16 +452,21 @@ def main():
     del hb
 
     # ---- per-rank record: who is slow, and on what -------------------------------------------------------------------
+    stage_names = [k for k, v in st.items() if v[1] > 0]
     mine = torch.tensor([ms_local / args.steps, e_wall_local / args.steps, h2d * args.steps / (e_wall_local * 1e-3) / 1e9,
                          h2d * args.steps / (p_wall_local * 1e-3) / 1e9, d2h * args.steps / (p_wall_local * 1e-3) / 1e9,
-                         float(clocks.get("sm_mhz") or 0)], device=dev, dtype=torch.float64)
+                         float(clocks.get("sm_mhz") or 0), float(clocks.get("mem_mhz") or 0), float(clocks.get("power_w") or 0)] +
+                        [st[k][0] / args.steps / F * 1e3 for k in stage_names], device=dev, dtype=torch.float64)
     allr = [torch.zeros_like(mine) for _ in range(world)]
     if world > 1:
         dist.all_gather(allr, mine)
     else:
         allr = [mine]
     per_rank = [{"rank": r, "ms_per_step": float(t[0]), "e2e_ms_per_step": float(t[1]), "e2e_h2d_GBps": float(t[2]),
-                 "pcie_alone_h2d_GBps": float(t[3]), "pcie_alone_d2h_GBps": float(t[4]), "sm_mhz": float(t[5])} for r, t in enumerate(allr)]
+                 "pcie_alone_h2d_GBps": float(t[3]), "pcie_alone_d2h_GBps": float(t[4]), "sm_mhz": float(t[5]), "mem_mhz": float(t[6]),
+                 "power_w": float(t[7]), "stage_us_per_frame": {k: round(float(t[8 + i]), 4) for i, k in enumerate(stage_names)}}
+                for r, t in enumerate(allr)]
+    slow = max(per_rank, key=lambda r: r["ms_per_step"]); fast = min(per_rank, key=lambda r: r["ms_per_step"])
 
     # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------------------------
     cpu, cli = None, None
@@ -478,6 +494,19 @@ def main():
                          "port: %d frames x %d passes on %d threads (%.1f s); single-thread port: %.1f frames/s over %d frames" %
                          (nfr, reps, cores, dt, (len(one["offsets"]) - 1) / dt1, len(one["offsets"]) - 1),
                "port_frames_per_s": v_port, "port_single_thread_frames_per_s": (len(one["offsets"]) - 1) / dt1, "reference_source": rs}
+        try:    # cloud_manip on 2 M points (config #5's cloud), the oracle port on one core
+            rng = np.random.default_rng(3); n_cm = 2_000_000
+            blob = rng.random(n_cm) < 0.6
+            cx = np.where(blob, rng.normal(0, 3, n_cm), rng.uniform(-100, 100, n_cm)).astype(np.float32)
+            cy = np.where(blob, rng.normal(0, 3, n_cm), rng.uniform(-100, 100, n_cm)).astype(np.float32)
+            cz = rng.uniform(-2, 10, n_cm).astype(np.float32)
+            th = np.float32(np.deg2rad(37.0)); cs, sn = np.float32(np.cos(th)), np.float32(np.sin(th))
+            rt = np.array([cs, -sn, 0, 3.5, sn, cs, 0, -1.25, 0, 0, 1, 0.2], np.float32)
+            t0 = time.perf_counter()
+            tx, ty, tz = O.transform(rt, cx, cy, cz); O.save_as_mat(cx, cy, cz); O.save_as_mat(tx, ty, tz)
+            cpu["cloud_manip_2M_points_port_ms_1_core"] = (time.perf_counter() - t0) * 1e3
+        except Exception as e:
+            cpu["cloud_manip_2M_points_port_ms_1_core"] = repr(e)[:200]
         if not args.no_cli and os.path.exists(pkg.CLI_PATH):
             try:
                 cli = cli_numbers(pkg, synth, O, args)
@@ -503,7 +532,10 @@ def main():
                         "limiter": "PCIe host-to-device copy: the e2e step takes %.2f ms, the copy engines alone need %.2f ms for the same %d MB in / %d MB out"
                                    % (e_wall / args.steps, p_wall / args.steps, h2d >> 20, d2h >> 20)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_ms_per_step": wall_ms / args.steps,
-                "per_rank": per_rank}
+                "per_rank": per_rank,
+                "rank_spread": {"slowest_rank": slow["rank"], "slowest_ms_per_step": slow["ms_per_step"], "fastest_ms_per_step": fast["ms_per_step"],
+                                "sum_of_ranks_frames_per_s": sum(F / (r["ms_per_step"] * 1e-3) for r in per_rank),
+                                "note": "value is the max-over-ranks number the contract asks for; identical work per rank, so a spread is the box (see per_rank clocks / stages)"}}
         if parity is not None:
             ok = all(v["ok"] for v in parity.values())
             line["parity_checked"] = {"frames": sum(v["frames"] for v in parity.values()), "ok": ok, **parity}

@@ -1,16 +1,13 @@
 """Multi-GPU host logic of the path: frames are independent (BatchMultiBevGen.cpp:727-757 carries no
 state between iterations), so they shard by index with NO data-path collective; label rows are split per GPU and
-gathered on the host.  The same formulas are used by the C++ CLI (host/batch_multi_bev_gen.cpp) and bench.py."""
+gathered on the host.  Callers: tools/bench_extra.py --sharded (BASELINE configs[2], [3] under torchrun: frame_shard for the
+keyframe batch, row_split for the K x M label table) and tests/test_sharding_gloo.py.  The C++ CLI splits the label rows
+with the same formula (host/batch_multi_bev_gen.cpp, label stage) and hands frames out per batch as workers become free."""
 
 
 def frame_shard(n_frames, rank, world):
     """Contiguous block [lo, hi) of the sorted frame list owned by `rank`."""
     return n_frames * rank // world, n_frames * (rank + 1) // world
-
-
-def batch_owner(batch_index, world):
-    """Dynamic variant used by the CLI workers degenerates to round-robin when all GPUs are equally fast."""
-    return batch_index % world
 
 
 def row_split(K, world):

@@ -65,8 +65,10 @@ def sharded():
         finally:
             sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     pkg, synth = load_pkg(), load_synth()
+    import importlib
+    sh = importlib.import_module("pcpt_b200.sharding")     # the shard formulas the gloo test checks on CPU
     K = 10000
-    lo, hi = K * rank // world, K * (rank + 1) // world
+    lo, hi = sh.frame_shard(K, rank, world)
     for sensor in ("OS1_64", "HDL_32E"):
         distinct = synth.make_batch(sensor, 32, first=1000 * rank)
         ms, n_total, S, st = device_rate(pkg, torch, dev, sensor, distinct, hi - lo, min(hi - lo, 4096 if sensor == "OS1_64" else 8192), device=local)
@@ -80,6 +82,7 @@ def sharded():
     xyz = synth.make_poses(K, seed=11, step=2.0)
     g = pkg.BevGen("OS1_64", device=local, max_frames_per_batch=2)
     t0 = time.perf_counter(); mi, _ = g.select_major(xyz); t_sel = time.perf_counter() - t0
+    lo, hi = sh.row_split(K, world)[rank]
     t0 = time.perf_counter(); lab, _, _ = g.labels(xyz, mi, lo, hi); t_lab = time.perf_counter() - t0
     g.close()
     h = hashlib.sha256(np.ascontiguousarray(lab).tobytes()).digest()
