@@ -75,15 +75,19 @@ def expand_multi(planes):
     return (((planes[:, l >> 3] >> (l & 7)[None, :, None, None].astype(np.uint8)) & 1) * 255).astype(np.uint8)
 
 
-def labels_from_ground_bits(ground_bits, owner, label_in, offsets):
+def labels_from_ground_bits(ground_bits, owner, label_in, offsets, frames=None):
     """[F][S] int16 labels of the ordered cloud from the compact outputs: 0 where the slot is ground (or empty), else the
-    label of the input point that owns the slot (BatchMultiBevGen.cpp:244-248 leaves it untouched)."""
-    F, S = owner.shape
-    g = np.unpackbits(np.asarray(ground_bits, np.uint32).reshape(F, -1).view(np.uint8), axis=1, bitorder="little")[:, :S].astype(bool)
-    lab = np.zeros((F, S), np.int16)
-    for f in range(F):
-        sel = (owner[f] > 0) & ~g[f]
-        lab[f, sel] = np.asarray(label_in)[int(offsets[f]) + owner[f][sel].astype(np.int64) - 1]
+    label of the input point that owns the slot (BatchMultiBevGen.cpp:244-248 leaves it untouched).  frames: the frame
+    indices the rows of `owner` stand for (default: all frames of the batch)."""
+    F = len(offsets) - 1
+    frames = list(range(F)) if frames is None else list(frames)
+    S = owner.shape[1]
+    gb = np.asarray(ground_bits, np.uint32).reshape(F, -1)
+    lab = np.zeros((len(frames), S), np.int16)
+    for j, f in enumerate(frames):
+        g = np.unpackbits(gb[f].view(np.uint8), bitorder="little")[:S].astype(bool)
+        sel = (owner[j] > 0) & ~g
+        lab[j, sel] = np.asarray(label_in)[int(offsets[f]) + owner[j][sel].astype(np.int64) - 1]
     return lab
 
 
@@ -108,17 +112,17 @@ def winner_mask(winner, offsets, f):
     return np.unpackbits(words.view(np.uint8), bitorder="little")[:n].astype(bool)
 
 
-def owner_from_winner(winner, offsets, row, col, H, S):
+def owner_from_winner(winner, offsets, row, col, H, S, frames=None):
     """[F][S] uint32, 1 + index of the input point that occupies the slot (0 = empty): the ordered cloud of
     getOrderedCloud (BatchMultiBevGen.cpp:94-117) expressed as a gather table, rebuilt on the host from the winner bits
     and the caller's own row/col — what a host does to write non_ground_point_cloud/*.pcd (:756)."""
-    F = len(offsets) - 1
-    own = np.zeros((F, S), np.uint32)
-    for f in range(F):
+    frames = list(range(len(offsets) - 1)) if frames is None else list(frames)
+    own = np.zeros((len(frames), S), np.uint32)
+    for j, f in enumerate(frames):
         o, e = int(offsets[f]), int(offsets[f + 1])
         idx = np.nonzero(winner_mask(winner, offsets, f))[0]
         slot = row[o:e][idx].astype(np.int64) * H + col[o:e][idx].astype(np.int64)
-        own[f, slot] = (idx + 1).astype(np.uint32)
+        own[j, slot] = (idx + 1).astype(np.uint32)
     return own
 
 
@@ -286,13 +290,15 @@ class BevGen:
         _ck(lib().bevgen_process_host_compact(self._ctx, C.c_int(F), _ptr(offs), C.byref(pts), C.byref(o)))
         return out
 
-    def compact_to_reference_layout(self, cout, batch):
+    def compact_to_reference_layout(self, cout, batch, frames=None):
         """Expands compact outputs into the dict process_host returns (owner, label, single, multi), using the caller's
-        own row / col / label arrays - what the CLI's encode pool does before writing files."""
+        own row / col / label arrays - what the CLI's encode pool does before writing files.  frames: only these frame
+        indices (rows of the result follow that list)."""
         offs = np.asarray(batch["offsets"], np.int64)
-        owner = owner_from_winner(cout["winner"], offs, _as(batch["row"], np.uint16), _as(batch["col"], np.uint16), self.params.horizon_scan, self.S)
-        return dict(owner=owner, label=labels_from_ground_bits(cout["ground"], owner, batch["label"], offs), single=np.asarray(cout["single"]),
-                    multi=expand_multi(cout["planes"]))
+        owner = owner_from_winner(cout["winner"], offs, _as(batch["row"], np.uint16), _as(batch["col"], np.uint16), self.params.horizon_scan, self.S, frames)
+        sel = slice(None) if frames is None else list(frames)
+        return dict(owner=owner, label=labels_from_ground_bits(cout["ground"], owner, batch["label"], offs, frames),
+                    single=np.asarray(cout["single"])[sel], multi=expand_multi(np.asarray(cout["planes"])[sel]))
 
     def process_packed_host(self, records, offsets, layout=None, out=None):
         """records: HOST uint8 array with the concatenated interleaved records of all frames (a binary PCD payload);

@@ -41,7 +41,6 @@ struct Scratch {            // device scratch for one wave of up to `frames` fra
   float4* rec = 0; float* gz = 0; uint32_t* cnt = 0; float* avg = 0;
   uint4* gsum = 0; uint32_t* slow = 0;   // per (row, 32-column group) summaries; per-frame "use the sweep kernel" flag
   uint32_t* gmask = 0;                   // [frames][ceil(S/32)]: ground_mat == 1 after loop 1, one bit per slot (slot-linear; k_seg_build)
-  uint32_t* gmrow = 0;                   // the same bits as k_ground_mark leaves them: one word per (row, 32-column group)
   uint32_t* seg_start = 0; uint16_t* seg_len = 0;   // [frames][SEG_CAP] segments bucketed by sector, slot order inside a bucket
   uint32_t* kdesc = 0; uint16_t* act = 0; uint32_t* n_act = 0;   // [frames][NSECT] bucket (base<<16|count), active sectors; [frames]
   uint32_t* owner = 0;                   // [frames][S] claim table, only for range images too large for k_order_winners' shared memory
@@ -145,7 +144,6 @@ static int alloc_scratch(Scratch& s, size_t frames, const SensorDev& sp, int max
   }
   CK(cudaMalloc(&s.gsum, frames * gsum_per_frame(sp) * sizeof(uint4)));
   CK(cudaMalloc(&s.gmask, frames * ((S + 31) / 32) * sizeof(uint32_t)));
-  CK(cudaMalloc(&s.gmrow, frames * gsum_per_frame(sp) * sizeof(uint32_t)));
   CK(cudaMalloc(&s.slow, frames * sizeof(uint32_t)));
   CK(cudaMalloc(&s.seg_start, frames * SEG_CAP * sizeof(uint32_t))); CK(cudaMalloc(&s.seg_len, frames * SEG_CAP * sizeof(uint16_t)));
   CK(cudaMalloc(&s.kdesc, frames * NSECT * sizeof(uint32_t))); CK(cudaMalloc(&s.act, frames * NSECT * sizeof(uint16_t)));
@@ -157,7 +155,7 @@ static int alloc_scratch(Scratch& s, size_t frames, const SensorDev& sp, int max
   return 0;
 }
 static void free_scratch(Scratch& s) {
-  cudaFree(s.rec); cudaFree(s.gmask); cudaFree(s.gmrow); cudaFree(s.gz); cudaFree(s.cnt); cudaFree(s.avg); cudaFree(s.gsum); cudaFree(s.slow); cudaFree(s.seg_start); cudaFree(s.seg_len); cudaFree(s.kdesc); cudaFree(s.act); cudaFree(s.n_act); cudaFree(s.owner); cudaFree(s.occ); cudaFree(s.cwin); cudaFree(s.cpt);
+  cudaFree(s.rec); cudaFree(s.gmask); cudaFree(s.gz); cudaFree(s.cnt); cudaFree(s.avg); cudaFree(s.gsum); cudaFree(s.slow); cudaFree(s.seg_start); cudaFree(s.seg_len); cudaFree(s.kdesc); cudaFree(s.act); cudaFree(s.n_act); cudaFree(s.owner); cudaFree(s.occ); cudaFree(s.cwin); cudaFree(s.cpt);
   s = Scratch();
 }
 static int alloc_io(DevIn& in, DevOut& out, size_t frames, size_t pts, size_t S) {
@@ -370,8 +368,8 @@ static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
   mark(3);
   {
     dim3 g((sp.H + GM_T - 1) / GM_T, w.nf);
-    if (sp.libm_double || sp.diag) k_ground_mark<true><<<g, GM_T, 0, st>>>(sp, w.sc->rec, w.sc->gmrow, w.sc->gz, w.sc->cnt, w.sc->gsum);
-    else k_ground_mark<false><<<g, GM_T, 0, st>>>(sp, w.sc->rec, w.sc->gmrow, w.sc->gz, w.sc->cnt, w.sc->gsum);
+    if (sp.libm_double || sp.diag) k_ground_mark<true><<<g, GM_T, 0, st>>>(sp, w.sc->rec, w.sc->gz, w.sc->cnt, w.sc->gsum);
+    else k_ground_mark<false><<<g, GM_T, 0, st>>>(sp, w.sc->rec, w.sc->gz, w.sc->cnt, w.sc->gsum);
   }
   mark(4);
   CK(cudaGetLastError());
@@ -382,7 +380,7 @@ static int wave_sweep(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
   NvtxRange nv("bevgen sweep: sector means");
   // segment form first; frames it cannot hold (> seg_cap segments) raise slow[f] and are swept by k_sector_mean
   k_seg_build<<<w.nf, SEGT, SMEM_SEG, st>>>(c->sp, c->seg_cap, w.sc->gsum, w.sc->rec, w.sc->avg, w.sc->slow, w.sc->seg_start,
-                                            w.sc->seg_len, w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->gmrow, w.sc->gmask, w.sc->cnt);
+                                            w.sc->seg_len, w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->gmask, w.sc->cnt);
   const dim3 fg(w.nf, FOLD_PASSES / c->fold_wpb), fb(32, c->fold_wpb);
   if ((c->sp.S & 7) == 0)   // every frame of gz starts on a 32-byte boundary: 256-bit loads
     k_seg_fold<true><<<fg, fb, 0, st>>>(c->sp, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->slow, w.sc->seg_start, w.sc->seg_len,
@@ -508,7 +506,10 @@ extern "C" int bevgen_sync(bevgen_ctx* c) {
 // ---- host-buffer path: H2D (copy stream) | kernels (compute stream) | D2H (third stream), double-buffered ------
 // The host path is PCIe-bound, so its chunks are kept small enough that H2D of chunk k+1, the kernels of chunk k and
 // D2H of chunk k-1 overlap (the device path uses max_frames_per_batch-sized waves instead).
-static int host_chunk(const bevgen_ctx* c) { return std::min(c->max_frames, 48); }
+static int host_chunk(const bevgen_ctx* c) {
+  static const int pref = [] { const char* e = getenv("BEVGEN_HOST_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 48; }();
+  return std::min(c->max_frames, pref);
+}
 
 static int alloc_lanes(bevgen_ctx* c) {
   for (auto& l : c->lanes) {

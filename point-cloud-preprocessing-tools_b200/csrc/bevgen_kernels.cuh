@@ -663,8 +663,7 @@ __device__ __forceinline__ bool ground_decision(const SensorDev& sp, const float
 
 constexpr int GM_T = 64;   // columns per CTA: H = 2083 columns fill 33 CTAs of 64 to 98.6 % (17 of 128: 95.7 %)
 template <bool DBL>
-__global__ void __launch_bounds__(GM_T) k_ground_mark(SensorDev sp, const float4* __restrict__ rec,
-                                                      uint32_t* __restrict__ gmrow, float* __restrict__ gz,
+__global__ void __launch_bounds__(GM_T) k_ground_mark(SensorDev sp, const float4* __restrict__ rec, float* __restrict__ gz,
                                                       uint32_t* __restrict__ cnt, uint4* __restrict__ gsum) {
   const int f = blockIdx.y;
   const int c0 = blockIdx.x * GM_T + threadIdx.x;
@@ -685,7 +684,6 @@ __global__ void __launch_bounds__(GM_T) k_ground_mark(SensorDev sp, const float4
   const int NG = (H + 31) >> 5;
   const size_t g0 = ((size_t)f * (sp.G + 1) + sp.G) * NG + (c0 >> 5);     // row N-1 first, walked upwards by -NG
   uint4* gs = gsum + g0;
-  uint32_t* gm = gmrow + g0;                                              // ground_mat == 1 bits of the group (k_seg_build re-packs them slot-linear)
   const unsigned lt = (1u << lane) - 1u;
 
   auto emit = [&](const float4& p, bool gm1) {
@@ -705,8 +703,11 @@ __global__ void __launch_bounds__(GM_T) k_ground_mark(SensorDev sp, const float4
     const unsigned below = pm & lt;
     const unsigned pk = __shfl_sync(0xffffffffu, k2, (31 - __clz(below)) & 31);
     const unsigned hm = __ballot_sync(0xffffffffu, part && below != 0u && pk != k2);
+    // summary of the (row, group): x = participating lanes, y = sector-change lanes, z = first | last sector << 16 (stored by
+    // those two lanes themselves; measured: fetching them to lane 0 with two shuffles for one 16-byte store is slower),
+    // w = the ground_mat == 1 bits of the group (k_seg_build re-packs those in slot order for k_finalize_bin)
     if (c0 - lane < H) {                                         // the group exists (warp-uniform)
-      if (lane == 0) { gs->x = pm; gs->y = hm; *gm = gmm; }
+      if (lane == 0) { gs->x = pm; gs->y = hm; gs->w = gmm; }
       uint16_t* fl = reinterpret_cast<uint16_t*>(&gs->z);
       if (part && below == 0u) fl[0] = (uint16_t)k2;
       if (part && (pm >> lane) == 1u) fl[1] = (uint16_t)k2;
@@ -720,15 +721,15 @@ __global__ void __launch_bounds__(GM_T) k_ground_mark(SensorDev sp, const float4
     const float4 direct = nxt;
     if (r >= 2) nxt = pr[-2 * H];                                 // next iteration's upper: in flight during this row's math
     float4 up = direct;
-    if (is_neg1(up)) up = pr[-H + dplus];                         // :146-149
-    if (is_neg1(up)) up = pr[-H + dminus];                        // :151-154
+    if (is_neg1(up)) up = pr[-H + dplus];                         // :146-149  (predicated loads; a warp-uniform skip of the
+    if (is_neg1(up)) up = pr[-H + dminus];                        // :151-154   chain behind __any_sync measured slower)
     if (is_neg1(up) && r >= 2) up = pr[-2 * H];                   // :157-160
     const bool invalid = is_neg1(lower) || is_neg1(up);           // :162
     const bool ground = !invalid && ground_decision<DBL>(sp, up, lower);
     emit(lower, !invalid && (ground || ground_prev));
     ground_prev = ground;
     lower = direct;
-    pr -= H; gzp -= H; gs -= NG; gm -= NG;
+    pr -= H; gzp -= H; gs -= NG;
   }
   emit(lower, ground_prev);   // row above the band only receives gm[row-1] = 1 (:181)
 }
@@ -844,8 +845,7 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
                                                      uint32_t* __restrict__ slow_flag, uint32_t* __restrict__ seg_start,
                                                      uint16_t* __restrict__ seg_len, uint32_t* __restrict__ kdesc,
                                                      uint16_t* __restrict__ act, uint32_t* __restrict__ n_act_out,
-                                                     const uint32_t* __restrict__ gmrow, uint32_t* __restrict__ gmask,
-                                                     uint32_t* __restrict__ cnt) {
+                                                     uint32_t* __restrict__ gmask, uint32_t* __restrict__ cnt) {
   extern __shared__ __align__(16) unsigned char seg_smem[];
   uint32_t* s_start = reinterpret_cast<uint32_t*>(seg_smem);   // [SEG_CAP] first slot of the segment
   uint32_t* s_endtmp = s_start + SEG_CAP;                       // [SEG_CAP] last participating slot of the segment
@@ -889,13 +889,12 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
   for (int i = tid; i < NSECT; i += SEGT) s_kcnt[i] = 0;
   for (int i = tid; i < SEG_CAP / 2; i += SEGT) s_np[i] = 0u;
   if (tid == 0) s_misc[0] = 0;
-  // ---- the ground_mat == 1 bits, re-packed from k_ground_mark's (row, 32-column group) words into one bit per slot in
+  // ---- the ground_mat == 1 bits, re-packed from k_ground_mark's (row, 32-column group) words (summary field w) into one bit per slot in
   // slot order (bit s & 31 of word s >> 5): k_finalize_bin walks the frame 32 consecutive slots per warp and then needs a
   // single broadcast word.  Rows are H columns wide and H is not a multiple of 32, so a word is pieced together from up to
   // four source words.  Independent of everything below; its loads overlap the summary loads of pass 1.
   {
     const int W = (sp.S + 31) >> 5;
-    const uint32_t* GR = gmrow + (size_t)f * n_groups;
     uint32_t* GB = gmask + (size_t)f * W;
     for (int w = tid; w < W; w += SEGT) {
       uint32_t out = 0u;
@@ -905,7 +904,7 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
         const int n = min(32 - b, min(32 - (c & 31), H - c));       // bits this source word supplies
         const int rb = r - sp.band_row0;
         if (rb >= 0) {
-          const uint32_t src = GR[rb * NG + (c >> 5)] >> (c & 31);
+          const uint32_t src = GS[rb * NG + (c >> 5)].w >> (c & 31);
           out |= (n == 32 ? src : (src & ((1u << n) - 1u))) << b;
         }
         b += n; slot += n; c += n;

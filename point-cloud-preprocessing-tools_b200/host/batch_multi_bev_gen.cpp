@@ -195,6 +195,8 @@ struct Shared {
   std::atomic<int> next_batch{0}; int n_batches = 0;
   std::mutex print_mu;
   std::atomic<long> frames_done{0};
+  // first batch back from the GPU: everything before it is start-up (pinned / device allocations, first PCD loads)
+  std::atomic<bool> first_seen{false}; std::chrono::steady_clock::time_point t_first; std::atomic<long> first_frames{0};
   std::atomic<bool> failed{false};
 };
 
@@ -382,6 +384,7 @@ struct GpuWorker {
       if (rc != 0) {
         std::cerr << "bevgen_process_host: " << bevgen_last_error() << std::endl; sh.failed = true; give_pin(p); break;
       }
+      if (!sh.first_seen.exchange(true)) { sh.t_first = std::chrono::steady_clock::now(); sh.first_frames = cur->count; }
       cur->pending_encodes = cur->count;
       for (int k = 0; k < cur->count; k++) {
         sh.pool->submit([this, cur, k] {
@@ -467,7 +470,15 @@ int main(int argc, char** argv) {
     for (auto& t : ths) t.join();
     pool.wait_idle();
   }
-  double total_ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+  const auto t_end = Clock::now();
+  double total_ms = std::chrono::duration<double, std::milli>(t_end - t0).count();
+  // start-up (allocations + the first batch's loads and GPU pass) and the rate of the pipeline once it is running
+  double startup_ms = 0.0, steady_fps = 0.0;
+  if (sh.first_seen) {
+    startup_ms = std::chrono::duration<double, std::milli>(sh.t_first - t0).count();
+    const double rest_s = std::chrono::duration<double>(t_end - sh.t_first).count();
+    if (rest_s > 0 && (long)sh.files.size() > sh.first_frames) steady_fps = ((long)sh.files.size() - sh.first_frames) / rest_s;
+  }
   if (sh.failed) return 1;
   // the reference averages its per-frame serial span (:749-759); here frames overlap, so this is wall time / frames
   std::cout << "[TIME] Average preprocessing and BEV generation: " << (sh.files.empty() ? 0.0 : total_ms / sh.files.size()) << "\n";
@@ -538,6 +549,7 @@ int main(int argc, char** argv) {
     j << "{\"frames\": " << sh.files.size() << ", \"gpus\": " << workers.size() << ", \"batch\": " << opt.batch << ", \"threads\": " << opt.threads
       << ", \"encode\": " << (opt.encode ? "true" : "false") << ", \"write_pcd\": " << (opt.write_pcd ? "true" : "false")
       << ", \"frames_wall_ms\": " << total_ms << ", \"frames_per_s\": " << (total_ms > 0 ? sh.files.size() / (total_ms * 1e-3) : 0.0)
+      << ", \"startup_ms\": " << startup_ms << ", \"frames_per_s_after_first_batch\": " << steady_fps
       << ", \"keyframes\": " << K << ", \"majors\": " << M << ", \"labels_wall_ms\": " << label_ms << "}\n";
   }
   for (auto& wk : workers) { if (wk->ctx) bevgen_destroy(wk->ctx); for (auto& p : wk->pins) p.release_all(); }
