@@ -1022,14 +1022,22 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
   __syncthreads();
   // ---- one warp walks the ordered segment list and hands out positions inside the sector buckets ----
   if (wid == 0) {
+    // The only serial dependence between two batches of 32 segments is the fill level of a sector both touch; the keys, the
+    // match and the rank inside the batch do not depend on it, so they are computed one batch ahead (the walk was a quarter
+    // of the kernel's samples: every step waited for its own shared-memory load, match and two warp syncs in a row).
+    const unsigned ltm = (1u << lane) - 1u;
+    unsigned k = lane < nseg ? (unsigned)s_key[lane] : NO_KEY;
+    unsigned peers = __match_any_sync(0xffffffffu, k);
     for (int b = 0; b < nseg; b += 32) {
       const int e = b + lane;
       const bool valid = e < nseg;
-      const unsigned k = valid ? (unsigned)s_key[e] : NO_KEY;
-      const unsigned peers = __match_any_sync(0xffffffffu, k);
-      const unsigned pos = valid ? (unsigned)s_kbase[k] + __popc(peers & ((1u << lane) - 1u)) : 0u;
+      const unsigned kc = k, pc = peers;
+      const int en = e + 32;                                        // next batch: key and match in flight during this one
+      k = en < nseg ? (unsigned)s_key[en] : NO_KEY;
+      peers = __match_any_sync(0xffffffffu, k);
+      const unsigned pos = valid ? (unsigned)s_kbase[kc] + __popc(pc & ltm) : 0u;
       __syncwarp();
-      if (valid && (peers >> lane) == 1u) s_kbase[k] = (uint16_t)(pos + 1u);  // the group's highest lane publishes the new fill level
+      if (valid && (pc >> lane) == 1u) s_kbase[kc] = (uint16_t)(pos + 1u);  // the group's highest lane publishes the new fill level
       if (valid) s_order[e] = (uint16_t)pos;
       __syncwarp();
     }
@@ -1080,7 +1088,10 @@ __global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const
 // grid (F, FOLD_PASSES / wpb), block (32, wpb): warp p of a frame owns the active sectors p*32 + lane (+ 32*FOLD_PASSES ...);
 // the list is sorted by cost, so a frame's pass 0 holds its 32 longest chains.
 #ifndef FOLD_DIST_N
-#define FOLD_DIST_N 3
+#define FOLD_DIST_N 2
+#endif
+#ifndef FOLD_SINGLE_BUFFER
+#define FOLD_SINGLE_BUFFER 1
 #endif
 constexpr int FOLD_DIST = FOLD_DIST_N;
 constexpr int FOLD_MAX_WPB = 4;
@@ -1098,13 +1109,22 @@ __device__ __forceinline__ F8 ldg_f8(const float* p) {
 struct FoldPos {            // a lane's position in its sector's window sequence
   unsigned cur, end;        // current / one-past-last segment (indices into the frame's bucketed segment list)
   unsigned j, hi;           // remaining slots [j, hi] of the current segment
+  unsigned nj, nhi;         // the FOLLOWING segment, fetched when the current one was entered: a position never waits for a
+                            // descriptor at a segment change (ncu: that dependent load was an exposed L2 round trip per step)
 };
 __device__ __forceinline__ bool fold_valid(const FoldPos& p) { return p.cur < p.end; }
+__device__ __forceinline__ void fold_fetch_next(FoldPos& p, const uint32_t* __restrict__ SS, const uint16_t* __restrict__ SL) {
+  if (p.cur + 1 < p.end) { p.nj = SS[p.cur + 1]; p.nhi = p.nj + SL[p.cur + 1]; }
+}
+__device__ __forceinline__ void fold_init(FoldPos& p, unsigned first, unsigned count, const uint32_t* __restrict__ SS, const uint16_t* __restrict__ SL) {
+  p.cur = first; p.end = first + count; p.j = SS[first]; p.hi = p.j + SL[first]; p.nj = 0u; p.nhi = 0u;
+  fold_fetch_next(p, SS, SL);
+}
 __device__ __forceinline__ void fold_advance(FoldPos& p, const uint32_t* __restrict__ SS, const uint16_t* __restrict__ SL) {
   const unsigned nj = (p.j & ~7u) + FOLD_STEP;
   if (nj <= p.hi) { p.j = nj; return; }
   p.cur++;
-  if (p.cur < p.end) { p.j = SS[p.cur]; p.hi = p.j + SL[p.cur]; }
+  if (p.cur < p.end) { p.j = p.nj; p.hi = p.nhi; fold_fetch_next(p, SS, SL); }
 }
 
 template <bool VEC>
@@ -1126,12 +1146,33 @@ __global__ void __launch_bounds__(32 * FOLD_MAX_WPB) k_seg_fold(SensorDev sp, co
     float acc = 0.0f;
     if (VEC) {
       static_assert(FOLD_STEP == 32, "the window mask of the 256-bit form is one 32-bit word");
-      FoldPos pc; pc.cur = d >> 16; pc.end = pc.cur + (d & 0xFFFFu); pc.j = SS[pc.cur]; pc.hi = pc.j + SL[pc.cur];
+      FoldPos pc; fold_init(pc, d >> 16, d & 0xFFFFu, SS, SL);
       FoldPos pa = pc;
 #pragma unroll
       for (int q = 0; q < FOLD_DIST; q++) {
         if (fold_valid(pa)) { prefetch_l1(Z + (pa.j & ~7u)); prefetch_l1(Z + (pa.j & ~7u) + FOLD_STEP - 1); fold_advance(pa, SS, SL); }
       }
+#if FOLD_SINGLE_BUFFER
+      // one window buffer: the loads find their lines in L1 (the prefetch position runs FOLD_DIST windows ahead), half the
+      // registers of the double-buffered form, no window copies
+      while (true) {
+        F8 w[FOLD_STEP / 8];
+        const unsigned jb = pc.j & ~7u;
+        const float* src = Z + jb;                                  // gz is padded: the window may pass the frame's end
+#pragma unroll
+        for (int u = 0; u < FOLD_STEP / 8; u++) w[u] = ldg_f8(src + 8 * u);
+        if (fold_valid(pa)) { prefetch_l1(Z + (pa.j & ~7u)); prefetch_l1(Z + (pa.j & ~7u) + FOLD_STEP - 1); fold_advance(pa, SS, SL); }
+        const unsigned m = (0xFFFFFFFFu << (pc.j - jb)) & (0xFFFFFFFFu >> (31u - min(pc.hi - jb, 31u)));
+#pragma unroll
+        for (int u = 0; u < FOLD_STEP / 8; u++) {
+#pragma unroll
+          for (int e = 0; e < 8; e++)
+            if (m & (1u << (8 * u + e))) acc = __fadd_rn(acc, w[u].v[e]);
+        }
+        fold_advance(pc, SS, SL);
+        if (!fold_valid(pc)) break;
+      }
+#else
       F8 w[FOLD_STEP / 8];
       unsigned wj = pc.j, whi = pc.hi;                              // the window held in w
       {
@@ -1164,6 +1205,7 @@ __global__ void __launch_bounds__(32 * FOLD_MAX_WPB) k_seg_fold(SensorDev sp, co
 #pragma unroll
         for (int u = 0; u < FOLD_STEP / 8; u++) w[u] = wn[u];
       }
+#endif
     } else {
       unsigned cur = d >> 16; const unsigned endseg = cur + (d & 0xFFFFu);
       unsigned j = SS[cur], hi = j + SL[cur];
