@@ -830,6 +830,9 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const float4* 
 // k_sector_mean (the sweep form).
 // k_seg_build: grid F, block SEGT, dynamic smem SMEM_SEG.
 // ------------------------------------------------------------------------------------------------------------
+#ifndef SEG_MIN_CTAS
+#define SEG_MIN_CTAS 2
+#endif
 constexpr int SEG_CAP = 4096;
 constexpr int SEGT = 512;
 constexpr int SMEM_SEG = SEG_CAP * 4 * 2 + NSECT * 4 + SEGT * 8 + 320 + SEG_CAP * 2 * 3 + (NSECT + 2) * 2 + 8 + SEG_CAP * 2;   // 92,464 B (two CTAs per SM)
@@ -840,7 +843,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 constexpr int FOLD_STEP = FOLD_STEP_N;           // heights per step of a chain in k_seg_fold
 constexpr int FOLD_PASSES = 12;         // warps per frame in k_seg_fold (32 sectors each; more sectors wrap around)
 
-__global__ void __launch_bounds__(SEGT) k_seg_build(SensorDev sp, int cap, const uint4* __restrict__ gsum,
+__global__ void __launch_bounds__(SEGT, SEG_MIN_CTAS) k_seg_build(SensorDev sp, int cap, const uint4* __restrict__ gsum,
                                                      const float4* __restrict__ rec, float* __restrict__ avg,
                                                      uint32_t* __restrict__ slow_flag, uint32_t* __restrict__ seg_start,
                                                      uint16_t* __restrict__ seg_len, uint32_t* __restrict__ kdesc,
