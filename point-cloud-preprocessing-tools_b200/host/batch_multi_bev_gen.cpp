@@ -59,6 +59,23 @@ struct ThreadPool {
     });
   }
   void submit(std::function<void()> f) { { std::lock_guard<std::mutex> l(mu); q.push_back(std::move(f)); } cv.notify_one(); }
+  void submit_urgent(std::function<void()> f) { { std::lock_guard<std::mutex> l(mu); q.push_front(std::move(f)); } cv.notify_one(); }
+  // fn(0) .. fn(n-1) on the pool, ahead of everything queued (a GPU worker is waiting for them), the caller taking its share
+  void parallel_for(int n, const std::function<void(int)>& fn) {
+    if (n <= 0) return;
+    struct St { std::atomic<int> next{0}, done{0}; std::mutex m; std::condition_variable c; };
+    auto st = std::make_shared<St>();
+    auto body = [st, n, &fn] {
+      for (;;) { const int i = st->next++; if (i >= n) break; fn(i); if (++st->done == n) { std::lock_guard<std::mutex> l(st->m); st->c.notify_all(); } }
+    };
+    const int helpers = std::min<int>(n - 1, (int)th.size());
+    for (int h = 0; h < helpers; h++) submit_urgent([st, n, &fn] {      // a helper that arrives late finds nothing left and never touches fn
+      for (;;) { const int i = st->next++; if (i >= n) break; fn(i); if (++st->done == n) { std::lock_guard<std::mutex> l(st->m); st->c.notify_all(); } }
+    });
+    body();
+    std::unique_lock<std::mutex> l(st->m);
+    st->c.wait(l, [&] { return st->done.load() == n; });
+  }
   void wait_idle() { std::unique_lock<std::mutex> l(mu); idle_cv.wait(l, [&] { return q.empty() && active == 0; }); }
   ~ThreadPool() { { std::lock_guard<std::mutex> l(mu); stop = true; } cv.notify_all(); for (auto& t : th) t.join(); }
 };
@@ -188,6 +205,12 @@ struct Batch {
   std::atomic<int> pending_encodes{0};
 };
 
+struct PhaseTimer {     // adds the scope's duration to an accumulator
+  std::atomic<long long>& acc; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit PhaseTimer(std::atomic<long long>& a) : acc(a) {}
+  ~PhaseTimer() { acc += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 struct Shared {
   Options opt; Dirs dirs; bevgen_params params; size_t S = 0;
   std::vector<std::string> files;
@@ -195,6 +218,8 @@ struct Shared {
   std::atomic<int> next_batch{0}; int n_batches = 0;
   std::mutex print_mu;
   std::atomic<long> frames_done{0};
+  // CPU seconds spent per phase, summed over all pool threads (--json-metrics): where the host side of the pipeline goes
+  std::atomic<long long> ns_load{0}, ns_stage{0}, ns_gpu_call{0}, ns_png{0}, ns_csv{0}, ns_bin{0}, ns_pcd{0};
   // first batch back from the GPU: everything before it is start-up (pinned / device allocations, first PCD loads)
   std::atomic<bool> first_seen{false}; std::chrono::steady_clock::time_point t_first; std::atomic<long> first_frames{0};
   std::atomic<bool> failed{false};
@@ -219,21 +244,31 @@ static void encode_frame(Shared& sh, const Batch& b, int k) {
     }
   } else if (sh.opt.encode) {
     // .bin: 24 layers concatenated row-major (:294-314)
-    std::string bin = sh.dirs.multi_bin + name + ".bin";
-    if (!imgio::write_bytes(bin, multi, (size_t)L * G * G)) std::cerr << "Can not open file: " << bin << "\n";
-    std::string img_dir = sh.dirs.multi_img + name + "/";
-    mkdir(img_dir.c_str(), 0777);                                           // mkdir(2), not system("mkdir -p") (:303-306)
-    char nm[16];
-    for (int l = 0; l < L; l++) {
-      snprintf(nm, sizeof nm, "%02d.png", l);                               // "{:02d}.png" (:316-318)
-      imgio::write_png_gray8(img_dir + nm, multi + (size_t)l * G * G, G, G, sh.opt.png_level);
+    {
+      PhaseTimer t(sh.ns_bin);
+      std::string bin = sh.dirs.multi_bin + name + ".bin";
+      if (!imgio::write_bytes(bin, multi, (size_t)L * G * G)) std::cerr << "Can not open file: " << bin << "\n";
     }
-    imgio::write_png_gray8(sh.dirs.single_img + name + ".png", single, G, G, sh.opt.png_level);   // :359-361
-    std::string csv = sh.dirs.single_csv + name + ".csv";
-    std::string txt = imgio::format_csv_u8(single, G, G);                   // :371
-    if (!imgio::write_bytes(csv, txt.data(), txt.size())) std::cerr << "Faied to export csv formatted BEV file: " << csv;
+    {
+      PhaseTimer t(sh.ns_png);
+      std::string img_dir = sh.dirs.multi_img + name + "/";
+      mkdir(img_dir.c_str(), 0777);                                         // mkdir(2), not system("mkdir -p") (:303-306)
+      char nm[16];
+      for (int l = 0; l < L; l++) {
+        snprintf(nm, sizeof nm, "%02d.png", l);                             // "{:02d}.png" (:316-318)
+        imgio::write_png_gray8(img_dir + nm, multi + (size_t)l * G * G, G, G, sh.opt.png_level);
+      }
+      imgio::write_png_gray8(sh.dirs.single_img + name + ".png", single, G, G, sh.opt.png_level);   // :359-361
+    }
+    {
+      PhaseTimer t(sh.ns_csv);
+      std::string csv = sh.dirs.single_csv + name + ".csv";
+      std::string txt = imgio::format_csv_u8(single, G, G);                 // :371
+      if (!imgio::write_bytes(csv, txt.data(), txt.size())) std::cerr << "Faied to export csv formatted BEV file: " << csv;
+    }
   }
   if (sh.opt.write_pcd) {
+    PhaseTimer t(sh.ns_pcd);
     // savePCDFileBinary(non_ground/<name>.pcd, cloud_ordered) (:755-756): S slots; slot record = winning input record
     // with its label replaced by the post-ground label, empty slots all-zero.  The library reports one winner bit per
     // input point (the last writer of each (row, col) slot, :102-116); the slot is the point's own row*H + col.
@@ -243,7 +278,17 @@ static void encode_frame(Shared& sh, const Batch& b, int k) {
     std::vector<uint8_t> out(h.size() + S * 26, 0);
     memcpy(out.data(), h.data(), h.size());
     uint8_t* rec = out.data() + h.size();
-    if (b.packed) {   // winners straight from the file's own records
+    static const pcdio::PackedLayout canon = [] { pcdio::PackedLayout c; c.stride = 26; const int o[8] = {0, 4, 8, 12, 16, 18, 20, 24}; memcpy(c.off, o, sizeof o); return c; }();
+    if (b.packed && b.lays[k] == canon) {   // the file's records ARE output records: copy 26 bytes, replace the label
+      const uint8_t* pay = b.files[k].data() + b.payload_pos[k];
+      for (size_t i = 0, n = b.npts[k]; i < n; i++) {
+        if (!((win[i >> 5] >> (i & 31)) & 1u)) continue;
+        const uint8_t* src = pay + i * 26;
+        uint16_t r, c; memcpy(&r, src + 16, 2); memcpy(&c, src + 18, 2);
+        const size_t s = (size_t)r * H + c;
+        memcpy(rec + s * 26, src, 24); memcpy(rec + s * 26 + 24, &lab[s], 2);
+      }
+    } else if (b.packed) {   // winners straight from the file's own records
       const uint8_t* pay = b.files[k].data() + b.payload_pos[k]; const pcdio::PackedLayout& L = b.lays[k];
       for (size_t i = 0, n = b.npts[k]; i < n; i++) {
         if (!((win[i >> 5] >> (i & 31)) & 1u)) continue;
@@ -295,6 +340,7 @@ struct GpuWorker {
       bt->loads.push_back(pr->get_future());
       Batch* raw = bt.get(); Shared* s = &sh;
       sh.pool->submit([raw, s, k, pr, keep = bt] {
+        PhaseTimer t(s->ns_load);
         const std::string& f = s->files[raw->first + k];
         raw->names[k] = short_name_of(f);
         std::string err;
@@ -333,12 +379,16 @@ struct GpuWorker {
   void give_pin(PinnedSet* p) { { std::lock_guard<std::mutex> l(pin_mu); free_pins.push_back(p); } pin_cv.notify_one(); }
 
   void run() {
-    pins.resize(3);
+    pins.resize(4);
     for (auto& p : pins) free_pins.push_back(&p);
-    std::shared_ptr<Batch> next = grab();
-    while (next && !sh.failed) {
-      std::shared_ptr<Batch> cur = next;
-      next = grab();                                   // its PCD parsing overlaps this batch's GPU work
+    // Three batches of PCD loads are always queued ahead of the batch on the GPU: the pool is FIFO, so a batch's loads sit in
+    // front of the encode tasks of the batches before it and the GPU never waits for a file behind a queue of PNG / PCD writers
+    std::deque<std::shared_ptr<Batch>> ahead;
+    auto refill = [&] { while (ahead.size() < 3) { auto b = grab(); if (!b) break; ahead.push_back(b); } };
+    refill();
+    while (!ahead.empty() && !sh.failed) {
+      std::shared_ptr<Batch> cur = ahead.front(); ahead.pop_front();
+      refill();
       for (auto& f : cur->loads) f.get();
       // the batch goes through the packed path iff every frame is an interleaved payload of one and the same layout
       cur->packed = sh.opt.packed && cur->count > 0;
@@ -362,23 +412,29 @@ struct GpuWorker {
       bevgen_outputs out{p->o_label, p->o_winner, p->o_single, p->o_multi, sh.opt.bvm_mode ? p->o_bvm : nullptr};
       cur->offs = offs;
       int rc;
+      const auto t_stage0 = Clock::now();
       if (cur->packed) {
         const size_t stride = (size_t)cur->lays[0].stride;
         if (!p->ensure_raw((size_t)offs[cur->count] * stride + 64)) { std::cerr << "pinned allocation failed" << std::endl; sh.failed = true; give_pin(p); break; }
-        for (int k = 0; k < cur->count; k++)           // staging = one copy of the file payload into pinned memory
+        sh.pool->parallel_for(cur->count, [&](int k) {  // staging = one copy of the file payload into pinned memory, frames in parallel
           if (cur->npts[k]) memcpy(p->raw + (size_t)offs[k] * stride, cur->files[k].data() + cur->payload_pos[k], cur->npts[k] * stride);
+        });
         const int* o = cur->lays[0].off;
         bevgen_record_layout lay{cur->lays[0].stride, o[0], o[1], o[2], o[3], o[4], o[5], o[7]};
+        sh.ns_stage += std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - t_stage0).count();
+        PhaseTimer t(sh.ns_gpu_call);
         rc = bevgen_process_packed_host(ctx, cur->count, offs.data(), p->raw, &lay, &out);
       } else {
-        for (int k = 0; k < cur->count; k++) {           // SoA staging into pinned memory
+        sh.pool->parallel_for(cur->count, [&](int k) {    // SoA staging into pinned memory, frames in parallel
           const pcdio::Cloud& c = cur->clouds[k]; size_t o = (size_t)offs[k], n = c.size();
-          if (!n) continue;
+          if (!n) return;
           memcpy(p->x + o, c.x.data(), n * 4); memcpy(p->y + o, c.y.data(), n * 4); memcpy(p->z + o, c.z.data(), n * 4);
           memcpy(p->inten + o, c.intensity.data(), n * 4); memcpy(p->row + o, c.row.data(), n * 2); memcpy(p->col + o, c.col.data(), n * 2);
           memcpy(p->label + o, c.label.data(), n * 2);
-        }
+        });
         bevgen_points in{p->x, p->y, p->z, p->inten, p->row, p->col, p->label};
+        sh.ns_stage += std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - t_stage0).count();
+        PhaseTimer t(sh.ns_gpu_call);
         rc = bevgen_process_host(ctx, cur->count, offs.data(), &in, &out);
       }
       if (rc != 0) {
@@ -546,10 +602,14 @@ int main(int argc, char** argv) {
   double label_ms = std::chrono::duration<double, std::milli>(Clock::now() - t1).count();
   if (!opt.json_metrics.empty()) {
     std::ofstream j(opt.json_metrics);
+    const double nfr = std::max<double>(1.0, (double)sh.files.size());
     j << "{\"frames\": " << sh.files.size() << ", \"gpus\": " << workers.size() << ", \"batch\": " << opt.batch << ", \"threads\": " << opt.threads
       << ", \"encode\": " << (opt.encode ? "true" : "false") << ", \"write_pcd\": " << (opt.write_pcd ? "true" : "false")
       << ", \"frames_wall_ms\": " << total_ms << ", \"frames_per_s\": " << (total_ms > 0 ? sh.files.size() / (total_ms * 1e-3) : 0.0)
       << ", \"startup_ms\": " << startup_ms << ", \"frames_per_s_after_first_batch\": " << steady_fps
+      << ", \"cpu_ms_per_frame\": {\"pcd_load\": " << sh.ns_load * 1e-6 / nfr << ", \"pinned_staging\": " << sh.ns_stage * 1e-6 / nfr
+      << ", \"gpu_call_wall\": " << sh.ns_gpu_call * 1e-6 / nfr << ", \"bin\": " << sh.ns_bin * 1e-6 / nfr << ", \"png_25\": " << sh.ns_png * 1e-6 / nfr
+      << ", \"csv\": " << sh.ns_csv * 1e-6 / nfr << ", \"pcd_write\": " << sh.ns_pcd * 1e-6 / nfr << "}"
       << ", \"keyframes\": " << K << ", \"majors\": " << M << ", \"labels_wall_ms\": " << label_ms << "}\n";
   }
   for (auto& wk : workers) { if (wk->ctx) bevgen_destroy(wk->ctx); for (auto& p : wk->pins) p.release_all(); }
