@@ -41,7 +41,7 @@ struct Scratch {            // device scratch for one wave of up to `frames` fra
   float4* rec = 0; float* gz = 0; uint32_t* cnt = 0; float* avg = 0;
   uint4* gsum = 0; uint32_t* slow = 0;   // per (row, 32-column group) summaries; per-frame "use the sweep kernel" flag
   uint32_t* gmask = 0;                   // [frames][ceil(S/32)]: ground_mat == 1 after loop 1, one bit per slot (slot-linear; k_seg_build)
-  uint32_t* seg_start = 0; uint16_t* seg_len = 0;   // [frames][SEG_CAP] segments bucketed by sector, slot order inside a bucket
+  uint32_t* seg_start = 0; uint16_t* seg_len = 0;   // [frames][SEG_STRIDE] segments bucketed by sector, slot order inside a bucket
   uint32_t* kdesc = 0; uint16_t* act = 0; uint32_t* n_act = 0;   // [frames][NSECT] bucket (base<<16|count), active sectors; [frames]
   uint32_t* owner = 0;                   // [frames][S] claim table, only for range images too large for k_order_winners' shared memory
   uint32_t* occ = 0;                     // [3][frames][ceil(S/32)] slot occupancy bits, contention bits, contended-id prefix
@@ -145,7 +145,7 @@ static int alloc_scratch(Scratch& s, size_t frames, const SensorDev& sp, int max
   CK(cudaMalloc(&s.gsum, frames * gsum_per_frame(sp) * sizeof(uint4)));
   CK(cudaMalloc(&s.gmask, frames * ((S + 31) / 32) * sizeof(uint32_t)));
   CK(cudaMalloc(&s.slow, frames * sizeof(uint32_t)));
-  CK(cudaMalloc(&s.seg_start, frames * SEG_CAP * sizeof(uint32_t))); CK(cudaMalloc(&s.seg_len, frames * SEG_CAP * sizeof(uint16_t)));
+  CK(cudaMalloc(&s.seg_start, frames * SEG_STRIDE * sizeof(uint32_t))); CK(cudaMalloc(&s.seg_len, frames * SEG_STRIDE * sizeof(uint16_t)));
   CK(cudaMalloc(&s.kdesc, frames * NSECT * sizeof(uint32_t))); CK(cudaMalloc(&s.act, frames * NSECT * sizeof(uint16_t)));
   CK(cudaMalloc(&s.n_act, frames * sizeof(uint32_t)));
   CK(cudaMalloc(&s.rec, frames * S * sizeof(float4)));
@@ -226,11 +226,13 @@ static int create_fill(bevgen_ctx* c, int device, const bevgen_params* p, int ma
   // records of up to 256 bytes (bevgen_process_packed_host): 256 of them + the alignment head per CTA
   CK(cudaFuncSetAttribute(k_unpack_records<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256 + 32));
   CK(cudaFuncSetAttribute(k_unpack_records<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256 + 32));
-  CK(cudaFuncSetAttribute(k_seg_build, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SEG));
+  CK(cudaFuncSetAttribute(k_seg_build<SEG_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SEG));
+  CK(cudaFuncSetAttribute(k_seg_build<SEG_CAP_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SEG_BIG));
   CK(cudaFuncSetAttribute(k_float_bev, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BVM));
   CK(cudaFuncSetAttribute(k_order_winners<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // function-wide: the largest any context may ask for
   CK(cudaFuncSetAttribute(k_order_winners<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(k_seg_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_seg_build<SEG_CAP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_seg_build<SEG_CAP_BIG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   if (const char* e = getenv("BEVGEN_SEG_CAP")) c->seg_cap = std::max(0, std::min(SEG_CAP, atoi(e)));
   if (const char* e = getenv("BEVGEN_FOLD_WPB")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->fold_wpb = v; }
   CK(cudaMalloc(&c->diag_d, 4 * sizeof(unsigned long long)));
@@ -378,9 +380,12 @@ static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
 }
 static int wave_sweep(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {
   NvtxRange nv("bevgen sweep: sector means");
-  // segment form first; frames it cannot hold (> seg_cap segments) raise slow[f] and are swept by k_sector_mean
-  k_seg_build<<<w.nf, SEGT, SMEM_SEG, st>>>(c->sp, c->seg_cap, w.sc->gsum, w.sc->rec, w.sc->avg, w.sc->slow, w.sc->seg_start,
-                                            w.sc->seg_len, w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->gmask, w.sc->cnt);
+  // segment form first: every frame with up to seg_cap segments, then (one CTA per SM, twice the shared memory) the frames with
+  // up to SEG_CAP_BIG; what neither holds raises slow[f] = 1 and is swept by k_sector_mean
+  k_seg_build<SEG_CAP><<<w.nf, SEGT, SMEM_SEG, st>>>(c->sp, c->seg_cap, w.sc->gsum, w.sc->rec, w.sc->avg, w.sc->slow, w.sc->seg_start,
+                                                     w.sc->seg_len, w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->gmask, w.sc->cnt);
+  k_seg_build<SEG_CAP_BIG><<<w.nf, SEGT, SMEM_SEG_BIG, st>>>(c->sp, SEG_CAP_BIG, w.sc->gsum, w.sc->rec, w.sc->avg, w.sc->slow, w.sc->seg_start,
+                                                             w.sc->seg_len, w.sc->kdesc, w.sc->act, w.sc->n_act, w.sc->gmask, w.sc->cnt);
   const dim3 fg(w.nf, FOLD_PASSES / c->fold_wpb), fb(32, c->fold_wpb);
   if ((c->sp.S & 7) == 0)   // every frame of gz starts on a 32-byte boundary: 256-bit loads
     k_seg_fold<true><<<fg, fb, 0, st>>>(c->sp, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->slow, w.sc->seg_start, w.sc->seg_len,
@@ -391,7 +396,7 @@ static int wave_sweep(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
   k_sector_mean<<<w.nf, 32, 2 * NSECT * sizeof(float), st>>>(c->sp, w.sc->rec, w.sc->gz, w.sc->cnt, c->cnt_lut, w.sc->avg, w.sc->slow);
   if (prof) cudaEventRecord(c->pev[5], st);
   CK(cudaGetLastError());
-  c->launches += 3;
+  c->launches += 4;
   return 0;
 }
 static int wave_back(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool prof) {

@@ -833,9 +833,15 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const float4* 
 #ifndef SEG_MIN_CTAS
 #define SEG_MIN_CTAS 2
 #endif
-constexpr int SEG_CAP = 4096;
+constexpr int SEG_CAP = 4096;          // segments a frame may have for the two-CTAs-per-SM build
+constexpr int SEG_CAP_BIG = 8192;      // ... for the one-CTA-per-SM build that takes the frames above it (one synthetic HDL_64E frame in
+                                       // two hundred has more than 4096 segments; without this they fell to the one-warp sweep, which
+                                       // made the sector-mean stage of a whole wave 4.6 times slower)
+constexpr int SEG_STRIDE = SEG_CAP_BIG;   // entries per frame of the segment lists in global memory
 constexpr int SEGT = 512;
-constexpr int SMEM_SEG = SEG_CAP * 4 * 2 + NSECT * 4 + SEGT * 8 + 320 + SEG_CAP * 2 * 3 + (NSECT + 2) * 2 + 8 + SEG_CAP * 2;   // 92,464 B (two CTAs per SM)
+__host__ __device__ constexpr int seg_smem_bytes(int cap) { return cap * 4 * 2 + NSECT * 4 + SEGT * 8 + 320 + cap * 2 * 3 + (NSECT + 2) * 2 + 8 + cap * 2; }
+constexpr int SMEM_SEG = seg_smem_bytes(SEG_CAP);          // 92,464 B (two CTAs per SM)
+constexpr int SMEM_SEG_BIG = seg_smem_bytes(SEG_CAP_BIG);  // 158,000 B
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #ifndef FOLD_STEP_N
 #define FOLD_STEP_N 32   // 16 is 10 % slower
@@ -843,29 +849,31 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 constexpr int FOLD_STEP = FOLD_STEP_N;           // heights per step of a chain in k_seg_fold
 constexpr int FOLD_PASSES = 12;         // warps per frame in k_seg_fold (32 sectors each; more sectors wrap around)
 
-__global__ void __launch_bounds__(SEGT, SEG_MIN_CTAS) k_seg_build(SensorDev sp, int cap, const uint4* __restrict__ gsum,
+template <int CAP>   // SEG_CAP: every frame; SEG_CAP_BIG: only the frames the first pass flagged (slow_flag == 2)
+__global__ void __launch_bounds__(SEGT, CAP == SEG_CAP ? SEG_MIN_CTAS : 1) k_seg_build(SensorDev sp, int cap, const uint4* __restrict__ gsum,
                                                      const float4* __restrict__ rec, float* __restrict__ avg,
                                                      uint32_t* __restrict__ slow_flag, uint32_t* __restrict__ seg_start,
                                                      uint16_t* __restrict__ seg_len, uint32_t* __restrict__ kdesc,
                                                      uint16_t* __restrict__ act, uint32_t* __restrict__ n_act_out,
                                                      uint32_t* __restrict__ gmask, uint32_t* __restrict__ cnt) {
   extern __shared__ __align__(16) unsigned char seg_smem[];
-  uint32_t* s_start = reinterpret_cast<uint32_t*>(seg_smem);   // [SEG_CAP] first slot of the segment
-  uint32_t* s_endtmp = s_start + SEG_CAP;                       // [SEG_CAP] last participating slot of the segment
-  uint32_t* s_kcnt = s_endtmp + SEG_CAP;                        // [NSECT] segments per sector
+  uint32_t* s_start = reinterpret_cast<uint32_t*>(seg_smem);   // [CAP] first slot of the segment
+  uint32_t* s_endtmp = s_start + CAP;                       // [CAP] last participating slot of the segment
+  uint32_t* s_kcnt = s_endtmp + CAP;                        // [NSECT] segments per sector
   uint32_t* s_lk = s_kcnt + NSECT;                              // [SEGT] sector of the last participating slot of the thread's groups
   int* s_lp = reinterpret_cast<int*>(s_lk + SEGT);              // [SEGT] its slot (relative to the frame), -1 if none
   uint32_t* s_scan = reinterpret_cast<uint32_t*>(s_lp + SEGT);  // [32]
   uint32_t* s_warp = s_scan + 32;                               // [32]
   uint32_t* s_misc = s_warp + 32;                               // [16]
-  uint16_t* s_len = reinterpret_cast<uint16_t*>(s_misc + 16);   // [SEG_CAP] last participating slot - first slot
-  uint16_t* s_key = s_len + SEG_CAP;                            // [SEG_CAP] sector of the segment
-  uint16_t* s_order = s_key + SEG_CAP;                          // [SEG_CAP] segment ids bucketed by sector, slot order kept
-  uint16_t* s_kbase = s_order + SEG_CAP;                        // [NSECT + 2] bucket base, later bucket end
-  // [SEG_CAP / 2] participating slots (ground, z != 0) of every segment, two 16-bit counts per word (smem atomics are 32-bit)
+  uint16_t* s_len = reinterpret_cast<uint16_t*>(s_misc + 16);   // [CAP] last participating slot - first slot
+  uint16_t* s_key = s_len + CAP;                            // [CAP] sector of the segment
+  uint16_t* s_order = s_key + CAP;                          // [CAP] segment ids bucketed by sector, slot order kept
+  uint16_t* s_kbase = s_order + CAP;                        // [NSECT + 2] bucket base, later bucket end
+  // [CAP / 2] participating slots (ground, z != 0) of every segment, two 16-bit counts per word (smem atomics are 32-bit)
   uint32_t* s_np = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(s_kbase + NSECT + 2 + 3) & ~(uintptr_t)7);
 
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (CAP != SEG_CAP && slow_flag[f] != 2u) return;             // second pass: only the frames the first one could not hold (uniform)
   const int H = sp.H, NG = (H + 31) >> 5;
   const int n_groups = (sp.G + 1) * NG;
   const int gpt = (n_groups + SEGT - 1) / SEGT;                 // consecutive groups per thread
@@ -890,13 +898,13 @@ __global__ void __launch_bounds__(SEGT, SEG_MIN_CTAS) k_seg_build(SensorDev sp, 
   };
 
   for (int i = tid; i < NSECT; i += SEGT) s_kcnt[i] = 0;
-  for (int i = tid; i < SEG_CAP / 2; i += SEGT) s_np[i] = 0u;
+  for (int i = tid; i < CAP / 2; i += SEGT) s_np[i] = 0u;
   if (tid == 0) s_misc[0] = 0;
   // ---- the ground_mat == 1 bits, re-packed from k_ground_mark's (row, 32-column group) words (summary field w) into one bit per slot in
   // slot order (bit s & 31 of word s >> 5): k_finalize_bin walks the frame 32 consecutive slots per warp and then needs a
   // single broadcast word.  Rows are H columns wide and H is not a multiple of 32, so a word is pieced together from up to
   // four source words.  Independent of everything below; its loads overlap the summary loads of pass 1.
-  {
+  if (CAP == SEG_CAP) {                                         // (the first pass does it for every frame)
     const int W = (sp.S + 31) >> 5;
     uint32_t* GB = gmask + (size_t)f * W;
     for (int w = tid; w < W; w += SEGT) {
@@ -954,7 +962,10 @@ __global__ void __launch_bounds__(SEGT, SEG_MIN_CTAS) k_seg_build(SensorDev sp, 
   unsigned total = 0;
   const unsigned ebase = block_scan(nh, &total);
   const int nseg = (int)total;
-  if (nseg > cap) { if (tid == 0) slow_flag[f] = 1u; return; }    // uniform: the sweep kernel takes this frame
+  if (nseg > cap) {                                               // uniform: the frame goes to the second pass if that can hold it
+    if (tid == 0) slow_flag[f] = (CAP == SEG_CAP && cap == SEG_CAP && nseg <= SEG_CAP_BIG) ? 2u : 1u;   // (2), else to the sweep kernel (1)
+    return;
+  }
   // ---- pass 3: emit segments in slot order (lengths follow once every start is known) ----
   {
     unsigned e = ebase;
@@ -1053,8 +1064,8 @@ __global__ void __launch_bounds__(SEGT, SEG_MIN_CTAS) k_seg_build(SensorDev sp, 
   __syncthreads();
   for (int e = tid; e < nseg; e += SEGT) {
     const unsigned pos = s_order[e];
-    seg_start[(size_t)f * SEG_CAP + pos] = s_start[e];
-    seg_len[(size_t)f * SEG_CAP + pos] = s_len[e];
+    seg_start[(size_t)f * SEG_STRIDE + pos] = s_start[e];
+    seg_len[(size_t)f * SEG_STRIDE + pos] = s_len[e];
     atomicAdd(&s_span[s_key[e]], (unsigned)s_len[e] + 1u);
     atomicAdd(&s_knp[s_key[e]], (s_np[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
   }
@@ -1140,8 +1151,8 @@ __global__ void __launch_bounds__(32 * FOLD_MAX_WPB) k_seg_fold(SensorDev sp, co
   if (slow_flag[f]) return;                                       // the sweep kernel takes this frame
   const unsigned n_act = n_act_in[f];
   const float* Z = gz + (size_t)f * sp.S;
-  const uint32_t* SS = seg_start + (size_t)f * SEG_CAP;
-  const uint16_t* SL = seg_len + (size_t)f * SEG_CAP;
+  const uint32_t* SS = seg_start + (size_t)f * SEG_STRIDE;
+  const uint16_t* SL = seg_len + (size_t)f * SEG_STRIDE;
   const unsigned pass = blockIdx.y * blockDim.y + threadIdx.y;
   for (unsigned a = pass * 32 + threadIdx.x; a < n_act; a += 32 * FOLD_PASSES) {
     const unsigned k = act[(size_t)f * NSECT + a];

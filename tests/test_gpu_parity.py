@@ -48,6 +48,20 @@ def test_sector_mean_sweep_fallback(pkg, synth, O, monkeypatch):
             g.close()
 
 
+def test_frames_above_the_first_segment_capacity(pkg, synth, O):
+    """Synthetic HDL_64E keyframe 2030 has 4195 single-sector segments, more than the two-CTAs-per-SM segment build holds (4096):
+    it must go through the second, larger build (not the one-warp sweep) and still be bit-exact; mixed with ordinary frames."""
+    frames = [synth.make_frame("HDL_64E", i) for i in (2029, 2030, 2031, 2030)]
+    offs = np.zeros(len(frames) + 1, np.int64); offs[1:] = np.cumsum([len(f["x"]) for f in frames])
+    batch = {k: np.concatenate([f[k] for f in frames]) for k in FIELDS}; batch["offsets"] = offs
+    ref = oracle_batch(O, "HDL_64E", batch)
+    g = pkg.BevGen("HDL_64E", device=0, max_frames_per_batch=4)
+    try:
+        assert_same(g.process_host(batch), ref, "frame 2030 (4195 segments)")
+    finally:
+        g.close()
+
+
 def test_large_range_image_global_claim_path(pkg, O):
     """A range image too large for the shared-memory ordering kernel (S = 128 x 8192 > 640 k slots) takes the
     global-memory claim path (k_order_claim / k_order_fill / k_winner_bits); same results expected."""
