@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""Seeded fuzz of the CUDA path against the oracle beyond the fixed frames of tests/ (a checker run, not a benchmark):
+"""TEST INFRASTRUCTURE (it loads the oracle).  Seeded fuzz of the CUDA path against the oracle beyond the fixed frames of the
+parity tests (a checker run, not a benchmark):
 organised "scene" frames with random ground planes / walls / dropouts / -1 markers, random unstructured frames of random size,
 hot-cell frames, all three sensors, through bevgen_process_host AND bevgen_process_host_compact (after host expansion).
-    python tools/gpu_fuzz.py [n_rounds=20] [seed0=0]      -> prints one line per round, exits 1 on the first mismatch"""
+    python tests/gpu_fuzz.py [n_rounds=20] [seed0=0]      -> prints one line per round, exits 1 on the first mismatch"""
 import os
 import sys
 
