@@ -1315,8 +1315,8 @@ __global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const fl
     int16_t lab = (int16_t)(__float_as_uint(p.w) & 0xFFFFu);
     bool ground = false;
     if (in && ((gv[u] >> lane) & 1u)) {          // ground_mat == 1 after loop 1
-      const int key = (int)sector_of(p.x, p.y);
-      const int sr = key / SECT_C, sc = key - sr * SECT_C;
+      const int sr = sector_axis(p.x, 75.0f, SECT_R), sc = sector_axis(p.y, 50.0f, SECT_C);   // getBelongingGrid, BatchMultiBevGen.h:73-99
+      const int key = sr * SECT_C + sc;
       bool cleared = false;
       // neighbour order (-1,0),(0,1),(0,-1),(1,0) (:73-84); (double)(z - avg) > 0.30  <=>  (z - avg) >= 0.3f
       // because 0.3f is the smallest float above the double 0.30 (:236-237)
@@ -1374,14 +1374,18 @@ __global__ void __launch_bounds__(1024, 1) k_finalize_bin(SensorDev sp, const fl
   }
   uint4* mo = reinterpret_cast<uint4*>(multi + (size_t)f * LAYERS * CELLS);
   constexpr int Q = CELL_WORDS / 4;   // uint4 per layer = 3136
-  for (int i = tid; i < LAYERS * Q; i += 1024) {
-    const int layer = i / Q, q = i - layer * Q;
-    const uint4 v = reinterpret_cast<const uint4*>(occ + (layer >> 3) * CELL_WORDS)[q];
-    const int l = layer & 7;
-    uint4 o;
-    o.x = ((v.x >> l) & 0x01010101u) * 255u; o.y = ((v.y >> l) & 0x01010101u) * 255u;
-    o.z = ((v.z >> l) & 0x01010101u) * 255u; o.w = ((v.w >> l) & 0x01010101u) * 255u;
-    __stcs(mo + i, o);
+  // a 16-byte piece of a bit plane is read once and expanded into its eight layers (eight coalesced streaming stores)
+  for (int i = tid; i < 3 * Q; i += 1024) {
+    const int plane = i >= 2 * Q ? 2 : (i >= Q ? 1 : 0), q = i - plane * Q;
+    const uint4 v = reinterpret_cast<const uint4*>(occ + plane * CELL_WORDS)[q];
+    uint4* dst = mo + (size_t)plane * 8 * Q + q;
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+      uint4 o;
+      o.x = ((v.x >> l) & 0x01010101u) * 255u; o.y = ((v.y >> l) & 0x01010101u) * 255u;
+      o.z = ((v.z >> l) & 0x01010101u) * 255u; o.w = ((v.w >> l) & 0x01010101u) * 255u;
+      __stcs(dst + (size_t)l * Q, o);
+    }
   }
 }
 
