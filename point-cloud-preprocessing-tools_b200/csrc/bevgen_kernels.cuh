@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
       }
       return;
     }
-    auto rc = [&](unsigned r, unsigned c, int i) { visit(r * H + c, i >= 0 && i < n && r < N && c < H, i); };
+    auto rc = [&](unsigned r, unsigned c, int i) { visit(r * H + c, r < N && c < H, i); };   // callers only pass 0 <= i < n
     if (vec) {
       for (int v = tid; v < n8; v += ORD_T) {
         const int i = v * 8 - mis;

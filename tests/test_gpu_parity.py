@@ -442,6 +442,14 @@ def test_compact_host_path_bit_exact_after_expand(gens, pkg, synth, O, sensor):
     assert_same(g.compact_to_reference_layout(out, batch), oracle_batch(O, sensor, batch), "compact pinned " + sensor)
     for a in list(pin.values())[:4] + list(out.values()):
         pkg.pinned_free(a)
+    # write-combined input staging (bevgen_host_alloc_wc): written once by the host, only ever read by the copy engine
+    wc = {k: pkg.pinned_empty(np.asarray(cb[k]).shape, np.asarray(cb[k]).dtype, write_combined=True) for k in ("x", "y", "z", "meta")}
+    for k in wc:
+        wc[k][...] = cb[k]
+    wc["offsets"] = cb["offsets"]
+    assert_same(g.compact_to_reference_layout(g.process_host_compact(wc), batch), oracle_batch(O, sensor, batch), "compact write-combined " + sensor)
+    for a in list(wc.values())[:4]:
+        pkg.pinned_free(a)
 
 
 def test_libm_double_switch_and_diag(pkg, O):
