@@ -834,14 +834,17 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const float4* 
 #define SEG_MIN_CTAS 2
 #endif
 constexpr int SEG_CAP = 4096;          // segments a frame may have for the two-CTAs-per-SM build
-constexpr int SEG_CAP_BIG = 8192;      // ... for the one-CTA-per-SM build that takes the frames above it (one synthetic HDL_64E frame in
-                                       // two hundred has more than 4096 segments; without this they fell to the one-warp sweep, which
-                                       // made the sector-mean stage of a whole wave 4.6 times slower)
+constexpr int SEG_CAP_BIG = 12288;     // ... for the one-CTA-per-SM build that takes the frames above it (one synthetic HDL_64E frame in
+                                       // two hundred has more than 4096 segments, noisier scenes have 6 k - 12 k; without this they fell
+                                       // to the one-warp sweep, which made the sector-mean stage of a whole wave 4.6 times slower)
 constexpr int SEG_STRIDE = SEG_CAP_BIG;   // entries per frame of the segment lists in global memory
 constexpr int SEGT = 512;
-__host__ __device__ constexpr int seg_smem_bytes(int cap) { return cap * 4 * 2 + NSECT * 4 + SEGT * 8 + 320 + cap * 2 * 3 + (NSECT + 2) * 2 + 8 + cap * 2; }
+// the big build keeps its bucket positions (s_order) in the dead half of s_endtmp: 14 instead of 16 bytes per segment
+__host__ __device__ constexpr int seg_smem_bytes(int cap) {
+  return cap * 4 * 2 + NSECT * 4 + SEGT * 8 + 320 + cap * 2 * (cap == SEG_CAP ? 3 : 2) + (NSECT + 2) * 2 + 8 + cap * 2;
+}
 constexpr int SMEM_SEG = seg_smem_bytes(SEG_CAP);          // 92,464 B (two CTAs per SM)
-constexpr int SMEM_SEG_BIG = seg_smem_bytes(SEG_CAP_BIG);  // 158,000 B
+constexpr int SMEM_SEG_BIG = seg_smem_bytes(SEG_CAP_BIG);  // 198,960 B
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #ifndef FOLD_STEP_N
 #define FOLD_STEP_N 32   // 16 is 10 % slower
@@ -867,8 +870,12 @@ __global__ void __launch_bounds__(SEGT, CAP == SEG_CAP ? SEG_MIN_CTAS : 1) k_seg
   uint32_t* s_misc = s_warp + 32;                               // [16]
   uint16_t* s_len = reinterpret_cast<uint16_t*>(s_misc + 16);   // [CAP] last participating slot - first slot
   uint16_t* s_key = s_len + CAP;                            // [CAP] sector of the segment
-  uint16_t* s_order = s_key + CAP;                          // [CAP] segment ids bucketed by sector, slot order kept
-  uint16_t* s_kbase = s_order + CAP;                        // [NSECT + 2] bucket base, later bucket end
+  // [CAP] segment ids bucketed by sector, slot order kept.  The big build places it behind the first NSECT words of s_endtmp,
+  // which is dead once the segment lengths exist (those NSECT words later hold s_span)
+  constexpr bool ALIAS = CAP != SEG_CAP;
+  static_assert(!ALIAS || CAP * 4 >= NSECT * 4 + CAP * 2, "s_order does not fit behind s_span inside s_endtmp");
+  uint16_t* s_order = ALIAS ? reinterpret_cast<uint16_t*>(s_endtmp + NSECT) : s_key + CAP;
+  uint16_t* s_kbase = ALIAS ? s_key + CAP : s_order + CAP;  // [NSECT + 2] bucket base, later bucket end
   // [CAP / 2] participating slots (ground, z != 0) of every segment, two 16-bit counts per word (smem atomics are 32-bit)
   uint32_t* s_np = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(s_kbase + NSECT + 2 + 3) & ~(uintptr_t)7);
 
