@@ -234,6 +234,23 @@ def main():
     print(json.dumps({"what": "host path HDL_64E (e2e): SoA staging / packed 26-byte records de-interleaved on the GPU / SoA + bird-view map",
                       "frames_per_s": {"soa": Fe / t_soa, "packed": Fe / t_pack, "soa_with_bvm": Fe / t_bvm},
                       "h2d_bytes_per_frame": {"soa": 22 * n_total / Fe, "packed": 26 * n_total / Fe}}), flush=True)
+    # ---- the single-frame form: bevgen_submit / bevgen_collect with 8 frames in flight ---------------
+    g8 = pkg.BevGen(sensor, device=0, max_frames_per_batch=8)
+    fl = [{k: hb[k][int(hb["offsets"][i]):int(hb["offsets"][i + 1])] for k in FIELDS} for i in range(32)]
+    nfr = 256
+    for i in range(8):
+        g8.submit(i, fl[i % 32])
+    t0 = time.perf_counter()
+    for i in range(nfr):
+        g8.collect(i)
+        if i + 8 < nfr + 8:
+            g8.submit(i + 8, fl[(i + 8) % 32])
+    dt = time.perf_counter() - t0
+    for i in range(nfr, nfr + 8):
+        g8.collect(i)
+    g8.close()
+    print(json.dumps({"what": "bevgen_submit / bevgen_collect, one HDL_64E frame per call, 8 in flight, pageable host arrays, Python caller (collect allocates its outputs)",
+                      "frames_per_s": nfr / dt}), flush=True)
     # ---- 8(f)-2: projection step, host arrays in/out ---------------------------------------------------------------------
     rng = np.random.default_rng(3)
     n = 8 * 65536
