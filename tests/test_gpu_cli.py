@@ -260,6 +260,36 @@ def test_cli_baseline_100_keyframes_hdl64e(tmp_path, pkg, synth, O):
             assert line in r.stdout, line
 
 
+def test_cli_pose_file_with_a_short_row(tmp_path, pkg, synth, O):
+    """readKeyframePose stops at the first row that does not split into 16 tokens (BatchMultiBevGen.cpp:415-419): the label
+    stage then sees only the rows before it, while every keyframe is still converted.  keyframe_label.csv must equal what
+    the reference's own main() writes for the same folder."""
+    import importlib, shutil
+    pcd = importlib.import_module("pcpt_b200.pcd")
+    sensor, n = "HDL_32E", 9
+    root, _ = _baseline_folder(str(tmp_path), synth, pcd, sensor, n, first=70)
+    pose = os.path.join(root, "keyframe_pose.csv")
+    lines = open(pose).read().splitlines()
+    lines[6] = ",".join(lines[6].split(",")[:15])                  # row 6 has 15 tokens: rows 0..5 are read, the rest ignored
+    open(pose, "w").write("\n".join(lines) + "\n")
+    r = subprocess.run([pkg.CLI_PATH, root, sensor], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Size of entry_token is: 15, while expecting 16." in r.stderr
+    assert "Finish reading all keyframe pose, total 6 entries." in r.stdout
+    lab = open(os.path.join(root, "keyframe_label.csv")).read()
+    assert len(lab.splitlines()) == 6
+    assert len(os.listdir(os.path.join(root, "output_multi_bev", "binary"))) == n
+    if O.ref_bevgen_lib() is None:
+        pytest.skip("oracle/_ref not present on this box")
+    ref_root = str(tmp_path / "ref")
+    os.makedirs(ref_root)
+    shutil.copytree(os.path.join(root, "keyframe_point_cloud"), os.path.join(ref_root, "keyframe_point_cloud"))
+    shutil.copy(pose, ref_root)
+    rc, out, err = O.ref_main(ref_root, sensor)
+    assert rc == 0, err[-2000:]
+    assert open(os.path.join(ref_root, "keyframe_label.csv")).read() == lab
+
+
 def test_cli_multi_gpu_outputs_identical(tmp_path, pkg, synth):
     """the same folder sharded over 2 GPUs gives byte-identical outputs to the 1-GPU run."""
     import importlib, shutil
