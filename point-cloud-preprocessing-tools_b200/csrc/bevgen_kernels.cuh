@@ -6,11 +6,13 @@
 // (CMakeLists.txt:10): every float op there is an individually rounded IEEE op.
 //
 // HBM layout per frame f of a batch (S = N_SCAN * Horizon_SCAN slots):
-//   owner [f][S]  u32   1 + winning input index per slot (0 = empty)        — output
+//   winner_bits   1 bit per INPUT point: the point is the last writer of its slot (see bevgen.h)        — output
 //   rec   [f][S]  f32x4 ordered cloud: x, y, z, w = {label:16 | I==-1:1 | owned:1} — scratch, written once
-//   gmask [f][ceil(S/32)] u32  ground_mat == 1 after loop 1, bit (s & 31) of word (s >> 5) for slot s  — scratch
-//   gz    [f][S]  f32   z of those slots (0 elsewhere)                       — scratch
-//   cnt   [f][3750] u32 zero-height ground slots per sector (the others are counted by the fold);  avg [f][3750] f32 sector mean heights — scratch
+//   gsum  [f][G+1][ceil(H/32)] uint4  per (band row, 32-column group): participating lanes, sector-change lanes, first | last
+//                 sector, ground_mat == 1 bits of the group (k_ground_mark)                             — scratch
+//   gmask [f][ceil(S/32)] u32  the same ground bits in slot order, bit (s & 31) of word (s >> 5) (k_seg_build)  — scratch
+//   gz    [f][S]  f32   z of the ground slots (0 elsewhere)                  — scratch
+//   cnt   [f][3750] u32 ground slots per sector (zero heights: k_ground_mark, the others: k_seg_build);  avg [f][3750] f32 sector mean heights — scratch
 //   label [f][S] i16, single [f][224*224] u8, multi [f][24][224*224] u8      — outputs
 #pragma once
 #include <cuda_runtime.h>
@@ -749,7 +751,7 @@ __global__ void __launch_bounds__(32) k_sector_mean(SensorDev sp, const float4* 
                                                      const uint32_t* __restrict__ slow_flag) {
   extern __shared__ float ssum[];                 // [NSECT] running sums of this frame, then [NSECT] counts of non-zero heights
   uint32_t* scnt = reinterpret_cast<uint32_t*>(ssum + NSECT);
-  if (slow_flag && !slow_flag[blockIdx.x]) return; // the segment form (k_sector_mean_seg) already did this frame
+  if (slow_flag && !slow_flag[blockIdx.x]) return; // the segment form (k_seg_build + k_seg_fold) already did this frame
   __shared__ __align__(16) float zb[2][32];       // the current step's 32 heights (double-buffered)
   const int f = blockIdx.x, lane = threadIdx.x;
   for (int i = lane; i < NSECT; i += 32) { ssum[i] = 0.0f; scnt[i] = 0u; }
@@ -1098,14 +1100,15 @@ __global__ void __launch_bounds__(SEGT, CAP == SEG_CAP ? SEG_MIN_CTAS : 1) k_seg
 }
 
 // k_seg_fold — one LANE per active sector runs the sector's serial chain sum = fl(sum + z) (:198) over its segments in
-// slot order, straight from gz.  The lane walks a flat sequence of windows of FOLD_STEP heights (16-byte aligned, padded
-// with +0, which never changes the sum), so the 32 chains of a warp stay in lockstep whatever their segment boundaries
-// are.  Then the IEEE divide (:210).
+// slot order, straight from gz.  The lane walks a flat sequence of windows of FOLD_STEP heights (32-byte aligned; heights
+// outside the segment are skipped by a window mask), so the 32 chains of a warp stay in lockstep whatever their segment
+// boundaries are.  Then the IEEE divide (:210).
 //
-// The chain is latency bound (round-1 ncu: 12 % warps active, one window = 8 dependent-free 128-bit loads that all miss
-// L1, then 32 dependent adds), so the address stream is decoupled from the adds: a position `pa` runs FOLD_DIST windows
-// ahead of the chain and only issues prefetches (the walk over segment descriptors does not depend on the sums); the
-// chain's own loads are issued one window ahead into a second register buffer and find their lines in L1.
+// The chain is latency bound (ncu: 15 % warps active; a frame's longest chain alone is ~165 steps of one warp), so the
+// address stream is decoupled from the adds: a position `pa` runs FOLD_DIST windows ahead of the chain and only issues
+// prefetches (the walk over segment descriptors does not depend on the sums), the chain's own four 256-bit loads per window
+// find their lines in L1, and every position holds the descriptor of its NEXT segment from the moment it enters the current
+// one.  One window buffer (61 registers; the double-buffered form needed 122 and kept the other wave's kernels off the SM).
 // grid (F, FOLD_PASSES / wpb), block (32, wpb): warp p of a frame owns the active sectors p*32 + lane (+ 32*FOLD_PASSES ...);
 // the list is sorted by cost, so a frame's pass 0 holds its 32 longest chains.
 #ifndef FOLD_DIST_N
