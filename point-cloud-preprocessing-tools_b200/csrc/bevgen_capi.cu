@@ -229,8 +229,10 @@ static int create_fill(bevgen_ctx* c, int device, const bevgen_params* p, int ma
   CK(cudaFuncSetAttribute(k_seg_build<SEG_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SEG));
   CK(cudaFuncSetAttribute(k_seg_build<SEG_CAP_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SEG_BIG));
   CK(cudaFuncSetAttribute(k_float_bev, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BVM));
-  CK(cudaFuncSetAttribute(k_order_winners<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // function-wide: the largest any context may ask for
-  CK(cudaFuncSetAttribute(k_order_winners<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_order_winners<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // function-wide: the largest any context may ask for
+  CK(cudaFuncSetAttribute(k_order_winners<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_order_winners<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_order_winners<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_seg_build<SEG_CAP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_seg_build<SEG_CAP_BIG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   if (const char* e = getenv("BEVGEN_SEG_CAP")) c->seg_cap = std::max(0, std::min(SEG_CAP, atoi(e)));
@@ -341,12 +343,14 @@ static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
     dim3 g((std::max<int>(w.max_n, (int)S) + SCAT_T - 1) / SCAT_T, w.nf);
     if (w.compact) {
       const uint16_t* meta = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint32_t*>(w.in.inten) - w.base);
-      k_order_winners<true><<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, meta, nullptr, occ, cont, cpre, w.sc->cwin, w.qbase, w.sc->cpt);
+      if (ord_needs_swizzle(sp.H)) k_order_winners<true, true><<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, meta, nullptr, occ, cont, cpre, w.sc->cwin, w.qbase, w.sc->cpt);
+      else k_order_winners<true, false><<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, meta, nullptr, occ, cont, cpre, w.sc->cwin, w.qbase, w.sc->cpt);
       mark(2);
       k_order_scatter<true><<<g, SCAT_T, 0, st>>>(sp, c->xf, w.offs_d, w.frame0, c->cw_stride, x, y, z, it, nullptr, nullptr, nullptr, occ, cont, cpre, w.sc->cwin,
                                                  w.sc->rec, w.out.wbits, w.qbase, w.sc->cpt);
     } else {
-      k_order_winners<false><<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, row, col, occ, cont, cpre, w.sc->cwin, w.qbase, w.sc->cpt);
+      if (ord_needs_swizzle(sp.H)) k_order_winners<false, true><<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, row, col, occ, cont, cpre, w.sc->cwin, w.qbase, w.sc->cpt);
+      else k_order_winners<false, false><<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, row, col, occ, cont, cpre, w.sc->cwin, w.qbase, w.sc->cpt);
       mark(2);
       k_order_scatter<false><<<g, SCAT_T, 0, st>>>(sp, c->xf, w.offs_d, w.frame0, c->cw_stride, x, y, z, it, row, col, lab, occ, cont, cpre, w.sc->cwin,
                                                   w.sc->rec, w.out.wbits, w.qbase, w.sc->cpt);

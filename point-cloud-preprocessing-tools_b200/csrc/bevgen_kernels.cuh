@@ -439,7 +439,16 @@ __global__ void __launch_bounds__(256) k_winner_bits(SensorDev sp, const int64_t
 #define ORD_THREADS 512   // measured: 0.275 / 0.251 / 0.261 us per frame for 256 / 512 / 1024 threads
 #endif
 constexpr int ORD_T = ORD_THREADS;
-__host__ __device__ inline size_t ord_smem_bytes(int S) { return (((size_t)S + 31) / 32) * 4 * 2 + 256; }
+// occupancy + contention words, each padded to a multiple of 32 words (the swizzle below permutes inside 32-word blocks)
+__host__ __device__ inline size_t ord_smem_bytes(int S) { return ((((size_t)S + 31) / 32 + 31) & ~(size_t)31) * 4 * 2 + 256; }
+// Shared-memory word of slot-word w.  Scans in sensor order (MulRan: row = k % 64, so the 32 lanes of a warp hold 32 rows of ONE
+// column) would hit words w = row * (H / 32) + const: with H = 1024 all in one bank, a 32-way conflict on every atomic (OS1_64:
+// 0.25 us per frame for 65 k points, as much as HDL_64E's two scans of 118 k).  XOR-ing the bank bits with the next five
+// bits spreads such a column over the banks and leaves scattered input as it was.
+// Only rows that are a multiple of 4 words long need it (H a multiple of 128; OS1_64: 1024); elsewhere consecutive rows already
+// start in different banks and the kernel is instantiated without the two extra instructions per point (ord_needs_swizzle).
+template <bool SWZ> __device__ __forceinline__ unsigned ord_swz(unsigned w) { return SWZ ? (w ^ ((w >> 5) & 31u)) : w; }
+__host__ __device__ inline bool ord_needs_swizzle(int H) { return (H & 127) == 0; }   // rows of a multiple of 4 words: 8-way conflicts or worse
 
 // 8 consecutive u16 as one 128-bit load: block v8 of the 16-byte aligned pointer.
 __device__ __forceinline__ uint4 ld8_u16(const uint16_t* aligned_base, int v8) {
@@ -448,7 +457,7 @@ __device__ __forceinline__ uint4 ld8_u16(const uint16_t* aligned_base, int v8) {
 
 // PACKED (bevgen_process_host_compact): `row` points at the u32 meta array instead (slot | flags, see bevgen.h), `col` is unused.
 constexpr unsigned META_SLOT = 0x00FFFFFFu, META_NEG1 = 1u << 24, META_LABELED = 1u << 25;
-template <bool PACKED>
+template <bool PACKED, bool SWZ>
 __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int64_t* __restrict__ offs, int cw_stride,
                                                           const uint16_t* __restrict__ row, const uint16_t* __restrict__ col,
                                                           uint32_t* __restrict__ occ_bits, uint32_t* __restrict__ cont_bits,
@@ -457,8 +466,9 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
   extern __shared__ __align__(16) unsigned char ord_smem[];
   const int W = (sp.S + 31) >> 5;
   uint32_t* occ = reinterpret_cast<uint32_t*>(ord_smem);           // [W]
-  uint32_t* cont = occ + W;                                        // [W]
-  uint32_t* misc = cont + W;                                       // [64] scan carries
+  const int WP = (W + 31) & ~31;                                   // padded: ord_swz stays inside a 32-word block
+  uint32_t* cont = occ + WP;                                       // [WP]
+  uint32_t* misc = cont + WP;                                      // [64] scan carries
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t o = offs[f];
   const int n = (int)(offs[f + 1] - o);
@@ -470,13 +480,14 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
   const uint16_t* Ra = R - mis; const uint16_t* Ca = C - mis;
   const int n8 = (n + mis + 7) >> 3;                                // 16-byte blocks that hold the frame's row/col
 
-  for (int i = tid; i < W; i += ORD_T) { occ[i] = 0u; cont[i] = 0u; }
+  for (int i = tid; i < WP; i += ORD_T) { occ[i] = 0u; cont[i] = 0u; }
   __syncthreads();
   // ---- scan 1: occupancy + contention bits ----
   auto visit1 = [&](unsigned slot, bool ok) {
     if (ok) {                                                       // :106-109
       const unsigned bit = 1u << (slot & 31);
-      if (atomicOr(&occ[slot >> 5], bit) & bit) atomicOr(&cont[slot >> 5], bit);
+      const unsigned w = ord_swz<SWZ>(slot >> 5);
+      if (atomicOr(&occ[w], bit) & bit) atomicOr(&cont[w], bit);
     }
   };
   // cpt_bits: one bit per INPUT point (bit index = o + i - qbase, qbase = 32-aligned first point of the wave), set iff the
@@ -485,9 +496,10 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
   const int64_t q0 = o - qbase;
   auto visit2 = [&](unsigned slot, bool ok, int i) {
     if (ok) {
-      const unsigned bit = 1u << (slot & 31), cw = cont[slot >> 5];
+      const unsigned w = ord_swz<SWZ>(slot >> 5);
+      const unsigned bit = 1u << (slot & 31), cw = cont[w];
       if (cw & bit) {
-        atomicMax(&cwin[(size_t)f * cw_stride + occ[slot >> 5] + __popc(cw & (bit - 1u))], (uint32_t)i + 1u);
+        atomicMax(&cwin[(size_t)f * cw_stride + occ[w] + __popc(cw & (bit - 1u))], (uint32_t)i + 1u);
         const int64_t q = q0 + i;
         atomicOr(&cpt_bits[q >> 5], 1u << (q & 31));
       }
@@ -533,12 +545,12 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
   scan([&](unsigned slot, bool ok, int) { visit1(slot, ok); });
   __syncthreads();
   // ---- occupancy / contention bits out; dense ids of the contended slots (prefix popcount, kept in `occ`) ----
-  for (int w = tid; w < W; w += ORD_T) { occ_bits[(size_t)f * W + w] = occ[w]; cont_bits[(size_t)f * W + w] = cont[w]; }
+  for (int w = tid; w < W; w += ORD_T) { occ_bits[(size_t)f * W + w] = occ[ord_swz<SWZ>(w)]; cont_bits[(size_t)f * W + w] = cont[ord_swz<SWZ>(w)]; }
   {
     const int wpt = (W + ORD_T - 1) / ORD_T;                        // consecutive words per thread
     const int w0 = min(tid * wpt, W), w1 = min(w0 + wpt, W);
     unsigned loc = 0;
-    for (int w = w0; w < w1; w++) loc += __popc(cont[w]);
+    for (int w = w0; w < w1; w++) loc += __popc(cont[ord_swz<SWZ>(w)]);
     unsigned incl = loc;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
@@ -547,7 +559,7 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
     unsigned wbase = 0, total = 0;
     for (int w = 0; w < ORD_T / 32; w++) { const unsigned t = misc[w]; if (w < wid) wbase += t; total += t; }
     unsigned run = wbase + incl - loc;
-    for (int w = w0; w < w1; w++) { occ[w] = run; cont_pre[(size_t)f * W + w] = run; run += __popc(cont[w]); }
+    for (int w = w0; w < w1; w++) { occ[ord_swz<SWZ>(w)] = run; cont_pre[(size_t)f * W + w] = run; run += __popc(cont[ord_swz<SWZ>(w)]); }
     // the serial loop's last writer (:102-116) = largest input index: one global atomicMax per contended point
     for (unsigned j = tid; j < total; j += ORD_T) cwin[(size_t)f * cw_stride + j] = 0u;
     if (total == 0) return;                                         // uniform
