@@ -1,3 +1,5 @@
+"""Device-path throughput on frames that are not the benchmark's: `noisy` (default) = the scene generator of tests/gpu_fuzz.py,
+`kitti` = the KITTI extractor's conventions.  Checks a sample of the outputs against the oracle as well (a tool run, it loads the oracle)."""
 import sys, importlib.util, numpy as np
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import bench, torch
@@ -5,7 +7,12 @@ from _load_pkg import load_pkg, load_synth, load_oracle
 spec = importlib.util.spec_from_file_location("gpu_fuzz", "tests/gpu_fuzz.py"); m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
 pkg, O = load_pkg(), load_oracle()
 sp = O.sensor("HDL_64E")
-frames = [m.scene_frame(np.random.default_rng(100 + s), sp) for s in range(32)]
+kind = sys.argv[1] if len(sys.argv) > 1 else "noisy"
+if kind == "kitti":      # KITTI-extractor convention: every valid point has intensity -1, every empty slot is an all-zero record at row = col = 0
+    synth = load_synth()
+    frames = [synth.make_frame("HDL_64E", 100 + s, kitti_quirk=True) for s in range(32)]
+else:
+    frames = [m.scene_frame(np.random.default_rng(100 + s), sp) for s in range(32)]
 offs = np.zeros(33, np.int64); offs[1:] = np.cumsum([len(f["x"]) for f in frames])
 distinct = {k: np.concatenate([f[k] for f in frames]) for k in bench.FIELDS}; distinct["offsets"] = offs
 F = 2220
@@ -24,4 +31,4 @@ e1.record(stream); g.sync(); torch.cuda.synchronize()
 g.set_profiling(True); g.process_device(F, batch["offsets"], pin, pout); g.sync(); st = g.stage_ms(); g.set_profiling(False)
 ref = O.frames(sp, offs, *[distinct[k] for k in bench.FIELDS], n_threads=16)
 ok = all(np.array_equal(dout["label"][i].cpu().numpy(), ref["label"][i % 32]) and np.array_equal(dout["multi"][i].cpu().numpy().reshape(24, 224, 224), ref["multi"][i % 32]) for i in list(range(40)) + [F - 1])
-print("noisy scene frames (1.2 k - 12 k segments, median 6.3 k): %.0f frames/s, %s, parity %s" % (F * 4 / (e0.elapsed_time(e1) * 1e-3), {k: round(v[0] / F * 1e3, 3) for k, v in st.items() if v[1] > 0}, ok))
+print(("KITTI-convention frames (all empties on slot 0)" if kind == "kitti" else "noisy scene frames (1.2 k - 12 k segments, median 6.3 k)") + ": %.0f frames/s, %s, parity %s" % (F * 4 / (e0.elapsed_time(e1) * 1e-3), {k: round(v[0] / F * 1e3, 3) for k, v in st.items() if v[1] > 0}, ok))
