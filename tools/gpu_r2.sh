@@ -31,10 +31,10 @@ if has bench; then
 fi
 if has san; then
   # compute-sanitizer over the small-sensor parity tests (memcheck: out-of-bounds / misaligned / leaks; racecheck: shared-memory hazards)
-  SEL='(synthetic_frames_bit_exact and HDL_32E) or (random_unstructured and HDL_32E) or (compact_host_path and HDL_32E) or (packed_records and pcd26) or top_flatten or labels_and_major or sweep_fallback or boundaries'
+  SEL='(synthetic_frames_bit_exact and HDL_32E) or (random_unstructured and HDL_32E) or (compact_host_path and HDL_32E) or (packed_records and pcd26) or top_flatten or labels_and_major or sweep_fallback or boundaries or above_the_first_segment or cloud_manip_contention'
   timeout 1500 compute-sanitizer --tool memcheck --leak-check full --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "$SEL" > gpurun_out/san_memcheck.log 2>&1; echo "memcheck exit $?" >> gpurun_out/san_memcheck.log
   grep -E "ERROR SUMMARY|LEAK SUMMARY|passed|failed|exit" gpurun_out/san_memcheck.log | tail -6
-  timeout 1500 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "(synthetic_frames_bit_exact and HDL_32E) or (compact_host_path and HDL_32E) or top_flatten" > gpurun_out/san_racecheck.log 2>&1; echo "racecheck exit $?" >> gpurun_out/san_racecheck.log
+  timeout 1500 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "(synthetic_frames_bit_exact and HDL_32E) or (compact_host_path and HDL_32E) or top_flatten or above_the_first_segment or cloud_manip_contention" > gpurun_out/san_racecheck.log 2>&1; echo "racecheck exit $?" >> gpurun_out/san_racecheck.log
   grep -E "RACECHECK SUMMARY|hazard|passed|failed|exit" gpurun_out/san_racecheck.log | tail -8
 fi
 if has ncu; then
