@@ -340,7 +340,7 @@ static int wave_front(bevgen_ctx* c, cudaStream_t st, const WaveArgs& w, bool pr
   if (fused_order(sp)) {
     const size_t W = (S + 31) / 32;
     uint32_t *occ = w.sc->occ, *cont = occ + (size_t)w.sc->frames * W, *cpre = cont + (size_t)w.sc->frames * W;
-    dim3 g((std::max<int>(w.max_n, (int)S) + SCAT_T - 1) / SCAT_T, w.nf);
+    dim3 g((std::max<int>(w.max_n, (int)S) + SCAT_T * SCAT_PPT - 1) / (SCAT_T * SCAT_PPT), w.nf);
     if (w.compact) {
       const uint16_t* meta = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint32_t*>(w.in.inten) - w.base);
       if (ord_needs_swizzle(sp.H)) k_order_winners<true, true><<<w.nf, ORD_T, ord_smem_bytes(sp.S), st>>>(sp, w.offs_d, c->cw_stride, meta, nullptr, occ, cont, cpre, w.sc->cwin, w.qbase, w.sc->cpt);
