@@ -38,3 +38,28 @@ def test_png_and_csv_encoders(tmp_path):
     m = np.isfinite(f)                                              # OpenCV's own float -> u8 conversion agrees where it is defined
     cvt = cv2.add(np.where(m, f, 0).astype(np.float32), 0, dtype=cv2.CV_8U)
     assert np.array_equal(png[m], cvt[m])
+
+
+def test_run_length_deflate_round_trips(tmp_path):
+    """imgio::deflate_rle (the PNG layers' encoder): any inflater must give the input back.  Run lengths around every
+    boundary of the length codes (3..10, 11/13/.., 227, 257, 258) and of the 258-byte match limit (259, 260, 261, 516, 517),
+    mixed literals, an empty input, an all-zero layer, noise."""
+    import zlib
+    exe = str(tmp_path / "deflate_probe")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "helpers", "deflate_probe.cpp"), "-lz"])
+    rng = np.random.default_rng(9)
+    cases = [b"", b"\x00", b"ab", bytes(224 * 225), rng.integers(0, 256, 5000).astype(np.uint8).tobytes(), bytes([255]) * 70000]
+    runs = bytearray()
+    for n in list(range(1, 40)) + [66, 67, 130, 131, 226, 227, 228, 256, 257, 258, 259, 260, 261, 262, 515, 516, 517, 518, 774, 1000]:
+        runs += bytes([n % 251]) * n + bytes([(n * 7 + 1) % 256])           # a run, then a different byte
+    cases.append(bytes(runs))
+    sparse = np.zeros(224 * 225, np.uint8); sparse[rng.integers(0, sparse.size, 900)] = 255
+    cases.append(sparse.tobytes())
+    for i, data in enumerate(cases):
+        src, dst = tmp_path / ("in%d" % i), tmp_path / ("out%d" % i)
+        src.write_bytes(data)
+        subprocess.check_call([exe, str(src), str(dst)])
+        z = dst.read_bytes()
+        assert zlib.decompress(z) == data, "case %d (%d bytes)" % (i, len(data))
+        if len(data) >= 50000 and data.count(0) + data.count(255) == len(data) and len(set(data)) == 1:
+            assert len(z) < len(data) // 100          # a constant layer costs 13 bits per 258 bytes
