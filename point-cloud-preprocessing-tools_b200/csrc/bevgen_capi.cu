@@ -473,9 +473,16 @@ static int tmp_reserve(bevgen_ctx* c, size_t bytes) {
 }
 
 // ---- device-resident path -------------------------------------------------------------------------------------
+// Every array of the two structs is required (a NULL would only surface as a fault inside a kernel); bvm alone is optional,
+// and a batch without a single point may come with NULL point arrays.
+static bool null_arrays(const bevgen_points* in, const bevgen_outputs* out, bool any_points = true) {
+  if (in && any_points && (!in->x || !in->y || !in->z || !in->intensity || !in->row || !in->col || !in->label)) return true;
+  return !out->label || !out->winner_bits || !out->single_bev || !out->multi_bev;
+}
 extern "C" int bevgen_process_device(bevgen_ctx* c, int nf, const int64_t* offsets, const bevgen_points* in, const bevgen_outputs* out) {
   if (!c || !offsets || !in || !out) return fail("bevgen_process_device: null argument");
   if (nf <= 0) return 0;
+  if (null_arrays(in, out, offsets[nf] > offsets[0])) return fail("bevgen_process_device: null array (only bevgen_outputs.bvm is optional)");
   CK(cudaSetDevice(c->device));
   int max_n_all = 0;
   if (upload_offsets(c, nf, offsets, c->s_comp, &max_n_all)) return -1;
@@ -579,7 +586,8 @@ static int process_host_impl(bevgen_ctx* c, int nf, const int64_t* offsets, cons
     for (int f = f0; f < f0 + n; f++) max_n = std::max<int64_t>(max_n, offsets[f + 1] - offsets[f]);
     // inputs of this lane may be overwritten once the kernels of its previous wave are done
     if (l.used) CK(cudaStreamWaitEvent(c->s_copy, l.ev_comp, 0));
-    nvtxRangePushA("bevgen H2D enqueue");
+    {
+    NvtxRange nv_h2d("bevgen H2D enqueue");   // scoped: an early CK return may not leave the range open
     if (records) {
       CK(cudaMemcpyAsync(l.raw, records + (size_t)base * lay->stride, np * lay->stride, cudaMemcpyHostToDevice, c->s_copy));
     } else if (compact) {   // 16 bytes per point: x, y, z + (slot | flags); l.in.inten holds the meta words
@@ -596,7 +604,7 @@ static int process_host_impl(bevgen_ctx* c, int nf, const int64_t* offsets, cons
       CK(cudaMemcpyAsync(l.in.col, in->col + base, np * 2, cudaMemcpyHostToDevice, c->s_copy));
       CK(cudaMemcpyAsync(l.in.label, in->label + base, np * 2, cudaMemcpyHostToDevice, c->s_copy));
     }
-    nvtxRangePop();
+    }
     CK(cudaEventRecord(l.ev_h2d, c->s_copy));
     CK(cudaStreamWaitEvent(c->s_comp, l.ev_h2d, 0));
     if (l.used) CK(cudaStreamWaitEvent(c->s_comp, l.ev_d2h, 0));   // outputs of the previous wave have left
@@ -616,7 +624,8 @@ static int process_host_impl(bevgen_ctx* c, int nf, const int64_t* offsets, cons
     if (run_wave(c, c->s_comp, l.sc, n, c->offs_d + f0, base, max_n, l.in, lo, false, f0, offsets[f0], offsets[f0 + n], compact)) return -1;
     CK(cudaEventRecord(l.ev_comp, c->s_comp));
     CK(cudaStreamWaitEvent(c->s_d2h, l.ev_comp, 0));
-    nvtxRangePushA("bevgen D2H enqueue");
+    {
+    NvtxRange nv_d2h("bevgen D2H enqueue");
     if (compact) {   // ground bits (in the lane's label buffer), winner bits, single, the three occupancy bit planes
       const size_t GW = (S + 31) / 32;
       CK(cudaMemcpyAsync(cout->ground_bits + (size_t)f0 * GW, l.out.label, (size_t)n * GW * 4, cudaMemcpyDeviceToHost, c->s_d2h));
@@ -630,7 +639,7 @@ static int process_host_impl(bevgen_ctx* c, int nf, const int64_t* offsets, cons
       CK(cudaMemcpyAsync(out->multi_bev + (size_t)f0 * LAYERS * CELLS, l.out.multi, (size_t)n * LAYERS * CELLS, cudaMemcpyDeviceToHost, c->s_d2h));
       if (out->bvm) CK(cudaMemcpyAsync(out->bvm + (size_t)f0 * BVM_CELLS, l.bvm, (size_t)n * BVM_CELLS * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
     }
-    nvtxRangePop();
+    }
     CK(cudaEventRecord(l.ev_d2h, c->s_d2h));
     l.used = true;
   }
@@ -643,6 +652,7 @@ static int process_host_impl(bevgen_ctx* c, int nf, const int64_t* offsets, cons
 extern "C" int bevgen_process_host(bevgen_ctx* c, int nf, const int64_t* offsets, const bevgen_points* in, const bevgen_outputs* out) {
   if (!c || !offsets || !in || !out) return fail("bevgen_process_host: null argument");
   if (nf <= 0) return 0;
+  if (null_arrays(in, out, offsets[nf] > offsets[0])) return fail("bevgen_process_host: null array (only bevgen_outputs.bvm is optional)");
   return process_host_impl(c, nf, offsets, in, nullptr, nullptr, out);
 }
 
@@ -668,6 +678,7 @@ extern "C" int bevgen_process_packed_host(bevgen_ctx* c, int nf, const int64_t* 
                                           const bevgen_record_layout* layout, const bevgen_outputs* out) {
   if (!c || !offsets || !records || !layout || !out) return fail("bevgen_process_packed_host: null argument");
   if (nf <= 0) return 0;
+  if (null_arrays(nullptr, out)) return fail("bevgen_process_packed_host: null array (only bevgen_outputs.bvm is optional)");
   RecLayout L;
   L.stride = layout->stride;
   const int offs[7] = {layout->off_x, layout->off_y, layout->off_z, layout->off_intensity, layout->off_row, layout->off_col, layout->off_label};
@@ -714,6 +725,7 @@ extern "C" int bevgen_submit(bevgen_ctx* c, int frame_id, int n_in, const float*
                              const float* intensity, const uint16_t* row, const uint16_t* col, const int16_t* label) {
   if (!c) return fail("bevgen_submit: null ctx");
   if (n_in < 0 || n_in > c->max_pts) return fail("bevgen_submit: n_in exceeds max_points_per_frame");
+  if (n_in > 0 && (!x || !y || !z || !intensity || !row || !col || !label)) return fail("bevgen_submit: null point array");
   CK(cudaSetDevice(c->device));
   for (auto& t : c->slots) { if (t.busy && t.frame_id == frame_id) return fail("bevgen_submit: frame_id already in flight"); }
   Slot* s = free_ring_slot(c);
@@ -723,8 +735,10 @@ extern "C" int bevgen_submit(bevgen_ctx* c, int frame_id, int n_in, const float*
   char* p = s->pin_in;
   float* px = (float*)p; float* py = px + n; float* pz = py + n; float* pi = pz + n;
   uint16_t* pr = (uint16_t*)(pi + n); uint16_t* pc = pr + n; int16_t* pl = (int16_t*)(pc + n);
-  memcpy(px, x, n * 4); memcpy(py, y, n * 4); memcpy(pz, z, n * 4); memcpy(pi, intensity, n * 4);
-  memcpy(pr, row, n * 2); memcpy(pc, col, n * 2); memcpy(pl, label, n * 2);
+  if (n) {   // an empty frame may come with NULL arrays
+    memcpy(px, x, n * 4); memcpy(py, y, n * 4); memcpy(pz, z, n * 4); memcpy(pi, intensity, n * 4);
+    memcpy(pr, row, n * 2); memcpy(pc, col, n * 2); memcpy(pl, label, n * 2);
+  }
   int64_t* po = (int64_t*)(s->pin_out);   // offsets live at the head of pin_out until the kernels ran
   po[0] = 0; po[1] = n_in;
   CK(cudaMemcpyAsync(s->offs_d, po, 16, cudaMemcpyHostToDevice, s->st));

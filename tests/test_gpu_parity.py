@@ -561,3 +561,37 @@ def test_cloud_manip_2m_points_device_resident(gens, O):
     bi = np.full((201, 201), 3.0, np.float32)
     rc = L.bevgen_cloud_manip(g._ctx, C.c_int64(0), rt.ctypes.data_as(C.c_void_p), None, None, None, None, None, None, bi.ctypes.data_as(C.c_void_p), None)
     assert rc == 0 and not bi.any()
+
+
+def test_null_arrays_are_refused_not_launched(pkg, synth):
+    """A NULL point / output array must come back as an error from the C-ABI instead of reaching a kernel (only
+    bevgen_outputs.bvm is optional); an empty frame may be submitted with NULL arrays; the context stays usable."""
+    import ctypes as C
+    sensor = "HDL_32E"
+    batch = synth.make_batch(sensor, 2, first=3)
+    g = pkg.BevGen(sensor, device=0, max_frames_per_batch=2)
+    L = pkg.lib()
+    try:
+        offs = np.ascontiguousarray(batch["offsets"], np.int64)
+        out = g.alloc_outputs(2, n_total=int(offs[-1]))
+        arrs = [np.ascontiguousarray(batch[k]) for k in FIELDS]
+        ptrs = [C.c_void_p(a.ctypes.data) for a in arrs]
+        full = pkg.Outputs(*[C.c_void_p(out[k].ctypes.data) for k in ("label", "winner", "single", "multi")], None)
+        for hole in range(7):       # one input array missing
+            pts = pkg.Points(*[None if i == hole else p for i, p in enumerate(ptrs)])
+            assert L.bevgen_process_host(g._ctx, C.c_int(2), C.c_void_p(offs.ctypes.data), C.byref(pts), C.byref(full)) == -1
+            assert b"null array" in L.bevgen_last_error()
+        pts = pkg.Points(*ptrs)
+        for hole in range(4):       # one output array missing
+            o = pkg.Outputs(*[None if i == hole else C.c_void_p(out[k].ctypes.data) for i, k in enumerate(("label", "winner", "single", "multi"))], None)
+            assert L.bevgen_process_host(g._ctx, C.c_int(2), C.c_void_p(offs.ctypes.data), C.byref(pts), C.byref(o)) == -1
+            assert L.bevgen_process_device(g._ctx, C.c_int(2), C.c_void_p(offs.ctypes.data), C.byref(pts), C.byref(o)) == -1
+        assert L.bevgen_submit(g._ctx, C.c_int(0), C.c_int(5), None, None, None, None, None, None, None) == -1
+        assert L.bevgen_submit(g._ctx, C.c_int(0), C.c_int(0), None, None, None, None, None, None, None) == 0   # empty frame
+        lab = np.empty(g.S, np.int16); single = np.empty((224, 224), np.uint8)
+        assert L.bevgen_collect(g._ctx, C.c_int(0), C.c_void_p(lab.ctypes.data), None, C.c_void_p(single.ctypes.data), None) == 0
+        assert not lab.any() and not single.any()
+        good = g.process_host(batch)                                    # and the context still computes
+        assert good["single"].any()
+    finally:
+        g.close()
