@@ -439,6 +439,14 @@ __global__ void __launch_bounds__(256) k_winner_bits(SensorDev sp, const int64_t
 #define ORD_THREADS 512   // measured: 0.275 / 0.251 / 0.261 us per frame for 256 / 512 / 1024 threads
 #endif
 constexpr int ORD_T = ORD_THREADS;
+#ifndef ORD_PREFETCH
+#define ORD_PREFETCH 0   // measured (profiles/r2_notes.md): 0.245 us per frame without, 0.252 with (40 registers, 3 CTAs per SM), 0.262 at 4 CTAs (spills)
+#endif
+#ifdef ORD_MIN_CTAS      // CTAs of 512 threads per SM the register allocation must leave room for (only with ORD_PREFETCH)
+#define ORD_BOUNDS __launch_bounds__(ORD_T, ORD_MIN_CTAS)
+#else
+#define ORD_BOUNDS __launch_bounds__(ORD_T)
+#endif
 // occupancy + contention words, each padded to a multiple of 32 words (the swizzle below permutes inside 32-word blocks)
 __host__ __device__ inline size_t ord_smem_bytes(int S) { return ((((size_t)S + 31) / 32 + 31) & ~(size_t)31) * 4 * 2 + 256; }
 // Shared-memory word of slot-word w.  Scans in sensor order (MulRan: row = k % 64, so the 32 lanes of a warp hold 32 rows of ONE
@@ -450,6 +458,19 @@ __host__ __device__ inline size_t ord_smem_bytes(int S) { return ((((size_t)S + 
 template <bool SWZ> __device__ __forceinline__ unsigned ord_swz(unsigned w) { return SWZ ? (w ^ ((w >> 5) & 31u)) : w; }
 __host__ __device__ inline bool ord_needs_swizzle(int H) { return (H & 127) == 0; }   // rows of a multiple of 4 words: 8-way conflicts or worse
 
+// dst = *p if i < n (dst keeps its value otherwise): a predicated load instead of a branch around it.  volatile: the loads stay
+// in program order, none is dropped; .cs = streaming (read once), .nc = read-only path.
+#define BEVGEN_LD_IF(NAME, CTYPE, CONS, PTXLD)                                                                          \
+  __device__ __forceinline__ void NAME(CTYPE& dst, const void* p, int i, int n) {                                       \
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.s32 q, %2, %3;\n\t@q " PTXLD " %0, [%1];\n\t}" : "+" CONS(dst) : "l"(p), "r"(i), "r"(n)); \
+  }
+BEVGEN_LD_IF(ld_f32_cs_if, float, "f", "ld.global.cs.f32")
+BEVGEN_LD_IF(ld_u32_cs_if, unsigned, "r", "ld.global.cs.u32")
+BEVGEN_LD_IF(ld_u32_nc_if, unsigned, "r", "ld.global.nc.u32")
+BEVGEN_LD_IF(ld_u16_nc_if, unsigned, "r", "ld.global.nc.u16")
+BEVGEN_LD_IF(ld_s16_cs_if, int, "r", "ld.global.cs.s16")
+#undef BEVGEN_LD_IF
+
 // 8 consecutive u16 as one 128-bit load: block v8 of the 16-byte aligned pointer.
 __device__ __forceinline__ uint4 ld8_u16(const uint16_t* aligned_base, int v8) {
   return __ldg(reinterpret_cast<const uint4*>(aligned_base) + v8);
@@ -458,7 +479,7 @@ __device__ __forceinline__ uint4 ld8_u16(const uint16_t* aligned_base, int v8) {
 // PACKED (bevgen_process_host_compact): `row` points at the u32 meta array instead (slot | flags, see bevgen.h), `col` is unused.
 constexpr unsigned META_SLOT = 0x00FFFFFFu, META_NEG1 = 1u << 24, META_LABELED = 1u << 25;
 template <bool PACKED, bool SWZ>
-__global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int64_t* __restrict__ offs, int cw_stride,
+__global__ void ORD_BOUNDS k_order_winners(SensorDev sp, const int64_t* __restrict__ offs, int cw_stride,
                                                           const uint16_t* __restrict__ row, const uint16_t* __restrict__ col,
                                                           uint32_t* __restrict__ occ_bits, uint32_t* __restrict__ cont_bits,
                                                           uint32_t* __restrict__ cont_pre, uint32_t* __restrict__ cwin,
@@ -526,13 +547,28 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
     }
     auto rc = [&](unsigned r, unsigned c, int i) { visit(r * H + c, r < N && c < H, i); };   // callers only pass 0 <= i < n
     if (vec) {
+#if ORD_PREFETCH
+      // Experiment, off by default: register double buffer - the next block's row / col words are in flight while this block's
+      // eight points go through the shared-memory atomics (ncu source view: a third of the kernel's stall samples sit on the
+      // first use of these loads).  Measured slower: the eight extra registers cost a CTA per SM (or spill), and the other
+      // warps already covered that wait (issue slots 71 % busy).
+      auto whole = [&](int v) { const int i = v * 8 - mis; return v < n8 && i >= 0 && i + 8 <= n; };
+      uint4 nr = make_uint4(0, 0, 0, 0), nc = nr;
+      if (whole(tid)) { nr = ld8_u16(Ra, tid); nc = ld8_u16(Ca, tid); }
+#endif
       for (int v = tid; v < n8; v += ORD_T) {
         const int i = v * 8 - mis;
+#if ORD_PREFETCH
+        const uint4 rr = nr, cc = nc;
+        if (whole(v + ORD_T)) { nr = ld8_u16(Ra, v + ORD_T); nc = ld8_u16(Ca, v + ORD_T); }
+#endif
         if (i < 0 || i + 8 > n) {                                   // head / tail block: stay inside the frame's elements
           for (int k = max(i, 0); k < min(i + 8, n); k++) rc(R[k], C[k], k);
           continue;
         }
+#if !ORD_PREFETCH
         const uint4 rr = ld8_u16(Ra, v), cc = ld8_u16(Ca, v);
+#endif
         rc(rr.x & 0xFFFFu, cc.x & 0xFFFFu, i);     rc(rr.x >> 16, cc.x >> 16, i + 1);
         rc(rr.y & 0xFFFFu, cc.y & 0xFFFFu, i + 2); rc(rr.y >> 16, cc.y >> 16, i + 3);
         rc(rr.z & 0xFFFFu, cc.z & 0xFFFFu, i + 4); rc(rr.z >> 16, cc.z >> 16, i + 5);
@@ -580,6 +616,10 @@ __global__ void __launch_bounds__(ORD_T) k_order_winners(SensorDev sp, const int
 #ifndef SCAT_PPT
 #define SCAT_PPT 1
 #endif
+#ifndef SCAT_PRED_LOADS
+#define SCAT_PRED_LOADS 0   // measured (profiles/r2_notes.md): 1.139 us per frame with the branch, 1.160 with predicated loads
+#endif
+
 template <bool PACKED>   // PACKED: `inten` points at the u32 meta array (slot | flags); row / col / label are unused
 __global__ void __launch_bounds__(SCAT_T) k_order_scatter(SensorDev sp, Xform xf, const int64_t* __restrict__ offs, int frame0, int cw_stride,
                                                         const float* __restrict__ x, const float* __restrict__ y,
@@ -608,6 +648,24 @@ __global__ void __launch_bounds__(SCAT_T) k_order_scatter(SensorDev sp, Xform xf
   for (int u = 0; u < P; u++) {
     const int i = i0 + u * SCAT_T;
     px[u] = py[u] = pz[u] = pin[u] = 0.f; meta[u] = META_SLOT; rr[u] = cc[u] = 0xFFFFu; lbl[u] = 0; cptw[u] = 0u;
+#if SCAT_PRED_LOADS
+    // Experiment, off by default: predicated loads in ONE basic block.  With `if (i < n) { loads }` the compiler evaluates the
+    // occupancy test in front of the branch, so a thread waits for its occupancy word before it issues the point's loads (ncu
+    // source view: 23 % of the kernel's stall samples on that shift, two memory round trips in series per thread).  Taking
+    // that round trip out changes nothing (1.160 against 1.139 us per frame): the kernel is bound by the rate at which the L2
+    // takes scattered 16-byte stores, not by the latency of a thread's own chain.
+    const int64_t q = o + i - qbase;
+    ld_f32_cs_if(px[u], x + o + i, i, n); ld_f32_cs_if(py[u], y + o + i, i, n); ld_f32_cs_if(pz[u], z + o + i, i, n);
+    if (PACKED) ld_u32_cs_if(meta[u], reinterpret_cast<const uint32_t*>(inten) + o + i, i, n);
+    else {
+      ld_u16_nc_if(rr[u], row + o + i, i, n); ld_u16_nc_if(cc[u], col + o + i, i, n);
+      ld_f32_cs_if(pin[u], inten + o + i, i, n); ld_s16_cs_if(lbl[u], label + o + i, i, n);
+    }
+    ld_u32_nc_if(cptw[u], cpt_bits + (q >> 5), i, n);
+    cptw[u] >>= (q & 31);
+    occw[u] = 0xFFFFFFFFu;
+    ld_u32_nc_if(occw[u], occ_bits + fw + (i >> 5), i, sp.S);
+#else
     occw[u] = i < sp.S ? __ldg(occ_bits + fw + (i >> 5)) : 0xFFFFFFFFu;
     if (i < n) {
       px[u] = __ldcs(x + o + i); py[u] = __ldcs(y + o + i); pz[u] = __ldcs(z + o + i);
@@ -616,6 +674,7 @@ __global__ void __launch_bounds__(SCAT_T) k_order_scatter(SensorDev sp, Xform xf
       const int64_t q = o + i - qbase;
       cptw[u] = __ldg(cpt_bits + (q >> 5)) >> (q & 31);
     }
+#endif
   }
 #pragma unroll
   for (int u = 0; u < P; u++) {
@@ -1165,25 +1224,49 @@ __device__ __forceinline__ F8 ldg_f8(const float* p) {
   return r;
 }
 
+#ifndef FOLD_RAW_DESC
+#define FOLD_RAW_DESC 0   // measured (profiles/r2_notes.md): sector_mean 0.479 us per frame without, 0.476 with - the wait moves, the chain stays
+#endif
 struct FoldPos {            // a lane's position in its sector's window sequence
   unsigned cur, end;        // current / one-past-last segment (indices into the frame's bucketed segment list)
   unsigned j, hi;           // remaining slots [j, hi] of the current segment
-  unsigned nj, nhi;         // the FOLLOWING segment, fetched when the current one was entered: a position never waits for a
-                            // descriptor at a segment change (ncu: that dependent load was an exposed L2 round trip per step)
+  unsigned nj, nlen;        // the FOLLOWING segment's start and length, fetched when the current one was entered.  FOLD_RAW_DESC
+                            // (experiment, off by default) leaves them untouched until the position moves on: computing
+                            // `nj + len` at fetch time makes every segment entry wait for the two loads it has just issued
+                            // (ncu source view: 27 % of the kernel's stall samples).  Measured: no change (0.476 against 0.479 us
+                            // per frame) - the wait moves to the window loads; the fold is bound by the bytes an SM keeps in
+                            // flight (32 one-warp CTAs x one 128-byte window per lane), not by where a warp waits.
 };
 __device__ __forceinline__ bool fold_valid(const FoldPos& p) { return p.cur < p.end; }
 __device__ __forceinline__ void fold_fetch_next(FoldPos& p, const uint32_t* __restrict__ SS, const uint16_t* __restrict__ SL) {
-  if (p.cur + 1 < p.end) { p.nj = SS[p.cur + 1]; p.nhi = p.nj + SL[p.cur + 1]; }
+#if FOLD_RAW_DESC
+  // predicated loads straight into the loop-carried registers: no copy that would wait for them
+  ld_u32_nc_if(p.nj, SS + p.cur + 1, (int)(p.cur + 1), (int)p.end);
+  ld_u16_nc_if(p.nlen, SL + p.cur + 1, (int)(p.cur + 1), (int)p.end);
+#else
+  if (p.cur + 1 < p.end) { p.nj = SS[p.cur + 1]; p.nlen = SL[p.cur + 1]; }
+#endif
 }
 __device__ __forceinline__ void fold_init(FoldPos& p, unsigned first, unsigned count, const uint32_t* __restrict__ SS, const uint16_t* __restrict__ SL) {
-  p.cur = first; p.end = first + count; p.j = SS[first]; p.hi = p.j + SL[first]; p.nj = 0u; p.nhi = 0u;
+  p.cur = first; p.end = first + count; p.j = SS[first]; p.hi = p.j + SL[first]; p.nj = 0u; p.nlen = 0u;
   fold_fetch_next(p, SS, SL);
 }
 __device__ __forceinline__ void fold_advance(FoldPos& p, const uint32_t* __restrict__ SS, const uint16_t* __restrict__ SL) {
   const unsigned nj = (p.j & ~7u) + FOLD_STEP;
   if (nj <= p.hi) { p.j = nj; return; }
   p.cur++;
-  if (p.cur < p.end) { p.j = p.nj; p.hi = p.nhi; fold_fetch_next(p, SS, SL); }
+  if (p.cur < p.end) {
+#if FOLD_RAW_DESC
+    // the old descriptor is consumed by (volatile, hence ordered) moves in front of the loads that overwrite its registers:
+    // left to itself the compiler loaded into a temporary and copied it over afterwards - a copy that waits for the load
+    unsigned len;
+    asm volatile("mov.u32 %0, %2;\n\tmov.u32 %1, %3;" : "=r"(p.j), "=r"(len) : "r"(p.nj), "r"(p.nlen));
+    p.hi = p.j + len;
+#else
+    p.j = p.nj; p.hi = p.nj + p.nlen;
+#endif
+    fold_fetch_next(p, SS, SL);
+  }
 }
 
 template <bool VEC>

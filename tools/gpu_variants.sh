@@ -1,7 +1,8 @@
 #!/bin/bash
 # A/B of compile-time variants on one box:  tools/gpu_variants.sh base <name> ...  where lib/libbevgen_cuda_<name>.so was
 # built beforehand with e.g. `nvcc ... -DSCAT_T=64 -shared -o lib/libbevgen_cuda_scat64.so csrc/bevgen_capi.cu`
-# (tunables: SCAT_T, ORD_THREADS, FOLD_DIST_N, FOLD_SINGLE_BUFFER, SEG_MIN_CTAS).  "base" = the library `make` built.
+# (tunables: SCAT_T, SCAT_PPT, SCAT_PRED_LOADS, ORD_THREADS, ORD_PREFETCH, ORD_MIN_CTAS, FOLD_DIST_N, FOLD_SINGLE_BUFFER, FOLD_RAW_DESC,
+# SEG_MIN_CTAS).  "base" = the library `make` built.
 mkdir -p gpurun_out; L=point-cloud-preprocessing-tools_b200/lib
 cp $L/libbevgen_cuda.so /tmp/base.so
 for v in "$@"; do
