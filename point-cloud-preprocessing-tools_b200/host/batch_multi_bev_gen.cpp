@@ -7,7 +7,7 @@
 //   loader pool (PCD parse)  ->  per-GPU worker (pack into pinned SoA, bevgen_process_host)  ->  encode pool
 //   (bin / 25 PNG / CSV / PCD), so file encoding is off the GPU critical path.  Frames shard over GPUs by batch index;
 //   label rows are split per GPU and gathered on the host; no collective.
-// Extra trailing options (not in the reference): --gpus N, --batch B, --threads T, --no-encode, --no-pcd,
+// Extra trailing options (not in the reference): --gpus N, --workers-per-gpu W, --batch B, --threads T, --no-encode, --no-pcd,
 //   --png-level L, --json-metrics FILE, --no-packed (parse every PCD on the host instead of de-interleaving binary
 //   payloads on the GPU).
 // Compiled a second time with -DBATCH_CLOUD_MANIP as `batch_cloud_manip <keyframes_root_dir>` (BatchCloudManip.cpp:269-331,
@@ -83,6 +83,8 @@ struct ThreadPool {
 struct Options {
   std::string root, sensor;
   int gpus = 1, batch = 16, threads = 0, png_level = 1;
+  int workers_per_gpu = 1;   // host threads (each with its own context) feeding one GPU: a worker stages, calls the GPU and hands
+                             // its batch to the encode pool one after the other, so a second one overlaps those serial sections
   bool encode = true, write_pcd = true, packed = true;
   bool bvm_mode = false;     // batch_cloud_manip
   std::string json_metrics;
@@ -173,16 +175,24 @@ struct PinnedSet {     // pinned staging of one batch: SoA inputs + outputs
     if (!raw) raw_cap = 0;
     return raw != nullptr;
   }
+  // SoA inputs: only batches that were parsed on the host need them (packed batches stage their records in `raw`), and pinning
+  // memory is slow (a 16-frame HDL_64E set: 52 MB of SoA inputs, tens of milliseconds), so they are allocated on first use
+  bool ensure_soa() {
+    if (x) return true;
+    auto A = [](size_t n) { return bevgen_host_alloc(n); };
+    const size_t pts = cap_pts;
+    x = (float*)A(pts * 4); y = (float*)A(pts * 4); z = (float*)A(pts * 4); inten = (float*)A(pts * 4);
+    row = (uint16_t*)A(pts * 2); col = (uint16_t*)A(pts * 2); label = (int16_t*)A(pts * 2);
+    return x && y && z && inten && row && col && label;
+  }
   bool alloc(size_t pts, int frames, size_t S_, bool with_bvm = false) {
     release(); cap_pts = pts; cap_frames = frames; S = S_;
     auto A = [](size_t n) { return bevgen_host_alloc(n); };
-    x = (float*)A(pts * 4); y = (float*)A(pts * 4); z = (float*)A(pts * 4); inten = (float*)A(pts * 4);
-    row = (uint16_t*)A(pts * 2); col = (uint16_t*)A(pts * 2); label = (int16_t*)A(pts * 2);
     o_label = (int16_t*)A((size_t)frames * S * 2); o_winner = (uint32_t*)A(bevgen_winner_words((int64_t)pts, frames) * 4);
     o_single = (uint8_t*)A((size_t)frames * BEVGEN_GRID_SIZE * BEVGEN_GRID_SIZE);
     o_multi = (uint8_t*)A((size_t)frames * BEVGEN_NUM_LAYERS * BEVGEN_GRID_SIZE * BEVGEN_GRID_SIZE);
     if (with_bvm) o_bvm = (float*)A((size_t)frames * BEVGEN_MANIP_GRID * BEVGEN_MANIP_GRID * sizeof(float));
-    return x && y && z && inten && row && col && label && o_label && o_winner && o_single && o_multi && (!with_bvm || o_bvm);
+    return o_label && o_winner && o_single && o_multi && (!with_bvm || o_bvm);
   }
   void release_all() { release(); bevgen_host_free(raw); raw = 0; raw_cap = 0; }
   void release() {
@@ -220,6 +230,9 @@ struct Shared {
   std::atomic<long> frames_done{0};
   // CPU seconds spent per phase, summed over all pool threads (--json-metrics): where the host side of the pipeline goes
   std::atomic<long long> ns_load{0}, ns_stage{0}, ns_gpu_call{0}, ns_png{0}, ns_csv{0}, ns_bin{0}, ns_pcd{0};
+  // wall time of the GPU worker threads' own (serial) sections, summed over workers: waiting for a batch's loads, for a free
+  // pinned set, handing the encode tasks to the pool (--json-metrics "worker_ms_per_batch", with staging and the GPU call)
+  std::atomic<long long> ns_w_loads{0}, ns_w_pin{0}, ns_w_submit{0}; std::atomic<long> batches_done{0};
   // first batch back from the GPU: everything before it is start-up (pinned / device allocations, first PCD loads)
   std::atomic<bool> first_seen{false}; std::chrono::steady_clock::time_point t_first; std::atomic<long> first_frames{0};
   std::atomic<bool> failed{false};
@@ -309,6 +322,7 @@ static void encode_frame(Shared& sh, const Batch& b, int k) {
   }
 }
 
+constexpr int STAGE_THREADS = 4;
 struct GpuWorker {
   Shared& sh; int dev; bevgen_ctx* ctx = nullptr; int ctx_max_pts = 0;
   std::vector<PinnedSet> pins; std::vector<PinnedSet*> free_pins; std::mutex pin_mu; std::condition_variable pin_cv;
@@ -379,6 +393,10 @@ struct GpuWorker {
   void give_pin(PinnedSet* p) { { std::lock_guard<std::mutex> l(pin_mu); free_pins.push_back(p); } pin_cv.notify_one(); }
 
   void run() {
+    // Staging threads of this worker alone: the shared pool's threads sit in encode tasks of several milliseconds, so helpers
+    // queued there arrived late and the worker copied most of a batch by itself (measured: 11 ms per 16-frame batch, 4.5 GB/s,
+    // the largest serial section of the pipeline)
+    ThreadPool stage_pool(STAGE_THREADS);
     pins.resize(4);
     for (auto& p : pins) free_pins.push_back(&p);
     // Three batches of PCD loads are always queued ahead of the batch on the GPU: the pool is FIFO, so a batch's loads sit in
@@ -389,7 +407,7 @@ struct GpuWorker {
     while (!ahead.empty() && !sh.failed) {
       std::shared_ptr<Batch> cur = ahead.front(); ahead.pop_front();
       refill();
-      for (auto& f : cur->loads) f.get();
+      { PhaseTimer t(sh.ns_w_loads); for (auto& f : cur->loads) f.get(); }
       // the batch goes through the packed path iff every frame is an interleaved payload of one and the same layout
       cur->packed = sh.opt.packed && cur->count > 0;
       for (int k = 0; k < cur->count && cur->packed; k++) cur->packed = cur->is_packed[k] && cur->lays[k] == cur->lays[0];
@@ -405,7 +423,8 @@ struct GpuWorker {
       int max_n = 0;
       for (int k = 0; k < cur->count; k++) { offs[k + 1] = offs[k] + (int64_t)frame_n(k); max_n = std::max<int>(max_n, (int)frame_n(k)); }
       if (!ensure_ctx(max_n)) { sh.failed = true; break; }
-      PinnedSet* p = take_pin((size_t)offs[cur->count]);
+      PinnedSet* p;
+      { PhaseTimer t(sh.ns_w_pin); p = take_pin((size_t)offs[cur->count]); }
       if (sh.failed) break;
       cur->pin = p;
       { std::lock_guard<std::mutex> l(sh.print_mu); for (int k = 0; k < cur->count; k++) std::cout << "Converting file: " << cur->names[k] << "\n"; }   // :744
@@ -416,7 +435,7 @@ struct GpuWorker {
       if (cur->packed) {
         const size_t stride = (size_t)cur->lays[0].stride;
         if (!p->ensure_raw((size_t)offs[cur->count] * stride + 64)) { std::cerr << "pinned allocation failed" << std::endl; sh.failed = true; give_pin(p); break; }
-        sh.pool->parallel_for(cur->count, [&](int k) {  // staging = one copy of the file payload into pinned memory, frames in parallel
+        stage_pool.parallel_for(cur->count, [&](int k) {  // staging = one copy of the file payload into pinned memory, frames in parallel
           if (cur->npts[k]) memcpy(p->raw + (size_t)offs[k] * stride, cur->files[k].data() + cur->payload_pos[k], cur->npts[k] * stride);
         });
         const int* o = cur->lays[0].off;
@@ -425,7 +444,8 @@ struct GpuWorker {
         PhaseTimer t(sh.ns_gpu_call);
         rc = bevgen_process_packed_host(ctx, cur->count, offs.data(), p->raw, &lay, &out);
       } else {
-        sh.pool->parallel_for(cur->count, [&](int k) {    // SoA staging into pinned memory, frames in parallel
+        if (!p->ensure_soa()) { std::cerr << "pinned allocation failed" << std::endl; sh.failed = true; give_pin(p); break; }
+        stage_pool.parallel_for(cur->count, [&](int k) {    // SoA staging into pinned memory, frames in parallel
           const pcdio::Cloud& c = cur->clouds[k]; size_t o = (size_t)offs[k], n = c.size();
           if (!n) return;
           memcpy(p->x + o, c.x.data(), n * 4); memcpy(p->y + o, c.y.data(), n * 4); memcpy(p->z + o, c.z.data(), n * 4);
@@ -442,13 +462,17 @@ struct GpuWorker {
       }
       if (!sh.first_seen.exchange(true)) { sh.t_first = std::chrono::steady_clock::now(); sh.first_frames = cur->count; }
       cur->pending_encodes = cur->count;
-      for (int k = 0; k < cur->count; k++) {
-        sh.pool->submit([this, cur, k] {
-          encode_frame(sh, *cur, k);
-          sh.frames_done++;
-          if (--cur->pending_encodes == 0) give_pin(cur->pin);
-        });
+      {
+        PhaseTimer t(sh.ns_w_submit);
+        for (int k = 0; k < cur->count; k++) {
+          sh.pool->submit([this, cur, k] {
+            encode_frame(sh, *cur, k);
+            sh.frames_done++;
+            if (--cur->pending_encodes == 0) give_pin(cur->pin);
+          });
+        }
       }
+      sh.batches_done++;
     }
   }
 };
@@ -474,6 +498,7 @@ int main(int argc, char** argv) {
     else if (a == "--batch") opt.batch = atoi(val("--batch"));
     else if (a == "--threads") opt.threads = atoi(val("--threads"));
     else if (a == "--png-level") opt.png_level = atoi(val("--png-level"));
+    else if (a == "--workers-per-gpu") opt.workers_per_gpu = std::max(1, std::min(8, atoi(val("--workers-per-gpu"))));
     else if (a == "--no-encode") opt.encode = false;
     else if (a == "--no-pcd") opt.write_pcd = false;
     else if (a == "--no-packed") opt.packed = false;
@@ -513,9 +538,10 @@ int main(int argc, char** argv) {
   ThreadPool pool(opt.threads);
   sh.pool = &pool;
   sh.n_batches = (int)((sh.files.size() + opt.batch - 1) / opt.batch);
-  const int n_workers = std::max(1, std::min(opt.gpus, std::max(1, sh.n_batches)));
+  const int n_gpus = std::max(1, std::min(opt.gpus, std::max(1, sh.n_batches)));
+  const int n_workers = std::max(n_gpus, std::min(n_gpus * opt.workers_per_gpu, std::max(1, sh.n_batches)));
   std::vector<std::unique_ptr<GpuWorker>> workers;
-  for (int g = 0; g < n_workers; g++) workers.emplace_back(new GpuWorker(sh, g));
+  for (int g = 0; g < n_workers; g++) workers.emplace_back(new GpuWorker(sh, g % n_gpus));
   // contexts are also needed for the label stage even when there is no frame to process
   for (auto& w : workers) if (!w->ensure_ctx((int)sh.S)) return 1;
 
@@ -542,7 +568,7 @@ int main(int argc, char** argv) {
   if (opt.bvm_mode) {   // batch_cloud_manip has no label stage (BatchCloudManip.cpp:327-330)
     if (!opt.json_metrics.empty()) {
       std::ofstream j(opt.json_metrics);
-      j << "{\"frames\": " << sh.files.size() << ", \"gpus\": " << workers.size() << ", \"frames_wall_ms\": " << total_ms << "}\n";
+      j << "{\"frames\": " << sh.files.size() << ", \"gpus\": " << n_gpus << ", \"frames_wall_ms\": " << total_ms << "}\n";
     }
     for (auto& wk : workers) { if (wk->ctx) bevgen_destroy(wk->ctx); for (auto& p : wk->pins) p.release_all(); }
     std::cout << "Done. " << std::endl;
@@ -603,13 +629,18 @@ int main(int argc, char** argv) {
   if (!opt.json_metrics.empty()) {
     std::ofstream j(opt.json_metrics);
     const double nfr = std::max<double>(1.0, (double)sh.files.size());
-    j << "{\"frames\": " << sh.files.size() << ", \"gpus\": " << workers.size() << ", \"batch\": " << opt.batch << ", \"threads\": " << opt.threads
+    j << "{\"frames\": " << sh.files.size() << ", \"gpus\": " << n_gpus << ", \"workers\": " << workers.size() << ", \"batch\": " << opt.batch << ", \"threads\": " << opt.threads
       << ", \"encode\": " << (opt.encode ? "true" : "false") << ", \"write_pcd\": " << (opt.write_pcd ? "true" : "false")
       << ", \"frames_wall_ms\": " << total_ms << ", \"frames_per_s\": " << (total_ms > 0 ? sh.files.size() / (total_ms * 1e-3) : 0.0)
       << ", \"startup_ms\": " << startup_ms << ", \"frames_per_s_after_first_batch\": " << steady_fps
       << ", \"cpu_ms_per_frame\": {\"pcd_load\": " << sh.ns_load * 1e-6 / nfr << ", \"pinned_staging\": " << sh.ns_stage * 1e-6 / nfr
       << ", \"gpu_call_wall\": " << sh.ns_gpu_call * 1e-6 / nfr << ", \"bin\": " << sh.ns_bin * 1e-6 / nfr << ", \"png_25\": " << sh.ns_png * 1e-6 / nfr
       << ", \"csv\": " << sh.ns_csv * 1e-6 / nfr << ", \"pcd_write\": " << sh.ns_pcd * 1e-6 / nfr << "}"
+      << ", \"worker_ms_per_batch\": {\"batches\": " << sh.batches_done << ", \"wait_loads\": " << sh.ns_w_loads * 1e-6 / std::max<double>(1.0, (double)sh.batches_done)
+      << ", \"wait_pinned_set\": " << sh.ns_w_pin * 1e-6 / std::max<double>(1.0, (double)sh.batches_done)
+      << ", \"staging\": " << sh.ns_stage * 1e-6 / std::max<double>(1.0, (double)sh.batches_done)
+      << ", \"gpu_call\": " << sh.ns_gpu_call * 1e-6 / std::max<double>(1.0, (double)sh.batches_done)
+      << ", \"submit_encodes\": " << sh.ns_w_submit * 1e-6 / std::max<double>(1.0, (double)sh.batches_done) << "}"
       << ", \"keyframes\": " << K << ", \"majors\": " << M << ", \"labels_wall_ms\": " << label_ms << "}\n";
   }
   for (auto& wk : workers) { if (wk->ctx) bevgen_destroy(wk->ctx); for (auto& p : wk->pins) p.release_all(); }

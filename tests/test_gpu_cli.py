@@ -305,3 +305,17 @@ def test_cli_multi_gpu_outputs_identical(tmp_path, pkg, synth):
         assert r.returncode == 0, r.stderr[-2000:]
         digests.append(_tree_digest(root, with_png_pixels=False))      # same encoder both times: raw bytes must match too
     assert digests[0] == digests[1]
+
+
+def test_cli_two_workers_per_gpu_outputs_identical(tmp_path, pkg, synth):
+    """--workers-per-gpu 2 (two host threads, each with its own context, feeding the same GPU) writes byte-identical files."""
+    import importlib
+    pcd = importlib.import_module("pcpt_b200.pcd")
+    sensor, n = "HDL_32E", 21
+    root, _ = _baseline_folder(str(tmp_path), synth, pcd, sensor, n, first=2100)
+    digests = []
+    for extra in ([], ["--workers-per-gpu", "2"], ["--workers-per-gpu", "3", "--batch", "2"]):
+        r = subprocess.run([pkg.CLI_PATH, root, sensor, "--batch", "4"] + extra, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append(_tree_digest(root, with_png_pixels=False))
+    assert digests[0] == digests[1] == digests[2]

@@ -27,8 +27,16 @@ try:
         pcd.write(os.path.join(root, "keyframe_point_cloud", "%06d.pcd" % i), fr[i % len(fr)])
     open(os.path.join(root, "keyframe_pose.csv"), "w").write("\n".join(synth.pose_csv_lines(synth.make_poses(n, seed=5, step=9.0))) + "\n")
     print("folder of %d keyframes written in %.1f s under %s; host threads %d" % (n, time.perf_counter() - t0, base, os.cpu_count()), flush=True)
-    for tag, extra in (("all files", []), ("all files, again (page cache warm)", []), ("no pcd", ["--no-pcd"]), ("no encode, no pcd", ["--no-encode", "--no-pcd"]),
-                       ("all files, batch 32", ["--batch", "32"]), ("all files, png level 2 (zlib)", ["--png-level", "2"])):
+    cases = (("all files", []), ("all files, again (page cache warm)", []), ("all files, 2 workers per GPU", ["--workers-per-gpu", "2"]),
+             ("all files, 3 workers per GPU", ["--workers-per-gpu", "3"]), ("all files, 2 workers, batch 8", ["--workers-per-gpu", "2", "--batch", "8"]),
+             ("all files, 4 workers, batch 8", ["--workers-per-gpu", "4", "--batch", "8"]),
+             ("no pcd, 2 workers", ["--no-pcd", "--workers-per-gpu", "2"]), ("no encode, no pcd", ["--no-encode", "--no-pcd"]),
+             ("no encode, no pcd, 2 workers", ["--no-encode", "--no-pcd", "--workers-per-gpu", "2"]),
+             ("all files, batch 32", ["--batch", "32"]), ("all files, batch 32, 2 workers", ["--batch", "32", "--workers-per-gpu", "2"]))
+    if os.environ.get("CLI_PROBE_CASES"):
+        want = set(os.environ["CLI_PROBE_CASES"].split(";"))
+        cases = tuple(c for c in cases if c[0] in want)
+    for tag, extra in cases:
         mj = os.path.join(base, "m.json")
         t0 = time.perf_counter()
         r = subprocess.run([pkg.CLI_PATH, root, "HDL_64E", "--json-metrics", mj] + extra, capture_output=True, text=True, timeout=900)
