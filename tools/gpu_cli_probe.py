@@ -32,14 +32,21 @@ try:
              ("all files, 4 workers, batch 8", ["--workers-per-gpu", "4", "--batch", "8"]),
              ("no pcd, 2 workers", ["--no-pcd", "--workers-per-gpu", "2"]), ("no encode, no pcd", ["--no-encode", "--no-pcd"]),
              ("no encode, no pcd, 2 workers", ["--no-encode", "--no-pcd", "--workers-per-gpu", "2"]),
-             ("all files, batch 32", ["--batch", "32"]), ("all files, batch 32, 2 workers", ["--batch", "32", "--workers-per-gpu", "2"]))
+             ("all files, batch 32", ["--batch", "32"]), ("all files, batch 32, 2 workers", ["--batch", "32", "--workers-per-gpu", "2"]),
+             ("all files, malloc keeps its memory", ["MALLOC_MMAP_THRESHOLD_=268435456", "MALLOC_TRIM_THRESHOLD_=2147483647", "MALLOC_TOP_PAD_=67108864"]),
+             ("all files, 24 threads", ["--threads", "24"]), ("all files, 32 threads", ["--threads", "32"]),
+             ("all files, 12 threads", ["--threads", "12"]),
+             ("all files, malloc keeps its memory, 24 threads", ["MALLOC_MMAP_THRESHOLD_=268435456", "MALLOC_TRIM_THRESHOLD_=2147483647", "MALLOC_TOP_PAD_=67108864", "--threads", "24"]))
     if os.environ.get("CLI_PROBE_CASES"):
         want = set(os.environ["CLI_PROBE_CASES"].split(";"))
         cases = tuple(c for c in cases if c[0] in want)
     for tag, extra in cases:
         mj = os.path.join(base, "m.json")
         t0 = time.perf_counter()
-        r = subprocess.run([pkg.CLI_PATH, root, "HDL_64E", "--json-metrics", mj] + extra, capture_output=True, text=True, timeout=900)
+        env = dict(os.environ)
+        while extra and "=" in extra[0] and not extra[0].startswith("--"):      # leading NAME=value items: environment of this case
+            k, v = extra[0].split("=", 1); env[k] = v; extra = extra[1:]
+        r = subprocess.run([pkg.CLI_PATH, root, "HDL_64E", "--json-metrics", mj] + extra, capture_output=True, text=True, timeout=900, env=env)
         wall = time.perf_counter() - t0
         m = json.load(open(mj)) if r.returncode == 0 and os.path.exists(mj) else {"error": r.stderr[-300:]}
         print(json.dumps({"what": tag, "process_wall_s": round(wall, 3), **m}), flush=True)
