@@ -107,7 +107,9 @@ BEVGEN_API void *bevgen_host_alloc_wc(size_t bytes);
  *   _host:   `in` / `out` are HOST buffers; H2D on a copy stream, kernels on the compute stream and D2H on a third
  *            stream are pipelined over chunks of max_frames_per_batch frames; returns when `out` is complete.
  *   _device: `in` / `out` are DEVICE buffers on the context's device (offsets stays a host array); work is
- *            enqueued on the context's compute stream; call bevgen_sync() before reading `out`.            */
+ *            enqueued on the context's compute stream; call bevgen_sync() before reading `out`.
+ * Every array of `in` and `out` is required (a NULL one is refused with -1, nothing is launched); only `out->bvm` is
+ * optional, and a batch without a single point may come with NULL point arrays.                               */
 BEVGEN_API int bevgen_process_host(bevgen_ctx *ctx, int n_frames, const int64_t *offsets, const bevgen_points *in,
                         const bevgen_outputs *out);
 BEVGEN_API int bevgen_process_device(bevgen_ctx *ctx, int n_frames, const int64_t *offsets, const bevgen_points *in,
@@ -173,7 +175,7 @@ BEVGEN_API int bevgen_process_packed_host(bevgen_ctx *ctx, int n_frames, const i
 /* Asynchronous single-frame form used by pipelined callers (one frame of the loop at :727-757):
  * submit copies the frame into the context's pinned ring and enqueues H2D + kernels + D2H; collect blocks on that
  * frame's event and copies the results out.  At most `max_frames_per_batch` frames may be in flight (ring slots are
- * built on demand).     */
+ * built on demand).  The point arrays may be NULL only when n_in == 0; collect's output pointers may each be NULL. */
 BEVGEN_API int bevgen_submit(bevgen_ctx *ctx, int frame_id, int n_in, const float *x, const float *y, const float *z,
                   const float *intensity, const uint16_t *row, const uint16_t *col, const int16_t *label);
 BEVGEN_API int bevgen_collect(bevgen_ctx *ctx, int frame_id, int16_t *label_out, uint32_t *winner_bits /* (n_in+31)/32 words */,
