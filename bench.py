@@ -245,6 +245,22 @@ def cli_numbers(pkg, synth, O, args, n_cli=100, n_ref=12):
                 continue
             m = json.load(open(mj)) if os.path.exists(mj) else {}
             out[tag] = {"frames": n_cli, "process_wall_s": wall, "frames_per_s_process": n_cli / wall, "metrics": m}
+        # the same with the folder grown to n_long keyframes: context creation and the pinned staging sets (tens of milliseconds each)
+        # are most of a 100-keyframe run; this is the rate a long folder sees
+        n_long = 600
+        try:
+            for i in range(n_cli, n_long):
+                pcd.write(os.path.join(root, "keyframe_point_cloud", "%06d.pcd" % i), fr[i % len(fr)])
+            open(os.path.join(root, "keyframe_pose.csv"), "w").write("\n".join(synth.pose_csv_lines(synth.make_poses(n_long, seed=5, step=9.0))) + "\n")
+            mj = os.path.join(base, "long.json")
+            t0 = time.perf_counter()
+            r = subprocess.run([pkg.CLI_PATH, root, args.sensor, "--json-metrics", mj], capture_output=True, text=True, timeout=900)
+            wall = time.perf_counter() - t0
+            out["all_files_%d_keyframes" % n_long] = ({"error": r.stderr[-300:]} if r.returncode != 0 else
+                                                      {"frames": n_long, "process_wall_s": wall, "frames_per_s_process": n_long / wall,
+                                                       "metrics": json.load(open(mj)) if os.path.exists(mj) else {}})
+        except Exception as e:    # e.g. a small /dev/shm: this leg must never take the bench line down
+            out["all_files_%d_keyframes" % n_long] = {"error": repr(e)}
         if O.ref_bevgen_lib() is not None:
             rroot = os.path.join(base, "ref"); os.makedirs(os.path.join(rroot, "keyframe_point_cloud"))
             for i in range(n_ref):
