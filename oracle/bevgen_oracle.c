@@ -14,21 +14,30 @@
  *     BatchMultiBevGen.cpp:575-636  getKeyFrameLabel
  *     src/Utility.cpp:72-124        parseSensorType / getSensorParams
  *     CloudManip.cpp:79-109,119-128 saveAsMat / rigid transform (pcl::transformPointCloud)
- *   widened rows, same status ("parity unpinned": no reference tests exist for them either):
+ *   widened rows:
  *     BatchCloudManip.cpp:201-226                saveAsMat with the label filter (oracle_bvm)
+ *     TopPartRegistration.cpp:79-141             extractTopAndFlatten (oracle_top_flatten)
  *     MulranPointCloudSelect.cpp:112-126         row / col projection (oracle_project_mulran)
  *     OxfordPointCloudSelect.cpp:201-219         row / col projection (oracle_project_oxford)
  *     KittiPointCloudSelect.cpp:188-243          ring detection + column (oracle_project_kitti)
- *     TopPartRegistration.cpp:79-141             extractTopAndFlatten (oracle_top_flatten)
  *
- * PARITY PIN STATUS: the reference ships no tests, golden vectors or fixtures for this path and its
- * translation unit cannot be compiled here (needs PCL, OpenCV C++, Eigen, Boost, VTK — all absent), so
- * the BEV/ground part of this oracle is "PARITY UNPINNED" by reference artefacts.  It is pinned instead
- * by (i) the hand-derived known-answer tests in tests/test_oracle_kat.py (one per quirk of SURVEY §8a.1),
- * (ii) an independent line-by-line Python restatement (oracle/bevgen_oracle_py.py) that must agree bit for
- * bit, and (iii) cv2 (OpenCV 4.13 wheel) for cv::divide / float->u8 semantics.  The label stage IS pinned
- * against the reference's own vendored nanoflann KD-tree, compiled in place into oracle/_ref/
- * (oracle/nanoflann_shim.cpp, tests/test_oracle_labels_ref.py, tests/golden/labels_*.npz).
+ * PARITY PIN STATUS.  The reference ships no tests, golden vectors or fixtures, and its own build system cannot run
+ * here (PCL, OpenCV C++, Eigen, Boost, VTK are absent).  PINNED TO THE REFERENCE'S OWN SOURCE TEXT all the same: its
+ * translation units compile UNMODIFIED, where they lie under /root/reference, against the stand-in headers of
+ * oracle/stub/ (recipe oracle/Makefile, target `ref`; shims oracle/ref_*_shim.cpp; outputs oracle/_ref/, git-ignored):
+ *     libbevgen_ref.so / _dbl.so   BatchMultiBevGen.cpp + src/Utility.cpp   order, ground, both BEVs, poses, labels, main()
+ *     libcloudmanip_ref.so         CloudManip.cpp                           saveAsMat, the tool's main()
+ *     libbatchcloudmanip_ref.so    BatchCloudManip.cpp                      oracle_bvm
+ *     libtoppart_ref.so            TopPartRegistration.cpp                  oracle_top_flatten
+ *     libnanoflann_ref.so          include/nanoflann.hpp                    the KD-tree of the label stage
+ * tests/test_reference_source_pin.py + tests/test_oracle_labels_ref.py hold every function above to those builds bit
+ * for bit (both overload sets of the unqualified atan2 / sqrt at :173); tests/golden/make_*_golden.py generate from them
+ * the vectors the GPU box (no /root/reference) checks oracle and CUDA against (tests/test_golden_vectors.py).
+ * Still "PARITY UNPINNED" by reference artefacts: the three projection restatements (oracle_project_*): the extractor
+ * translation units are not compiled (file formats, pose interpolation and viewers around ten lines of arithmetic);
+ * they rest on known-answer tests (tests/test_oracle_kat.py) and the glibc atan2f / atan2 they call.
+ * Also kept: one hand-derived known-answer test per quirk of SURVEY §8a.1, and an independent line-by-line Python
+ * restatement (oracle/bevgen_oracle_py.py) that must agree bit for bit (tests/test_oracle_cross.py).
  *
  * Third-party semantics restated (not under /root/reference, versions unpinned by the reference):
  *   PCL  PointCloud::resize value-initialises (all-zero records);  transformPointCloud (PCL >= 1.9, SSE2

@@ -368,6 +368,22 @@ def ref_save_as_mat(x, y, z, csv_path, interval=1.0):
     return m.reshape(201, 201)
 
 
+def ref_top_flatten(x, y, z, label):
+    """extractTopAndFlatten of the reference's own TopPartRegistration.cpp (:79-141) -> (out_x, out_y); None if oracle/_ref lacks it."""
+    L = _ref_so("libtoppart_ref.so")
+    if L is None:
+        return None
+    x, px = _f(x); y, py = _f(y); z, pz = _f(z)
+    label = np.ascontiguousarray(label, np.int16)
+    n = len(x)
+    ox = np.empty(max(n, 1), np.float32); oy = np.empty(max(n, 1), np.float32)
+    L.ref_extract_top_and_flatten.restype = C.c_int64
+    m = L.ref_extract_top_and_flatten(C.c_int64(n), px, py, pz, _p(label, C.c_int16), _p(ox, C.c_float), _p(oy, C.c_float), C.c_int64(max(n, 1)))
+    if m < 0:
+        raise RuntimeError("ref_extract_top_and_flatten: an output z is not 0")
+    return ox[:m].copy(), oy[:m].copy()
+
+
 def ref_cloud_manip_matrix(tx, ty, tz, theta_deg, x, y, z):
     """(rt[12], x', y', z'): the Affine3f of CloudManip.cpp:119-126 and pcl::transformPointCloud, as oracle/stub restates Eigen / PCL."""
     L = _ref_so("libcloudmanip_ref.so")

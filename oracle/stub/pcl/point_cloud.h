@@ -6,6 +6,9 @@
 #include <vector>
 #include <Eigen/Core>
 
+// PCL 1.10's Ptr types are boost::shared_ptr and the reference names that type directly (TopPartRegistration.cpp:364)
+namespace boost { using std::shared_ptr; using std::make_shared; }
+
 namespace pcl {
 template <class PointT>
 class PointCloud {
@@ -21,6 +24,8 @@ class PointCloud {
     if (width * height != n) { width = static_cast<std::uint32_t>(n); height = 1; }
   }
   void clear() { points.clear(); width = height = 0; }
+  void reserve(std::size_t n) { points.reserve(n); }
+  void push_back(const PointT& p) { points.push_back(p); width = static_cast<std::uint32_t>(points.size()); height = 1; }   // PCL 1.10 point_cloud.h:548-553
   PointT& operator[](std::size_t i) { return points[i]; }
   const PointT& operator[](std::size_t i) const { return points[i]; }
 };

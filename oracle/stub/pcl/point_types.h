@@ -20,11 +20,35 @@
 #include <tuple>
 #include <unistd.h>
 
+namespace pcl { namespace stub {
+// what getArray3fMap() / getNormalVector3fMap() return in PCL (an Eigen::Map over three floats): assignment copies x, y, z
+struct Map3f {
+  float* p;
+  Map3f& operator=(const Map3f& o) { p[0] = o.p[0]; p[1] = o.p[1]; p[2] = o.p[2]; return *this; }
+};
+} }
 #define PCL_ADD_POINT4D \
-  union EIGEN_ALIGN16 { float data[4]; struct { float x; float y; float z; }; };
+  union EIGEN_ALIGN16 { float data[4]; struct { float x; float y; float z; }; }; \
+  inline ::pcl::stub::Map3f getArray3fMap() { return ::pcl::stub::Map3f{data}; }
 
 namespace pcl {
-struct Normal { float normal_x, normal_y, normal_z, curvature; };
+struct Normal {
+  union EIGEN_ALIGN16 { float data_n[4]; struct { float normal_x, normal_y, normal_z; }; };
+  float curvature;
+  Normal() : curvature(0.f) { data_n[0] = data_n[1] = data_n[2] = data_n[3] = 0.f; }
+  inline stub::Map3f getNormalVector3fMap() { return stub::Map3f{data_n}; }
+};
+struct PointXYZ {                      // pcl/impl/point_types.hpp: x = y = z = 0, data[3] = 1
+  PCL_ADD_POINT4D
+  PointXYZ() { data[0] = data[1] = data[2] = 0.f; data[3] = 1.f; }
+};
+struct PointNormal {
+  PCL_ADD_POINT4D
+  union EIGEN_ALIGN16 { float data_n[4]; struct { float normal_x, normal_y, normal_z; }; };
+  float curvature;
+  PointNormal() : curvature(0.f) { data[0] = data[1] = data[2] = 0.f; data[3] = 1.f; data_n[0] = data_n[1] = data_n[2] = data_n[3] = 0.f; }
+  inline stub::Map3f getNormalVector3fMap() { return stub::Map3f{data_n}; }
+};
 namespace stub {
 struct Field { std::string name; std::size_t offset; std::size_t size; char type; };
 template <class T> struct pcd_type;

@@ -20,7 +20,7 @@
 using std::cerr; using std::cin; using std::cout; using std::endl; using std::ends; using std::ios; using std::istream; using std::ostream;
 
 namespace pcl { namespace visualization {
-enum RenderingProperties { PCL_VISUALIZER_POINT_SIZE = 0 };
+enum RenderingProperties { PCL_VISUALIZER_POINT_SIZE = 0, PCL_VISUALIZER_COLOR = 4 };
 template <class PointT> struct PointCloudColorHandlerCustom {
   PointCloudColorHandlerCustom(const typename PointCloud<PointT>::Ptr&, double, double, double) {}
 };
@@ -30,9 +30,14 @@ struct PCLVisualizer {
   template <class PointT, class H> bool addPointCloud(const typename PointCloud<PointT>::Ptr&, const H&, const std::string&) { return true; }
   template <class C, class H> bool addPointCloud(const C&, const H&, const std::string&) { return true; }
   void addCoordinateSystem(double, const std::string&, int) {}
-  void setBackgroundColor(double, double, double, int) {}
+  void setBackgroundColor(double, double, double, int = 0) {}
   bool setPointCloudRenderingProperties(int, double, const std::string&) { return true; }
+  // TopPartRegistration.cpp:365-374 (its viewer is out of scope as well: compiled, never run)
+  template <class PointT> bool addPointCloud(const typename PointCloud<PointT>::Ptr&, const std::string&) { return true; }
+  bool setPointCloudRenderingProperties(int, double, double, double, const std::string&) { return true; }
+  template <class PointT, class PointNT> bool addPointCloudNormals(const typename PointCloud<PointT>::Ptr&, const typename PointCloud<PointNT>::Ptr&,
+                                                                    int, float, const std::string&) { return true; }
   bool wasStopped() const { return true; }
-  void spinOnce() {}
+  void spinOnce(int = 1) {}
 };
 } }

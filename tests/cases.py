@@ -111,3 +111,27 @@ def digest(a):
     if a.dtype == np.float32:                       # NaN payloads are not part of the contract
         a = np.where(np.isnan(a), np.float32(np.nan), a).view(np.uint32)
     return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def top_flatten_cases(O, synth):
+    """Inputs of extractTopAndFlatten: a real ground-removed keyframe (what non_ground_point_cloud/*.pcd holds), wide random
+    clouds with distinct heights, the 20-point threshold, the cell borders, an empty cloud.  The reference sorts a cell's
+    points with std::sort, whose order of EQUAL heights is unspecified, so every case but the last keeps heights distinct."""
+    sp = O.sensor("HDL_64E")
+    f = synth.make_frame("HDL_64E", 77)
+    oc = O.order(sp, *[f[k] for k, _ in FIELD_TYPES])
+    lab = O.mark_ground(sp, oc)[0]
+    zz = oc["z"].copy(); zz += np.arange(len(zz), dtype=np.float32) * np.float32(1e-7)      # break the (many) equal heights of empty slots
+    out = [("keyframe", oc["x"], oc["y"], zz.astype(np.float32), lab)]
+    rng = np.random.default_rng(21)
+    for n, spread in ((300_007, 130.0), (5_003, 60.0), (977, 12.0)):
+        z = rng.permutation(n).astype(np.float32) * np.float32(0.001) - np.float32(3.0)      # distinct
+        out.append(("random %d" % n, rng.uniform(-spread, spread, n).astype(np.float32), rng.uniform(-spread, spread, n).astype(np.float32),
+                    z, rng.integers(-2, 3, n).astype(np.int16)))
+    # exactly 19 / 20 / 22 / 23 points in a cell (:124 threshold, :123 round(0.2 * n): 4, 4, 5), cell borders at +-10 m (:104-105 round)
+    xs, ys, zs = [], [], []
+    for cx, cnt in ((-95.0, 19), (-75.0, 20), (-55.0, 22), (-35.0, 23), (9.999, 30), (10.0, 30), (10.001, 30), (-100.0, 25), (99.999, 25), (100.0, 25)):
+        xs += [cx] * cnt; ys += [5.0] * cnt; zs += list(np.arange(cnt) * 0.5 + len(zs))
+    out.append(("thresholds", np.array(xs, np.float32), np.array(ys, np.float32), np.array(zs, np.float32), np.ones(len(xs), np.int16)))
+    out.append(("empty", np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros(0, np.int16)))
+    return out

@@ -74,3 +74,38 @@ def test_cuda_labels_match_reference_generated_vectors(pkg, synth):
             assert cases.digest(np.concatenate(parts)) == gold["labels"], (K, seed)
     finally:
         g.close()
+
+
+# ---- extractTopAndFlatten: vectors generated from TopPartRegistration.cpp itself -------------------------
+TOP = np.load(os.path.join(HERE, "golden", "top_flatten_golden.npz"))
+
+
+def _check_top(name, got_x, got_y, what):
+    key = name.replace(" ", "_")
+    gx, gy = np.asarray(got_x, np.float32), np.asarray(got_y, np.float32)
+    assert len(gx) == int(TOP[key + ":n"]), (what, name, len(gx), int(TOP[key + ":n"]))
+    if key + ":x" in TOP.files:
+        assert np.array_equal(gx.view(np.uint32), TOP[key + ":x"].view(np.uint32)), (what, name, "x")
+        assert np.array_equal(gy.view(np.uint32), TOP[key + ":y"].view(np.uint32)), (what, name, "y")
+    assert cases.digest(np.concatenate([gx, gy])) == str(TOP[key + ":sha256"]), (what, name)
+
+
+def test_oracle_top_flatten_matches_reference_generated_vectors(O, synth):
+    names = []
+    for name, x, y, z, lab in cases.top_flatten_cases(O, synth):
+        ox, oy, _ = O.top_flatten(x, y, z, lab)
+        _check_top(name, ox, oy, "oracle")
+        names.append(name.replace(" ", "_"))
+    assert sorted(k[:-2] for k in TOP.files if k.endswith(":n")) == sorted(names)
+
+
+@pytest.mark.gpu
+def test_cuda_top_flatten_matches_reference_generated_vectors(pkg, synth, O):
+    g = pkg.BevGen("HDL_64E", device=0, max_frames_per_batch=2)
+    try:
+        for name, x, y, z, lab in cases.top_flatten_cases(O, synth):
+            gx, gy, gi = g.top_flatten(x, y, z, lab)
+            _check_top(name, gx, gy, "CUDA")
+            assert np.array_equal(x[gi].view(np.uint32), np.asarray(gx, np.float32).view(np.uint32)), name
+    finally:
+        g.close()

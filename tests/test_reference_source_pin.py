@@ -263,3 +263,41 @@ def test_batch_cloud_manip_frame(R, synth, tmp_path):
         want = R.bvm(oc, olab)
         assert np.array_equal(m.view(np.uint32), want.view(np.uint32)) and (want > 0).sum() > 200
         assert open(tmp_path / ("b%d.csv" % idx)).read() == "\n".join(", ".join("%.4g" % v for v in row) for row in want) + "\n"
+
+
+def test_extract_top_and_flatten(R, synth):
+    """the oracle's extractTopAndFlatten == TopPartRegistration.cpp:79-141 compiled from the reference's own source
+    (oracle/_ref/libtoppart_ref.so, oracle/ref_top_part_shim.cpp).  With equal heights in one cell only the multiset of a cell's
+    picks is defined (std::sort), which the last block checks."""
+    if R.ref_top_flatten(np.zeros(1, np.float32), np.zeros(1, np.float32), np.zeros(1, np.float32), np.ones(1, np.int16)) is None:
+        pytest.skip("oracle/_ref/libtoppart_ref.so not built")
+    sizes = {}
+    for name, x, y, z, lab in cases.top_flatten_cases(R, synth):
+        rx, ry = R.ref_top_flatten(x, y, z, lab)
+        ox, oy, oi = R.top_flatten(x, y, z, lab)
+        assert len(rx) == len(ox), (name, len(rx), len(ox))
+        assert np.array_equal(rx.view(np.uint32), ox.view(np.uint32)) and np.array_equal(ry.view(np.uint32), oy.view(np.uint32)), name
+        assert np.array_equal(x[oi].view(np.uint32), ox.view(np.uint32)), name
+        sizes[name] = len(ox)
+    assert sizes["keyframe"] > 1000 and sizes["random 300007"] > 10000 and sizes["empty"] == 0
+    # cells along x: -95 and -100 share cell 0 (19 + 25 = 44 points -> round(8.8) = 9); 20 -> 4; 22 -> round(4.4) = 4; 23 -> round(4.6) = 5;
+    # 9.999 -> cell 5 (30 -> 6); 10.0 (5.5 rounds away from zero) and 10.001 -> cell 6 (60 -> 12); 99.999 and 100 -> cell 10: outside
+    assert sizes["thresholds"] == 9 + 4 + 4 + 5 + 6 + 12, sizes
+    # ties: quantised heights - the selected heights per cell agree as multisets, and the count is exact
+    rng = np.random.default_rng(5)
+    n = 50_000
+    x = rng.uniform(-100, 100, n).astype(np.float32); y = rng.uniform(-100, 100, n).astype(np.float32)
+    z = (rng.integers(-8, 40, n) * 0.25).astype(np.float32); lab = np.ones(n, np.int16)
+    rx, ry = R.ref_top_flatten(x, y, z, lab)
+    ox, oy, oi = R.top_flatten(x, y, z, lab)
+    assert len(rx) == len(ox)
+    zmap = {}
+    for xi, yi, zi in zip(x.tolist(), y.tolist(), z.tolist()):
+        zmap.setdefault((xi, yi), []).append(zi)
+    cell = lambda a, b: (int(np.round(np.float32(a + np.float32(100)) / np.float32(20))), int(np.round(np.float32(b + np.float32(100)) / np.float32(20))))
+    def per_cell(px, py):
+        d = {}
+        for a, b in zip(px.tolist(), py.tolist()):
+            d.setdefault(cell(a, b), []).append(max(zmap[(a, b)]))
+        return {k: sorted(v) for k, v in d.items()}
+    assert per_cell(rx, ry) == per_cell(ox, oy)
