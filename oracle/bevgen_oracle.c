@@ -29,13 +29,13 @@
  *     libcloudmanip_ref.so         CloudManip.cpp                           saveAsMat, the tool's main()
  *     libbatchcloudmanip_ref.so    BatchCloudManip.cpp                      oracle_bvm
  *     libtoppart_ref.so            TopPartRegistration.cpp                  oracle_top_flatten
+ *     lib{mulran,oxford,kitti}select_ref.so / _dbl.so   {Mulran,Oxford,Kitti}PointCloudSelect.cpp: extractPointCloud, run on scan
+ *                                  files in the datasets' layouts            oracle_project_mulran / _oxford / _kitti
  *     libnanoflann_ref.so          include/nanoflann.hpp                    the KD-tree of the label stage
  * tests/test_reference_source_pin.py + tests/test_oracle_labels_ref.py hold every function above to those builds bit
- * for bit (both overload sets of the unqualified atan2 / sqrt at :173); tests/golden/make_*_golden.py generate from them
+ * for bit (both overload sets of the unqualified atan2 / sqrt / round); tests/golden/make_*_golden.py generate from them
  * the vectors the GPU box (no /root/reference) checks oracle and CUDA against (tests/test_golden_vectors.py).
- * Still "PARITY UNPINNED" by reference artefacts: the three projection restatements (oracle_project_*): the extractor
- * translation units are not compiled (file formats, pose interpolation and viewers around ten lines of arithmetic);
- * they rest on known-answer tests (tests/test_oracle_kat.py) and the glibc atan2f / atan2 they call.
+ * No function of this file is left "parity unpinned".
  * Also kept: one hand-derived known-answer test per quirk of SURVEY §8a.1, and an independent line-by-line Python
  * restatement (oracle/bevgen_oracle_py.py) that must agree bit for bit (tests/test_oracle_cross.py).
  *

@@ -182,27 +182,27 @@ def bvm(oc, label):
     return m.reshape(201, 201)
 
 
-def project_mulran(x, y):
+def project_mulran(x, y, double_libm=False):
     """MulranPointCloudSelect.cpp:112-126 -> (row, col)."""
     x, px = _f(x); y, py = _f(y)
     row = np.empty(len(x), np.uint16); col = np.empty(len(x), np.uint16)
-    lib().oracle_project_mulran(C.c_int64(len(x)), px, py, _p(row, C.c_uint16), _p(col, C.c_uint16))
+    lib(double_libm).oracle_project_mulran(C.c_int64(len(x)), px, py, _p(row, C.c_uint16), _p(col, C.c_uint16))
     return row, col
 
 
-def project_kitti(x, y):
+def project_kitti(x, y, double_libm=False):
     """KittiPointCloudSelect.cpp:188-243 -> (row, col); 0xFFFF = not placed."""
     x, px = _f(x); y, py = _f(y)
     row = np.empty(len(x), np.uint16); col = np.empty(len(x), np.uint16)
-    lib().oracle_project_kitti(C.c_int64(len(x)), px, py, _p(row, C.c_uint16), _p(col, C.c_uint16))
+    lib(double_libm).oracle_project_kitti(C.c_int64(len(x)), px, py, _p(row, C.c_uint16), _p(col, C.c_uint16))
     return row, col
 
 
-def project_oxford(x, y, z):
+def project_oxford(x, y, z, double_libm=False):
     """OxfordPointCloudSelect.cpp:201-219 -> (x_negated, z_negated, row, col)."""
     x = np.array(x, np.float32); z = np.array(z, np.float32); y, py = _f(y)
     row = np.empty(len(x), np.uint16); col = np.empty(len(x), np.uint16)
-    lib().oracle_project_oxford(C.c_int64(len(x)), _p(x, C.c_float), py, _p(z, C.c_float), _p(row, C.c_uint16), _p(col, C.c_uint16))
+    lib(double_libm).oracle_project_oxford(C.c_int64(len(x)), _p(x, C.c_float), py, _p(z, C.c_float), _p(row, C.c_uint16), _p(col, C.c_uint16))
     return x, z, row, col
 
 
@@ -382,6 +382,30 @@ def ref_top_flatten(x, y, z, label):
     if m < 0:
         raise RuntimeError("ref_extract_top_and_flatten: an output z is not 0")
     return ox[:m].copy(), oy[:m].copy()
+
+
+_EXTRACTOR_SCAN = {"mulran": "sensor_data/Ouster/%010d.bin", "oxford": "velodyne_left/%010d.bin", "kitti": "velodyne/%06d.bin"}
+
+
+def ref_extract_point_cloud(dataset, root, x, y, z, intensity, timestamp=1234567, double_libm=False):
+    """extractPointCloud of the reference's own {Mulran,Oxford,Kitti}PointCloudSelect.cpp on a scan file written under `root` in that
+    dataset's layout (MulRan / KITTI: x y z intensity per point; Oxford: all x, all y, all z, all intensities) -> dict of the
+    returned cloud's fields; None if oracle/_ref lacks the build."""
+    L = _ref_so("lib%sselect_ref%s.so" % (dataset, "_dbl" if double_libm else ""))
+    if L is None:
+        return None
+    pts = [np.ascontiguousarray(a, np.float32) for a in (x, y, z, intensity)]
+    path = os.path.join(root, _EXTRACTOR_SCAN[dataset] % timestamp)
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    (np.stack(pts, 0) if dataset == "oxford" else np.stack(pts, 1)).tofile(path)
+    cap = max(len(pts[0]) + 1, 64 * 2083)
+    out = {k: np.zeros(cap, t) for k, t in (("x", np.float32), ("y", np.float32), ("z", np.float32), ("intensity", np.float32),
+                                            ("row", np.uint16), ("col", np.uint16), ("label", np.int16))}
+    L.ref_extract_point_cloud.restype = C.c_int64
+    n = L.ref_extract_point_cloud(str(root).encode(), C.c_int64(timestamp), C.c_int64(cap), *[_p(out[k], t) for k, t in (
+        ("x", C.c_float), ("y", C.c_float), ("z", C.c_float), ("intensity", C.c_float), ("row", C.c_uint16), ("col", C.c_uint16), ("label", C.c_int16))])
+    assert 0 <= n <= cap, n
+    return {k: v[:n] for k, v in out.items()}
 
 
 def ref_cloud_manip_matrix(tx, ty, tz, theta_deg, x, y, z):

@@ -5,7 +5,10 @@
 //     atan2 / sqrt / round into the global namespace, which decides how BatchMultiBevGen.cpp:173 binds
 //     (-DSTUB_NO_MATH_H builds the other possibility).  See ../README.md.
 #pragma once
+#include <fstream>
+#include <iomanip>
 #include <iostream>
+#include <sstream>
 #include <string>
 #include <pcl/point_cloud.h>
 #ifndef STUB_NO_MATH_H
@@ -16,8 +19,10 @@
 #define M_PI 3.14159265358979323846
 #endif
 #endif
-// vtkIOStream.h's export list (BatchCloudManip.cpp:324 writes bare `endl`)
+// vtkIOStream.h's export list (BatchCloudManip.cpp:324 writes bare `endl`, MulranPointCloudSelect.cpp:105-106 bare `ifstream`)
 using std::cerr; using std::cin; using std::cout; using std::endl; using std::ends; using std::ios; using std::istream; using std::ostream;
+using std::fstream; using std::ifstream; using std::ofstream; using std::istringstream; using std::ostringstream; using std::stringstream;
+using std::dec; using std::hex; using std::setfill; using std::setprecision; using std::setw;
 
 namespace pcl { namespace visualization {
 enum RenderingProperties { PCL_VISUALIZER_POINT_SIZE = 0, PCL_VISUALIZER_COLOR = 4 };

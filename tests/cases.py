@@ -135,3 +135,43 @@ def top_flatten_cases(O, synth):
     out.append(("thresholds", np.array(xs, np.float32), np.array(ys, np.float32), np.array(zs, np.float32), np.ones(len(xs), np.int16)))
     out.append(("empty", np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros(0, np.int16)))
     return out
+
+
+KITTI_SCANS = [(0, {}), (1, dict(start_negative=True)), (2, dict(n_rings=70, short_rings=(0, 1, 33))), (3, dict(n_rings=3, jitter=False))]
+KITTI_H = 2083                                      # KittiPointCloudSelect.cpp:148-149
+PROJECTION_SPECIALS = [0.0, -0.0, 1.0, -1.0, 1e-30, -1e-30, 1e30, np.inf, -np.inf, np.nan, 1e-7, -1e-7]
+
+
+def projection_cloud(n=300_001, seed=11):
+    """The cloud of test_projection_step_bit_exact: normal coordinates with every pair of special values (zeros of both signs,
+    axis points, huge / tiny / non-finite) in the first 144 points."""
+    rng = np.random.default_rng(seed)
+    x = rng.normal(0, 30, n).astype(np.float32); y = rng.normal(0, 30, n).astype(np.float32); z = rng.normal(-1, 3, n).astype(np.float32)
+    sp = PROJECTION_SPECIALS
+    k = 0
+    for a in sp:
+        for b in sp:
+            x[k], y[k], z[k] = a, b, sp[(k * 7) % len(sp)]; k += 1
+    return x, y, z
+
+
+def kitti_structured(x, y, z, row, col):
+    """The structured cloud KittiPointCloudSelect.cpp:206-243 returns, rebuilt from per-point (row, col) (0xFFFF = not placed):
+    slot row * 2083 + col holds its LAST writer with intensity -1 and label -2 (:233-238), every other slot is all-zero (:207)."""
+    S = 64 * KITTI_H
+    out = {k: np.zeros(S, t) for k, t in (("x", np.float32), ("y", np.float32), ("z", np.float32), ("intensity", np.float32),
+                                          ("row", np.uint16), ("col", np.uint16), ("label", np.int16))}
+    placed = np.nonzero(np.asarray(row) != 0xFFFF)[0]
+    slot = np.asarray(row)[placed].astype(np.int64) * KITTI_H + np.asarray(col)[placed]
+    last = np.full(S, -1, np.int64)
+    np.maximum.at(last, slot, placed)                # the serial loop's last writer = the largest input index
+    s = np.nonzero(last >= 0)[0]; i = last[s]
+    out["x"][s] = x[i]; out["y"][s] = y[i]; out["z"][s] = z[i]
+    out["intensity"][s] = -1; out["row"][s] = np.asarray(row)[i]; out["col"][s] = np.asarray(col)[i]; out["label"][s] = -2
+    return out
+
+
+def structured_digest(c):
+    return digest(np.concatenate([np.asarray(c[k]).view(np.uint8) if c[k].dtype != np.float32 else
+                                  np.where(np.isnan(c[k]), np.float32(np.nan), c[k]).view(np.uint8)
+                                  for k in ("x", "y", "z", "intensity", "row", "col", "label")]))

@@ -109,3 +109,56 @@ def test_cuda_top_flatten_matches_reference_generated_vectors(pkg, synth, O):
             assert np.array_equal(x[gi].view(np.uint32), np.asarray(gx, np.float32).view(np.uint32)), name
     finally:
         g.close()
+
+
+# ---- the extractors' projection step: vectors generated from {Mulran,Oxford,Kitti}PointCloudSelect.cpp themselves --
+PROJ = json.load(open(os.path.join(HERE, "golden", "projection_golden.json")))
+
+
+def _check_projection(project, kitti, what, sfx=""):
+    """project(kind, x, y, z) -> dict(row, col, x, z), the C-ABI's shape; kitti(seed) -> the scan's x, y, z."""
+    x, y, z = cases.projection_cloud()
+    g = PROJ["mulran" + sfx]; n = g["n"]
+    r = project(0, x[:n], y[:n], None)
+    assert cases.digest(r["row"]) == g["row"] and cases.digest(r["col"]) == g["col"], (what, "mulran")
+    g = PROJ["oxford" + sfx]
+    assert g["n"] == len(x)
+    r = project(1, x, y, z)
+    for k in ("row", "col", "x", "z"):
+        assert cases.digest(r[k]) == g[k], (what, "oxford", k)
+    for seed, _ in cases.KITTI_SCANS:
+        g = PROJ["kitti_%d%s" % (seed, sfx)]
+        kx, ky, kz = kitti(seed)
+        assert len(kx) == g["n"]
+        r = project(2, kx, ky, None)
+        s = cases.kitti_structured(kx, ky, kz, r["row"], r["col"])
+        assert int((s["label"] == -2).sum()) == g["written_slots"], (what, "kitti", seed)
+        assert cases.structured_digest(s) == g["structured"], (what, "kitti", seed)
+
+
+def _kitti_scans(synth):
+    kws = dict(cases.KITTI_SCANS)
+    return lambda seed: synth.make_kitti_scan(seed, **kws[seed])
+
+
+@pytest.mark.parametrize("double_libm", [False, True])
+def test_oracle_projection_matches_reference_generated_vectors(O, synth, double_libm):
+    def project(kind, x, y, z):
+        if kind == 0:
+            row, col = O.project_mulran(x, y, double_libm=double_libm)
+            return dict(row=row, col=col)
+        if kind == 1:
+            nx, nz, row, col = O.project_oxford(x, y, z, double_libm=double_libm)
+            return dict(row=row, col=col, x=nx, z=nz)
+        row, col = O.project_kitti(x, y, double_libm=double_libm)
+        return dict(row=row, col=col)
+    _check_projection(project, _kitti_scans(synth), "oracle", "_double_libm" if double_libm else "")
+
+
+@pytest.mark.gpu
+def test_cuda_projection_matches_reference_generated_vectors(pkg, synth):
+    g = pkg.BevGen("HDL_64E", device=0, max_frames_per_batch=2)
+    try:
+        _check_projection(lambda kind, x, y, z: g.project(kind, x, y, z), _kitti_scans(synth), "CUDA")
+    finally:
+        g.close()

@@ -301,3 +301,78 @@ def test_extract_top_and_flatten(R, synth):
             d.setdefault(cell(a, b), []).append(max(zmap[(a, b)]))
         return {k: sorted(v) for k, v in d.items()}
     assert per_cell(rx, ry) == per_cell(ox, oy)
+
+
+# ---- the extractors' projection step: {Mulran,Oxford,Kitti}PointCloudSelect.cpp compiled unmodified -------------
+def _extractor(R, dataset, root, x, y, z, double_libm):
+    inten = (np.arange(len(x)) % 251).astype(np.float32)
+    r = R.ref_extract_point_cloud(dataset, str(root), x, y, z, inten, double_libm=double_libm)
+    if r is None:
+        pytest.skip("oracle/_ref/lib%sselect_ref.so not built" % dataset)
+    return r, inten
+
+
+@pytest.mark.parametrize("double_libm", [False, True])
+def test_mulran_and_oxford_projection(R, tmp_path, double_libm):
+    """oracle_project_mulran / _oxford == extractPointCloud of the reference's own translation units (MulranPointCloudSelect.cpp:95-130,
+    OxfordPointCloudSelect.cpp:146-224), run on scan files in the datasets' layouts: random clouds plus zeros of both signs, axis
+    points, huge / tiny / non-finite coordinates; both overload sets of the unqualified atan2 / sqrt / round."""
+    x, y, z = cases.projection_cloud()
+    # MulRan reads at most 64 * 1024 points (:110); one below that, the read that hits end-of-file appends one more point (:111-127)
+    for n in (65_535, 64 * 1024, 70_000, 1, 0):
+        r, inten = _extractor(R, "mulran", tmp_path, x[:n], y[:n], z[:n], double_libm)
+        m = min(n, 64 * 1024)
+        assert len(r["x"]) == min(n + 1, 64 * 1024), (n, len(r["x"]))
+        row, col = R.project_mulran(x[:m], y[:m], double_libm=double_libm)
+        assert np.array_equal(r["row"][:m], row) and np.array_equal(r["col"][:m], col), n
+        assert _same_float(r["x"][:m], x[:m]) and _same_float(r["y"][:m], y[:m]) and _same_float(r["z"][:m], z[:m])
+        assert np.array_equal(r["intensity"][:m], inten[:m]) and set(r["label"][:m].tolist()) <= {-2}
+        if m:
+            assert row.max() == min(m, 64) - 1
+        if m > 60_000:
+            assert col.max() == 1024                                          # col == Horizon_SCAN is reachable (:125)
+    for n in (len(x), 1000, 0):
+        r, inten = _extractor(R, "oxford", tmp_path, x[:n], y[:n], z[:n], double_libm)
+        nx, nz, row, col = R.project_oxford(x[:n], y[:n], z[:n], double_libm=double_libm)
+        assert len(r["x"]) == n
+        assert np.array_equal(r["row"], row) and np.array_equal(r["col"], col), (n, int((r["col"] != col).sum()))
+        assert _same_float(r["x"], nx) and _same_float(r["z"], nz) and _same_float(r["y"], y[:n])       # upside-down mount: x, z negated
+        assert np.array_equal(r["intensity"], inten) and set(r["label"].tolist()) <= {-2}
+        if n > 100_000:
+            assert col.max() < 1056 and set(np.unique(row)) == set(range(32))
+
+
+@pytest.mark.parametrize("double_libm", [False, True])
+@pytest.mark.parametrize("seed,kw", cases.KITTI_SCANS)
+def test_kitti_ring_detection(R, synth, tmp_path, seed, kw, double_libm):
+    """oracle_project_kitti == extractPointCloud of KittiPointCloudSelect.cpp (:156-246): the structured 64 x 2083 cloud it returns
+    equals the one rebuilt from the oracle's per-point (row, col) - ring detection with short rings, spurious sign flips, a scan that
+    starts below 0 degrees, more than 64 rings; the last writer of a slot wins; intensity -1 / label -2 in written slots."""
+    x, y, z = synth.make_kitti_scan(seed, **kw)
+    r, _ = _extractor(R, "kitti", tmp_path, x, y, z, double_libm)
+    row, col = R.project_kitti(x, y, double_libm=double_libm)
+    want = cases.kitti_structured(x, y, z, row, col)
+    assert len(r["x"]) == 64 * cases.KITTI_H
+    for k in want:
+        assert _same_float(r[k], want[k]) if want[k].dtype == np.float32 else np.array_equal(r[k], want[k]), (k, seed)
+    assert (want["label"] == -2).sum() > 1000
+
+
+def test_kitti_full_scan_and_collisions(R, tmp_path):
+    """A scan of exactly 64 * 2083 points (the extractor's read limit, :172-173: no read past end-of-file) whose rings revisit columns:
+    later points replace earlier ones in their slot."""
+    n = 64 * cases.KITTI_H
+    k = np.arange(n)
+    ring = k // 2083
+    az = (((k % 2083) * 0.3461) % 360.0)                                      # two passes over each ring's columns: collisions
+    az = np.where(az > 180.0, az - 360.0, az) + 1e-3
+    rad = 5.0 + (k % 97) * 0.31
+    x = (rad * np.cos(np.deg2rad(az))).astype(np.float32); y = (rad * np.sin(np.deg2rad(az))).astype(np.float32)
+    z = (ring * 0.05 - 1.7).astype(np.float32)
+    r, _ = _extractor(R, "kitti", tmp_path, x, y, z, False)
+    row, col = R.project_kitti(x, y)
+    want = cases.kitti_structured(x, y, z, row, col)
+    for key in want:
+        assert _same_float(r[key], want[key]) if want[key].dtype == np.float32 else np.array_equal(r[key], want[key]), key
+    placed = row != 0xFFFF
+    assert placed.sum() > (want["label"] == -2).sum() > 1000                  # some slots were written more than once
