@@ -3,7 +3,7 @@
 frames with random ground planes / walls / dropouts / -1 markers, random unstructured frames, hot-cell frames, synthetic keyframes;
 all three sensors) through the reference's own source (oracle/_ref/libbevgen_ref.so = BatchMultiBevGen.cpp compiled unmodified)
 and through the oracle: ordered cloud, owner, ground_mat, labels, both BEVs, .bin bytes, CSV text - for both overload sets of the
-unqualified atan2 / sqrt.  gpu_fuzz.py holds CUDA to the oracle on these frames, this holds the oracle to the reference.
+unqualified atan2 / sqrt; HDL_64E frames also through BatchCloudManip.cpp's own pipeline (labels + the 201 x 201 float map).  gpu_fuzz.py holds CUDA to the oracle on these frames, this holds the oracle to the reference.
     python tests/cpu_fuzz_ref.py [n_rounds=20] [seed0=0]      -> one line per round, exits 1 on the first mismatch
 Needs oracle/_ref (built where /root/reference exists)."""
 import os
@@ -18,6 +18,8 @@ import cases  # noqa: E402
 from gpu_fuzz import scene_frame  # noqa: E402
 from test_reference_source_pin import check_frame  # noqa: E402
 
+FIELDS = ("x", "y", "z", "intensity", "row", "col", "label")
+
 
 def main():
     n_rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 20
@@ -26,6 +28,8 @@ def main():
     if O.ref_bevgen_lib() is None:
         sys.exit("oracle/_ref/libbevgen_ref.so not built")
     total = 0
+    import tempfile
+    tmp = tempfile.mkdtemp()
     for rnd in range(n_rounds):
         rng = np.random.default_rng(1000 + seed0 + rnd)                 # the frame recipe of gpu_fuzz.py, draw for draw
         sensor = ("HDL_64E", "OS1_64", "HDL_32E")[rnd % 3]
@@ -41,6 +45,12 @@ def main():
                 _, o = check_frame(O, sensor, f, what="round %d frame %d" % (rnd, i))
                 _, od = check_frame(O, sensor, f, double_libm=True, what="round %d frame %d (double libm)" % (rnd, i))
                 ground += int(((o["label"] == 0) & (o["owner"] > 0)).sum())
+                in_range = bool((f["row"] < sp.n_scan).all() and (f["col"] < sp.horizon_scan).all())   # its getOrderedCloud (:47-63) has no bounds test: out of range = a wild write
+                if sensor == "HDL_64E" and in_range:      # BatchCloudManip.cpp's own order / ground / saveAsMat with the label filter (HDL-64E constants), SURVEY 8(f)-3
+                    blab, bm = O.ref_bcm_frame(*[f[k] for k in FIELDS], out_prefix=os.path.join(tmp, "b"))
+                    assert np.array_equal(blab, o["label"]), "round %d frame %d: batch_cloud_manip labels" % (rnd, i)
+                    want = O.bvm(O.order(sp, *[f[k] for k in FIELDS]), o["label"])
+                    assert np.array_equal(bm.view(np.uint32), want.view(np.uint32)), "round %d frame %d: batch_cloud_manip map" % (rnd, i)
                 differ += int((o["label"] != od["label"]).sum())
         except AssertionError as e:
             print("round %d seed %d %s: MISMATCH %s" % (rnd, 1000 + seed0 + rnd, sensor, e), flush=True)
