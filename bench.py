@@ -143,6 +143,17 @@ def algorithmic_bytes(sensor_S, n_in_total, F):
     return n_in_total * 22 + F * (sensor_S * 2 + 50176 + 1204224)
 
 
+def workload_config(args, world, n_total, in_bytes):
+    """`config` of the bench line, the same dict in both arms (the reference arm times bounded samples of this workload: its
+    sample size is in `cpu_baseline.sample` / `sample_frames_per_step`).  n_total = points of rank 0's F tiled frames."""
+    F = args.frames
+    return {"workload": "BASELINE configs[1]: %s synthetic keyframes (~%dk pts/frame), hot loop BatchMultiBevGen.cpp:735-747"
+                        % (args.sensor, round(n_total / F / 1000)),
+            "sensor": args.sensor, "frames_per_step_per_gpu": F, "frames_per_wave": args.wave,
+            "l2_policy": "inputs larger than L2 (%.2f GB of points per step)" % (in_bytes / 1e9),
+            "parallelism": "frames sharded by index, %d process(es), no collective" % world}
+
+
 def ref_source_rate(O, args, distinct, cores, seconds):
     """frames/s of the reference's OWN source (oracle/_ref/libbevgen_ref.so = BatchMultiBevGen.cpp compiled against
     oracle/stub), one process per host core; None when the library did not travel to this box."""
@@ -169,7 +180,10 @@ def run_reference(args, rank, world):
     O, synth = load_oracle(), load_synth()
     cores = os.cpu_count() or 1
     F = args.ref_frames or 32 * cores
-    distinct = synth.make_batch(args.sensor, min(args.distinct, F))
+    full = synth.make_batch(args.sensor, args.distinct)                         # rank 0's distinct frames of the product arm
+    distinct = full if F >= args.distinct else synth.make_batch(args.sensor, F)
+    lens = np.diff(full["offsets"])
+    n_tiled = int(sum(int(lens[i % len(lens)]) for i in range(args.frames)))   # points of the product arm's args.frames tiled frames (22 B each)
     batch = tile_batch(distinct, F)
     sp = O.sensor(args.sensor)
     call = lambda: O.frames(sp, batch["offsets"], *[batch[k] for k in FIELDS], n_threads=cores)
@@ -189,8 +203,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": (F / v) * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s synthetic keyframes, hot loop BatchMultiBevGen.cpp:735-747 without file encoders" % args.sensor,
-                       "frames_per_step": F, "sensor": args.sensor},
+            "config": workload_config(args, world, n_tiled, 22 * n_tiled), "sample_frames_per_step": F,
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample,
                              "port_frames_per_s": v_port, "reference_source": rs},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -535,11 +548,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic (%d distinct seeded %s frames per rank, tiled to %d)" % (args.distinct, args.sensor, F),
-                "config": {"workload": "BASELINE configs[1]: %s synthetic keyframes (~%dk pts/frame), hot loop BatchMultiBevGen.cpp:735-747"
-                                       % (args.sensor, round(n_total / F / 1000)),
-                           "sensor": args.sensor, "frames_per_step_per_gpu": F, "frames_per_wave": args.wave,
-                           "l2_policy": "inputs larger than L2 (%.2f GB of points per step)" % (in_bytes / 1e9),
-                           "parallelism": "frames sharded by index, %d process(es), no collective" % world},
+                "config": workload_config(args, world, n_total, in_bytes),
                 "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "frames_per_step_per_gpu": Fe, "ms_per_step": e_wall / args.steps, "api": "bevgen_process_host_compact",
                         "input_staging": "pinned, write-combined" if args.wc else "pinned",

@@ -18,7 +18,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "BEV frames/sec (HDL-64E)" and d["unit"] == "frames/s"
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["value"] > 0
     assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1 and d["ms_per_step"] > 0 and d["gpu_launches"] == 0
-    assert d["config"]["workload"] and d["config"]["frames_per_step"] == 4
+    assert d["config"]["workload"].startswith("BASELINE configs[1]: HDL_64E") and d["sample_frames_per_step"] == 4
+    assert d["config"]["frames_per_step_per_gpu"] == 4440 and d["config"]["frames_per_wave"] == 2220      # the product arm's config, word for word
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
     assert cb["port_frames_per_s"] > 0
