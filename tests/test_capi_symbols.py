@@ -74,3 +74,26 @@ def test_clis_are_built_print_usage_and_have_no_cpu_fallback(tmp_path, pkg):
         root = str(tmp_path / "kf"); os.makedirs(os.path.join(root, "keyframe_point_cloud"))
         r = subprocess.run([pkg.CLI_PATH, root, "HDL_64E"], capture_output=True, text=True, timeout=60)
         assert r.returncode == 1 and "no CUDA device (there is no CPU fallback)" in r.stderr
+
+
+def test_built_library_holds_sm100a_images_of_every_kernel(pkg):
+    """The in-tree library (the one the GPU box loads) carries sm_100a machine code and nothing else - no PTX to JIT, no other
+    architecture - and every kernel DESIGN.md §4 names is in it (cuobjdump comes with the CUDA toolkit of this image)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump")
+    so = pkg.LIB_PATH
+    elfs = subprocess.run([cuobjdump, "-lelf", so], capture_output=True, text=True).stdout.split("\n")
+    elfs = [l for l in elfs if l.startswith("ELF file")]
+    assert elfs and all(l.rstrip().endswith(".sm_100a.cubin") for l in elfs), elfs
+    r = subprocess.run([cuobjdump, "-lptx", so], capture_output=True, text=True)
+    assert "No PTX file found" in r.stdout + r.stderr and "PTX file " not in r.stdout, r.stdout
+    text = subprocess.run([cuobjdump, "-elf", so], capture_output=True, text=True).stdout
+    kernels = set(re.findall(r"\.text\._ZN6bevgen\d+(k_[a-z0-9_]+?)(?:I|E)", text))
+    want = {"k_order_winners", "k_order_scatter", "k_order_claim", "k_order_fill", "k_winner_bits", "k_ground_mark", "k_seg_build", "k_seg_fold",
+            "k_sector_mean", "k_build_cnt_lut", "k_finalize_bin", "k_float_bev", "k_unpack_records", "k_project", "k_kitti_azimuth",
+            "k_kitti_rings", "k_kitti_assign", "k_select_major", "k_labels", "k_cloud_manip", "k_manip_merge", "k_top_keys", "k_rs_hist",
+            "k_rs_scan", "k_rs_scatter", "k_top_cells", "k_top_gather"}
+    assert want <= kernels, sorted(want - kernels)
